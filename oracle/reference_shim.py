@@ -1,0 +1,82 @@
+"""Import the *unmodified* reference modules from /root/reference (build container only).
+
+TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box; callers must check
+`available()` first.  Two shims are needed:
+  * `timm.models.layers.trunc_normal_` (timm is not installed) -> torch.nn.init.trunc_normal_
+  * `get_grid` hard-codes `.cuda()` (model/Transolver_Structured_Mesh_2D.py:189,195): on a CPU-only
+    host `torch.Tensor.cuda` is patched to identity while the model is constructed.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("TBNS_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "model", "Physics_Attention.py"))
+
+
+def _install_shims():
+    sys.dont_write_bytecode = True  # the mount is read-only
+    if "timm" not in sys.modules:
+        timm = types.ModuleType("timm")
+        models = types.ModuleType("timm.models")
+        layers = types.ModuleType("timm.models.layers")
+        layers.trunc_normal_ = torch.nn.init.trunc_normal_
+        timm.models = models
+        models.layers = layers
+        sys.modules["timm"] = timm
+        sys.modules["timm.models"] = models
+        sys.modules["timm.models.layers"] = layers
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+
+
+@contextlib.contextmanager
+def cpu_cuda_identity():
+    """Make `.cuda()` a no-op when there is no GPU (reference hard-codes it in get_grid)."""
+    if torch.cuda.is_available():
+        yield
+        return
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = orig
+
+
+def physics_attention():
+    _install_shims()
+    import importlib
+    return importlib.import_module("model.Physics_Attention")
+
+
+def transolver_2d():
+    _install_shims()
+    import importlib
+    return importlib.import_module("model.Transolver_Structured_Mesh_2D")
+
+
+def transolver_irregular():
+    _install_shims()
+    import importlib
+    return importlib.import_module("model.Transolver_Irregular_Mesh")
+
+
+def sol_2d():
+    _install_shims()
+    import importlib
+    return importlib.import_module("model.SOL_Transolver_Structured_Mesh_2D")
+
+
+def testloss():
+    _install_shims()
+    import importlib
+    return importlib.import_module("utils.testloss")

@@ -1,0 +1,84 @@
+"""CPU tests: the oracle restatement (forward and hand-derived backward) against the golden vectors
+that oracle/make_golden.py produced from the live reference modules, and against the reference itself
+when /root/reference is mounted (build container)."""
+import pytest
+import torch
+
+from oracle import physics_attention as O
+from oracle import reference_shim as ref
+
+TOL = 1e-10  # float64 restatement vs float64 reference
+
+
+def _grid(fx):
+    kw = fx["kwargs"]
+    return (kw["H"], kw["W"]) if "H" in kw else None
+
+
+@pytest.mark.parametrize("name", ["pa_structured_small.pt", "pa_structured_g64.pt", "pa_irregular_small.pt",
+                                  "pa_irregular_inner_ne_dim.pt", "pa_ckpt_ep400_block3.pt"])
+def test_pa_oracle_matches_golden(golden, name):
+    fx = golden(name)
+    out, sv = O.pa_forward(fx["inputs"][0], fx["state"], fx["kwargs"]["heads"], _grid(fx))
+    assert O.rel_l2(out, fx["out"]) < TOL
+    dx, g = O.pa_backward(fx["dout"], fx["state"], sv)
+    assert O.rel_l2(dx, fx["dinputs"][0]) < TOL
+    for k in O.PA_KEYS:
+        ref_g = fx["grads"][k]
+        if float(ref_g.abs().max()) == 0.0:
+            assert float(g[k].abs().max()) == 0.0, k
+        else:
+            assert O.rel_l2(g[k], ref_g) < 1e-9, k
+
+
+def test_temperature_clamp_gradient_is_zero_outside(golden):
+    fx = golden("pa_structured_small.pt")  # taus = 0.05, 0.1, 0.7, 7.0
+    g = fx["grads"]["temperature"].reshape(-1)
+    assert g[0] == 0 and g[3] == 0 and g[1] != 0 and g[2] != 0
+    _, sv = O.pa_forward(fx["inputs"][0], fx["state"], 4, _grid(fx))
+    _, og = O.pa_backward(fx["dout"], fx["state"], sv)
+    og = og["temperature"].reshape(-1)
+    assert og[0] == 0 and og[3] == 0
+
+
+@pytest.mark.parametrize("name", ["block_structured_mid.pt", "block_structured_last.pt", "block_irregular_last.pt"])
+def test_block_oracle_matches_golden(golden, name):
+    fx = golden(name)
+    out, sv = O.block_forward(fx["inputs"][0], fx["state"], fx["kwargs"]["num_heads"], _grid(fx))
+    assert O.rel_l2(out, fx["out"]) < TOL
+    dfx, g = O.block_backward(fx["dout"], fx["state"], sv)
+    assert O.rel_l2(dfx, fx["dinputs"][0]) < TOL
+    for k, ref_g in fx["grads"].items():
+        assert O.rel_l2(g[k], ref_g) < 1e-9, k
+
+
+def test_structured_rejects_wrong_grid(golden):
+    fx = golden("pa_structured_small.pt")
+    with pytest.raises(RuntimeError):
+        O.pa_forward(fx["inputs"][0][:, :-1], fx["state"], 4, _grid(fx))
+
+
+@pytest.mark.skipif(not ref.available(), reason="/root/reference not mounted (GPU box)")
+@pytest.mark.parametrize("structured", [True, False])
+def test_oracle_vs_live_reference_fp32(structured):
+    PA = ref.physics_attention()
+    torch.manual_seed(5)
+    if structured:
+        m = PA.Physics_Attention_Structured_Mesh_2D(64, heads=8, dim_head=8, dropout=0.0, slice_num=32, H=9, W=11)
+        x = torch.randn(2, 99, 64)
+        grid = (9, 11)
+    else:
+        m = PA.Physics_Attention_Irregular_Mesh(64, heads=4, dim_head=16, dropout=0.0, slice_num=16)
+        x = torch.randn(2, 77, 64)
+        grid = None
+    x.requires_grad_(True)
+    y = m(x)
+    dout = torch.randn_like(y)
+    y.backward(dout)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    out, sv = O.pa_forward(x.detach(), sd, m.heads, grid)
+    assert O.rel_l2(out, y) < 2e-6
+    dx, g = O.pa_backward(dout, sd, sv)
+    assert O.rel_l2(dx, x.grad) < 2e-5
+    for k, p in m.named_parameters():
+        assert O.rel_l2(g[k], p.grad) < 5e-5, k
