@@ -1,0 +1,137 @@
+/*
+ * tbns.h — C ABI of the B200-native Physics-Attention path (libtbns.so, sm_100a only).
+ *
+ * The reference (OnurBasci/TransformerBasedNavierStokeSolver) is pure PyTorch and has no FFI of its
+ * own; each entry point below replaces a span of reference Python and cites it (paths relative to
+ * the reference root).  Conventions:
+ *   - every pointer is a DEVICE pointer unless named h_*; the caller allocates all outputs,
+ *     saved-for-backward buffers and workspaces (sizes via the *_bytes helpers); the library never
+ *     frees or retains caller memory beyond the call;
+ *   - row-major, fp32 unless stated; `stream` is a cudaStream_t passed as void*; calls are
+ *     asynchronous w.r.t. the host and re-entrant;
+ *   - return 0 on success, negative error code otherwise; tbns_last_error() gives the message
+ *     (thread-local).  There is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef TBNS_H
+#define TBNS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBNS_OK 0
+#define TBNS_ERR_INVALID (-1)
+#define TBNS_ERR_CUDA (-2)
+#define TBNS_ERR_UNSUPPORTED (-3)
+
+/* operand precision of the large token-dimension contractions (projections, to_out, MLP) */
+#define TBNS_PREC_FP32 0 /* fp32 operands, fp32 FMA accumulate  (north_star "fp32 mode", <=1e-5)  */
+#define TBNS_PREC_BF16 1 /* bf16 operands, fp32 accumulate       (north_star "bf16 mode", <=2e-3) */
+
+const char* tbns_last_error(void);
+int tbns_version(void);
+/* 1 when the runtime sees an sm_100 device; compute entry points fail otherwise. */
+int tbns_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generic strided GEMM with the gathers/epilogues the path needs:  C[b] = epi(A[b] (M x K) * B[b] (K x N))
+ * Building block of every dense contraction on the path (conv-as-implicit-GEMM, Linear, deslice+to_out,
+ * all dgrad/wgrad).  See DESIGN.md §kernels.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct tbns_gemm_desc {
+  int M, N, K;
+  int batch;                    /* >=1 ; batch strides in elements                                   */
+  long long sA, sB, sC, sR, sAux;
+  const float* A; long long lda;
+  int a_kind;                   /* 0: A(m,k)=A[m*lda+k] (K contiguous) ; 1: A(m,k)=A[k*lda+m]        */
+  const float* B; long long ldb;
+  int b_kind;                   /* 0: B(k,n)=B[n*ldb+k] (K contiguous) ; 1: B(k,n)=B[k*ldb+n]        */
+  float* C; long long ldc;
+  /* 3x3/pad-1 gather on the token index of A (row-major grid, token = i*Wg + j, per batch image):
+   * 0 none; 1: a_kind 0, m = token, k = tap*Cin + ci (conv fprop / dgrad with flip=1);
+   * 2: a_kind 1, k = token, m = tap*Cin + ci (conv wgrad)                                          */
+  int conv_mode, Hg, Wg, Cin, flip;
+  const float* bias;            /* [N] or NULL                                                       */
+  const float* residual; long long ldr; /* [M,N] or NULL                                            */
+  int act;                      /* 0 none ; 1 GELU(erf), pre-activation -> aux_out if non-NULL ;
+                                   2 multiply by GELU'(aux_in[m,n])                                  */
+  float* aux_out; const float* aux_in; long long ldaux;
+  int precision;                /* TBNS_PREC_*                                                       */
+  int split_k; float* ws;       /* split_k>1: ws holds split_k*batch*M*N floats                      */
+  /* scatter==1: C is ignored; element (m=tap*Cin+ci, n) goes to (n<I ? Cx : Cfx)[(n%I)*Cin*taps + ci*taps + tap]
+   * i.e. straight into nn.Conv2d / nn.Linear weight.grad layout                                    */
+  int scatter, I, taps; float* Cx; float* Cfx;
+} tbns_gemm_desc;
+
+int tbns_gemm(const tbns_gemm_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (nn.LayerNorm(hidden_dim), eps 1e-5):
+ *   model/Transolver_Structured_Mesh_2D.py:59,63,66 and forward :70-73
+ * ------------------------------------------------------------------------------------------- */
+int tbns_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                       int rows, int C, float eps, void* stream);
+/* dx = LN'(dy) + (dres ? dres : 0); dgamma/dbeta reduced deterministically through ws
+ * (tbns_layernorm_bwd_ws_floats(C) floats). */
+size_t tbns_layernorm_bwd_ws_floats(int C);
+int tbns_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* dres, float* dx, float* dgamma, float* dbeta, float* ws, int rows, int C,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weight packing for the projections (nn.Conv2d 3x3 / nn.Linear pair in_project_x, in_project_fx:
+ * model/Physics_Attention.py:18-19, :74-75).  taps = 9 (structured) or 1 (irregular).
+ *   Wf [2I][taps*C]  : Wf[n][tap*C+ci]     = W_{x|fx}[n%I][ci][tap]    (fprop B operand, K contiguous)
+ *   Wd [C][taps*2I]  : Wd[ci][tap*2I + n]  = same element               (dgrad B operand, K contiguous)
+ *   bcat [2I]
+ * ------------------------------------------------------------------------------------------- */
+int tbns_pack_proj_weights(const float* Wx, const float* bx, const float* Wfx, const float* bfx, float* Wf, float* Wd,
+                           float* bcat, int I, int C, int taps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Slice stage (model/Physics_Attention.py:40-42 / :98-101):
+ *   w[b,n,h,g] = softmax_g((X[b,n,h,:].Ws[g,:] + bs[g]) / tau_h),  partial sums over token chunks of
+ *   s = sum_n w and Tt = sum_n w (x) F.   XF = [X | F] is [B*N, 2I].  clamp=1 clamps tau to [0.1,5].
+ *   part: [B,H,nchunk,G,D+1] with nchunk = tbns_slice_nchunk(N).
+ * ------------------------------------------------------------------------------------------- */
+int tbns_slice_nchunk(int N);
+int tbns_pa_slice_fwd(const float* XF, const float* Ws, const float* bs, const float* temperature, float* w,
+                      float* part, int B, int N, int H, int D, int G, int clamp, void* stream);
+
+/* Token stage (model/Physics_Attention.py:43-52 / :102-111) + fold of to_out into P:
+ *   reduces `part` -> s[B,H,G], Tt[B,H,G,D]; tok = Tt/(s+1e-5); q,k,v; A = softmax(q k^T D^-1/2); O = A v;
+ *   P[b,h*G+g,c] = sum_d O[b,h,g,d] * Wo[c,h*D+d].   Wo is [Cout, H*D]. */
+int tbns_pa_token_attn_fwd(const float* part, int nchunk, const float* Wq, const float* Wk, const float* Wv,
+                           const float* Wo, float* s, float* Tt, float* tok, float* q, float* k, float* v, float* A,
+                           float* O, float* P, int B, int H, int D, int G, int Cout, void* stream);
+
+/* Backward of the token stage.  dP [B,H*G,Cout] ->  dTt [B,H,G,D], ds [B,H,G], and per-(b,h) partials
+ *   dWqkv_part [B*H,3,D,D],  dWo_part [B,Cout,H*D]  (reduce over the leading dim with tbns_reduce_rows). */
+int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const float* Wk, const float* Wv, const float* Wo,
+                           const float* s, const float* tok, const float* q, const float* k, const float* v,
+                           const float* A, const float* O, float* dTt, float* ds, float* dWqkv_part, float* dWo_part,
+                           int B, int H, int D, int G, int Cout, void* stream);
+
+/* Backward of the slice stage (SURVEY §8 a-bwd): recomputes logits / softmax from XF.
+ *   dw [B,N,H*G] (deslice gradient), dTt, ds  ->  dXF [B*N,2I],
+ *   dWs_part [B*H*nchunk, G, D+1] (last column = dbs), dtau_part [B*H*nchunk]. */
+int tbns_pa_slice_bwd(const float* XF, const float* Ws, const float* bs, const float* temperature, const float* dw,
+                      const float* dTt, const float* ds, float* dXF, float* dWs_part, float* dtau_part, int B, int N,
+                      int H, int D, int G, int clamp, void* stream);
+/* dtau_part [B,H,nchunk] -> dtemperature [H], applying the clamp mask [0.1<=tau<=5] when clamp=1 */
+int tbns_pa_dtau_finish(const float* dtau_part, const float* temperature, float* dtemperature, int B, int H,
+                        int nchunk, int clamp, void* stream);
+
+/* out[j] = sum_i in[i*cols + j], i < rows (fixed order, deterministic). */
+int tbns_reduce_rows(const float* in, float* out, int rows, long long cols, void* stream);
+/* column sums of a [rows, cols] matrix (bias gradients); ws: tbns_colsum_ws_floats(cols) floats */
+size_t tbns_colsum_ws_floats(long long cols);
+int tbns_colsum(const float* in, long long ld, float* out, float* ws, int rows, int cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBNS_H */

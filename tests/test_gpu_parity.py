@@ -1,0 +1,326 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test drives the CUDA kernels through the
+C ABI (ctypes -> libtbns.so) and compares with the CPU oracle / the golden vectors produced by the live
+reference.  Tolerances are the ones BASELINE.json's north_star states:
+    fp32 mode: per-layer relative L2 <= 1e-5      bf16 mode: <= 2e-3
+Gradients are held to 1e-4 (fp32) — they pass through long fp32 reductions over all tokens."""
+import math
+
+import pytest
+import torch
+
+from oracle import physics_attention as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_OUT_TOL = 1e-5
+FP32_GRAD_TOL = 1e-4
+BF16_OUT_TOL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from transformerbasednavierstokesolver_b200 import _lib
+    assert _lib.load().tbns_device_ok() == 1, _lib.load().tbns_last_error()
+    return torch.device("cuda:0")
+
+
+def _ops():
+    from transformerbasednavierstokesolver_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------------------------------------
+# generic GEMM engine
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (200, 130, 52), (37, 5, 7), (1, 300, 33), (513, 64, 1)])
+@pytest.mark.parametrize("a_kind,b_kind", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_layouts(dev, M, N, K, a_kind, b_kind):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + a_kind * 2 + b_kind)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    Ad = (A if a_kind == 0 else A.t()).contiguous().to(dev)
+    Bd = (B.t() if b_kind == 0 else B).contiguous().to(dev)
+    C = torch.empty(M, N, device=dev)
+    ops.gemm(M=M, N=N, K=K, A=Ad, lda=Ad.shape[1], a_kind=a_kind, B=Bd, ldb=Bd.shape[1], b_kind=b_kind, C=C, ldc=N)
+    assert O.rel_l2(C.cpu(), A.double() @ B.double()) < 2e-6
+
+
+def test_gemm_batched_splitk_epilogues(dev):
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    Bt, M, N, K = 3, 70, 36, 1000
+    A = torch.randn(Bt, M, K, generator=g)
+    B = torch.randn(Bt, K, N, generator=g)
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(Bt, M, N, generator=g)
+    C = torch.empty(Bt, M, N, device=dev)
+    ops.gemm(M=M, N=N, K=K, A=A.to(dev), lda=K, a_kind=0, B=B.to(dev), ldb=N, b_kind=1, C=C, ldc=N, batch=Bt, sA=M * K, sB=K * N,
+             sC=M * N, sR=M * N, bias=bias.to(dev), residual=res.to(dev), ldr=N, split_k=5)
+    ref = A.double() @ B.double() + bias.double() + res.double()
+    assert O.rel_l2(C.cpu(), ref) < 2e-6
+    # GELU epilogue with pre-activation side output, then GELU' multiply
+    pre = torch.empty(Bt, M, N, device=dev)
+    ops.gemm(M=M, N=N, K=K, A=A.to(dev), lda=K, a_kind=0, B=B.to(dev), ldb=N, b_kind=1, C=C, ldc=N, batch=Bt, sA=M * K, sB=K * N,
+             sC=M * N, sAux=M * N, bias=bias.to(dev), act=1, aux_out=pre, ldaux=N)
+    pre_ref = (A.double() @ B.double() + bias.double()) / 1.0
+    assert O.rel_l2(pre.cpu(), pre_ref) < 2e-6
+    assert O.rel_l2(C.cpu(), O.gelu(pre_ref)) < 2e-6
+    small = (pre_ref / 30.0).float()
+    ops.gemm(M=M, N=N, K=K, A=A.to(dev), lda=K, a_kind=0, B=B.to(dev), ldb=N, b_kind=1, C=C, ldc=N, batch=Bt, sA=M * K, sB=K * N,
+             sC=M * N, sAux=M * N, act=2, aux_in=small.to(dev), ldaux=N)
+    assert O.rel_l2(C.cpu(), (A.double() @ B.double()) * O.gelu_grad(small.double())) < 2e-6
+
+
+@pytest.mark.parametrize("Bt,Hg,Wg,C,I2", [(2, 5, 7, 8, 12), (1, 9, 4, 12, 20), (1, 1, 1, 4, 4)])
+def test_gemm_conv_modes(dev, Bt, Hg, Wg, C, I2):
+    """conv fprop / dgrad / wgrad gathers against the oracle's shifted-matmul restatement"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(Bt + Hg + Wg)
+    I = I2 // 2
+    N = Hg * Wg
+    x = torch.randn(Bt, N, C, generator=g)
+    Wx = torch.randn(I, C, 3, 3, generator=g)
+    Wfx = torch.randn(I, C, 3, 3, generator=g)
+    bx, bfx = torch.randn(I, generator=g), torch.randn(I, generator=g)
+    Wf, Wd, bcat = ops.pack_proj_weights(Wx.to(dev), bx.to(dev), Wfx.to(dev), bfx.to(dev))
+    XF = torch.empty(Bt * N, I2, device=dev)
+    ops.gemm(M=Bt * N, N=I2, K=9 * C, A=x.to(dev), lda=C, a_kind=0, B=Wf, ldb=9 * C, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Hg,
+             Wg=Wg, Cin=C, bias=bcat)
+    ref = O.proj_fwd(x.double(), Wx.double(), bx.double(), Wfx.double(), bfx.double(), (Hg, Wg))
+    assert O.rel_l2(XF.cpu().reshape(Bt, N, I2), ref) < 2e-6
+    dXF = torch.randn(Bt, N, I2, generator=g)
+    rdx, rdWx, rdbx, rdWfx, rdbfx = O.proj_bwd(dXF.double(), x.double(), Wx.double(), Wfx.double(), (Hg, Wg))
+    dx = torch.empty(Bt, N, C, device=dev)
+    ops.gemm(M=Bt * N, N=C, K=9 * I2, A=dXF.to(dev), lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=dx, ldc=C, conv_mode=1, Hg=Hg,
+             Wg=Wg, Cin=I2, flip=1)
+    assert O.rel_l2(dx.cpu(), rdx) < 2e-6
+    dWx = torch.empty(I, C, 3, 3, device=dev)
+    dWfx = torch.empty(I, C, 3, 3, device=dev)
+    for sk in (1, 3):
+        ops.gemm(M=9 * C, N=I2, K=Bt * N, A=x.to(dev), lda=C, a_kind=1, B=dXF.to(dev), ldb=I2, b_kind=1, conv_mode=2, Hg=Hg, Wg=Wg,
+                 Cin=C, split_k=sk, scatter=(dWx, dWfx), I=I, taps=9)
+        assert O.rel_l2(dWx.cpu(), rdWx) < 2e-6
+        assert O.rel_l2(dWfx.cpu(), rdWfx) < 2e-6
+    db = ops.colsum(dXF.to(dev).reshape(Bt * N, I2), Bt * N, I2)
+    assert O.rel_l2(db.cpu(), torch.cat([rdbx, rdbfx])) < 2e-6
+
+
+def test_gemm_bf16_mode_rounds_operands(dev):
+    ops = _ops()
+    from transformerbasednavierstokesolver_b200._lib import TBNS_PREC_BF16
+    g = torch.Generator().manual_seed(9)
+    A = torch.randn(64, 96, generator=g)
+    B = torch.randn(96, 48, generator=g)
+    C = torch.empty(64, 48, device=dev)
+    ops.gemm(M=64, N=48, K=96, A=A.to(dev), lda=96, a_kind=0, B=B.to(dev), ldb=48, b_kind=1, C=C, ldc=48, precision=TBNS_PREC_BF16)
+    ref = A.bfloat16().double() @ B.bfloat16().double()
+    assert O.rel_l2(C.cpu(), ref) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,C", [(1000, 256), (37, 64), (5, 30), (4096, 128)])
+def test_layernorm(dev, rows, C):
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows + C)
+    x = torch.randn(rows, C, generator=g) * 2 + 0.5
+    gam, bet = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    dy = torch.randn(rows, C, generator=g)
+    dres = torch.randn(rows, C, generator=g)
+    y, mean, rstd = ops.layernorm_fwd(x.to(dev), gam.to(dev), bet.to(dev))
+    ry, rmean, rrstd = O.layernorm_fwd(x.double(), gam.double(), bet.double())
+    assert O.rel_l2(y.cpu(), ry) < 2e-6
+    dx, dg, db = ops.layernorm_bwd(dy.to(dev), x.to(dev), mean, rstd, gam.to(dev), dres.to(dev))
+    rdx, rdg, rdb = O.layernorm_bwd(dy.double(), x.double(), rmean, rrstd, gam.double())
+    assert O.rel_l2(dx.cpu(), rdx + dres.double()) < 5e-6
+    assert O.rel_l2(dg.cpu(), rdg) < 5e-6
+    assert O.rel_l2(db.cpu(), rdb) < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# attention module / block / model against the golden vectors of the live reference
+# ------------------------------------------------------------------------------------------------
+def _build_pa(fx, dev, precision):
+    from transformerbasednavierstokesolver_b200.model import Physics_Attention as PA
+    cls = getattr(PA, fx["kind"])
+    m = cls(**fx["kwargs"])
+    m.load_state_dict({k: v.float() for k, v in fx["state"].items()}, strict=True)
+    m.precision = precision
+    return m.to(dev)
+
+
+PA_FIXTURES = ["pa_structured_small.pt", "pa_structured_g64.pt", "pa_irregular_small.pt", "pa_irregular_inner_ne_dim.pt",
+               "pa_ckpt_ep400_block3.pt"]
+
+
+@pytest.mark.parametrize("name", PA_FIXTURES)
+def test_pa_module_fp32_matches_reference_golden(dev, golden, name):
+    fx = golden(name)
+    m = _build_pa(fx, dev, "fp32")
+    x = fx["inputs"][0].float().to(dev).requires_grad_(True)
+    out = m(x)
+    out.backward(fx["dout"].float().to(dev))
+    assert O.rel_l2(out.cpu(), fx["out"]) < FP32_OUT_TOL
+    assert O.rel_l2(x.grad.cpu(), fx["dinputs"][0]) < FP32_GRAD_TOL
+    for k, p in m.named_parameters():
+        ref = fx["grads"][k]
+        if float(ref.abs().max()) == 0.0:
+            assert float(p.grad.abs().max()) == 0.0, k   # clamped temperature heads
+        else:
+            assert O.rel_l2(p.grad.cpu(), ref) < FP32_GRAD_TOL, k
+
+
+@pytest.mark.parametrize("name", PA_FIXTURES)
+def test_pa_module_bf16_mode(dev, golden, name):
+    """bf16 mode on shared bf16-representable weights and inputs (SURVEY.md §7 hard part 1)"""
+    fx = golden(name)
+    state = {k: v.float().bfloat16().double() for k, v in fx["state"].items()}
+    x = fx["inputs"][0].float().bfloat16().double()
+    kw = fx["kwargs"]
+    ref, _ = O.pa_forward(x, state, kw["heads"], (kw["H"], kw["W"]) if "H" in kw else None)
+    fx2 = dict(fx, state=state)
+    m = _build_pa(fx2, dev, "bf16")
+    out = m(x.float().to(dev))
+    assert O.rel_l2(out.cpu(), ref) < BF16_OUT_TOL
+
+
+@pytest.mark.parametrize("name", ["block_structured_mid.pt", "block_structured_last.pt", "block_irregular_last.pt"])
+def test_block_fp32_matches_reference_golden(dev, golden, name):
+    fx = golden(name)
+    if fx["kind"] == "block_structured":
+        from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Transolver_block
+    else:
+        from transformerbasednavierstokesolver_b200.model.Transolver_Irregular_Mesh import Transolver_block
+    m = Transolver_block(**fx["kwargs"])
+    m.load_state_dict({k: v.float() for k, v in fx["state"].items()}, strict=True)
+    m.Attn.precision = "fp32"
+    m = m.to(dev)
+    x = fx["inputs"][0].float().to(dev).requires_grad_(True)
+    out = m(x)
+    out.backward(fx["dout"].float().to(dev))
+    assert O.rel_l2(out.cpu(), fx["out"]) < FP32_OUT_TOL
+    assert O.rel_l2(x.grad.cpu(), fx["dinputs"][0]) < FP32_GRAD_TOL
+    for k, p in m.named_parameters():
+        assert O.rel_l2(p.grad.cpu(), fx["grads"][k]) < FP32_GRAD_TOL, k
+
+
+@pytest.mark.parametrize("name", ["model_2d_unified.pt", "model_2d_plainpos.pt", "model_irregular.pt"])
+def test_model_fp32_matches_reference_golden(dev, golden, name):
+    import transformerbasednavierstokesolver_b200 as pkg
+    fx = golden(name)
+    pkg.set_default_precision("fp32")
+    try:
+        if fx["kind"] == "model_2d":
+            from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Model
+        else:
+            from transformerbasednavierstokesolver_b200.model.Transolver_Irregular_Mesh import Model
+        m = Model(**fx["kwargs"])
+        m.load_state_dict({k: v.float() for k, v in fx["state"].items()}, strict=True)
+        m = m.to(dev)
+        x = fx["x"].float().to(dev)
+        f = fx["fx"].float().to(dev) if "fx" in fx else None
+        y = fx["y"].float().to(dev)
+        out = m(x, f)
+        assert O.rel_l2(out.cpu(), fx["out"]) < FP32_OUT_TOL
+        n = out.shape[0]
+        loss = (torch.linalg.vector_norm(out.reshape(n, -1) - y.reshape(n, -1), dim=1) / torch.linalg.vector_norm(y.reshape(n, -1), dim=1)).sum()
+        assert abs(float(loss) - float(fx["loss"])) < 1e-5 * abs(float(fx["loss"]))
+        loss.backward()
+        for k, p in m.named_parameters():
+            if k in fx["grads"]:
+                assert O.rel_l2(p.grad.cpu(), fx["grads"][k]) < 2 * FP32_GRAD_TOL, k
+        if "rollout" in fx:  # closed-loop autoregressive rollout (exp_ns.py:225-241)
+            with torch.no_grad():
+                ff = f.clone()
+                preds = []
+                for _ in range(fx["rollout"].shape[-1]):
+                    im = m(x, fx=ff)
+                    preds.append(im)
+                    ff = torch.cat((ff[..., 1:], im), -1)
+            roll = torch.cat(preds, -1)
+            assert O.rel_l2(roll.cpu(), fx["rollout"]) < 5e-5
+            e_ref = float(O.rel_l2_sum(fx["rollout"], fx["y"].expand_as(fx["rollout"])))
+            e_new = float(O.rel_l2_sum(roll.cpu().double(), fx["y"].expand_as(fx["rollout"])))
+            assert abs(e_new - e_ref) < 1e-5 * abs(e_ref)   # "unchanged rollout error" (fp32 mode)
+    finally:
+        pkg.set_default_precision("bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configuration sizes against the oracle (CPU, seconds)
+# ------------------------------------------------------------------------------------------------
+def _rand_state(cls, kwargs, seed):
+    torch.manual_seed(seed)
+    m = cls(**kwargs)
+    with torch.no_grad():
+        m.in_project_slice.weight.mul_(4.0)   # sharpen the slice softmax (random init is near-uniform)
+        m.temperature.copy_(torch.linspace(0.2, 1.5, kwargs["heads"]).reshape(1, -1, 1, 1))
+    return m
+
+
+@pytest.mark.parametrize("cfg", ["cfg1_ns64", "cfg3_darcy85", "cfg4_elas972"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pa_baseline_config_sizes(dev, cfg, precision):
+    from transformerbasednavierstokesolver_b200.model import Physics_Attention as PA
+    if cfg == "cfg1_ns64":
+        cls, kw, B, N = PA.Physics_Attention_Structured_Mesh_2D, dict(dim=256, heads=8, dim_head=32, slice_num=32, H=64, W=64), 2, 4096
+    elif cfg == "cfg3_darcy85":
+        cls, kw, B, N = PA.Physics_Attention_Structured_Mesh_2D, dict(dim=128, heads=8, dim_head=16, slice_num=64, H=85, W=85), 1, 7225
+    else:
+        cls, kw, B, N = PA.Physics_Attention_Irregular_Mesh, dict(dim=128, heads=8, dim_head=16, slice_num=64), 1, 972
+    m = _rand_state(cls, kw, 7)
+    x = torch.nn.functional.layer_norm(torch.randn(B, N, kw["dim"]), (kw["dim"],))
+    if precision == "bf16":
+        with torch.no_grad():
+            for p in m.parameters():
+                p.copy_(p.bfloat16().float())
+        x = x.bfloat16().float()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    grid = (kw["H"], kw["W"]) if "H" in kw else None
+    ref, sv = O.pa_forward(x, sd, kw["heads"], grid)          # fp32 oracle on CPU
+    m.precision = precision
+    m = m.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    out = m(xd)
+    tol = FP32_OUT_TOL if precision == "fp32" else BF16_OUT_TOL
+    assert O.rel_l2(out.cpu(), ref) < tol
+    # size-independent properties: slice weights are a partition of unity; sum_g s_g == N per (b,h)
+    dout = torch.randn_like(ref)
+    out.backward(dout.to(dev))
+    rdx, rg = O.pa_backward(dout, sd, sv)
+    gtol = 2e-4 if precision == "fp32" else 2e-2
+    assert O.rel_l2(xd.grad.cpu(), rdx) < gtol
+    assert O.rel_l2(m.in_project_x.weight.grad.cpu(), rg["in_project_x.weight"]) < gtol
+    assert O.rel_l2(m.to_out[0].weight.grad.cpu(), rg["to_out.0.weight"]) < gtol
+    assert O.rel_l2(m.temperature.grad.cpu(), rg["temperature"]) < (1e-3 if precision == "fp32" else 5e-2)
+
+
+def test_slice_weights_partition_of_unity_full_size(dev):
+    """property test at cfg-5 width (N = 65 536 tokens): rows of w sum to 1, sum_g s = N, Tt = w^T F"""
+    ops = _ops()
+    from transformerbasednavierstokesolver_b200 import _lib
+    lib = _lib.load()
+    B, N, H, D, G = 1, 65536, 8, 32, 64
+    g = torch.Generator(device="cpu").manual_seed(1)
+    XF = torch.randn(B * N, 2 * H * D, generator=g).to(dev)
+    Ws = (torch.randn(G, D, generator=g) * 0.5).to(dev)
+    bs = torch.randn(G, generator=g).to(dev)
+    tau = torch.linspace(0.05, 6.0, H).to(dev)
+    nchunk = lib.tbns_slice_nchunk(N)
+    w = torch.empty(B, N, H * G, device=dev)
+    part = torch.empty(B * H * nchunk * G * (D + 1), device=dev)
+    _lib.check(lib.tbns_pa_slice_fwd(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), w.data_ptr(), part.data_ptr(), B, N,
+                                     H, D, G, 1, torch.cuda.current_stream().cuda_stream), "slice_fwd")
+    w4 = w.view(B, N, H, G)
+    assert float((w4.sum(-1) - 1).abs().max()) < 1e-5
+    p = part.view(B, H, nchunk, G, D + 1).sum(2)
+    assert float((p[..., D].sum(-1) - N).abs().max()) < 0.05
+    F = XF[:, H * D:].view(B, N, H, D)
+    Tt = torch.einsum("bnhg,bnhd->bhgd", w4.double(), F.double())
+    assert O.rel_l2(p[..., :D].cpu(), Tt.cpu()) < 1e-5
+    # clamp: heads with tau outside [0.1, 5] behave like tau at the bound
+    L = (XF[:, :H * D].view(B, N, H, D).double() @ Ws.double().t() + bs.double()) / tau.double().clamp(0.1, 5.0)[None, None, :, None]
+    assert O.rel_l2(w4.cpu(), torch.softmax(L, -1).cpu()) < 1e-5

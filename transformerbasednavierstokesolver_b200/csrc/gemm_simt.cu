@@ -1,0 +1,322 @@
+// Generic fp32 SIMT GEMM with the gathers and epilogues of the Physics-Attention path.
+//
+// This is the exact-arithmetic engine of the path: fp32 FMA accumulation (north_star "fp32 mode",
+// per-layer rel-L2 <= 1e-5) and, with precision == TBNS_PREC_BF16, operands rounded to bf16 on the way
+// into shared memory so its results equal the tensor-core (tcgen05) path up to fp32 summation order.
+// It also serves every contraction the tcgen05 kernels do not cover (odd shapes, wgrad scatter).
+//
+// Implements, depending on the descriptor (include/tbns.h):
+//   conv 3x3 fprop / Linear projections   model/Physics_Attention.py:94-97, :36-39
+//   deslice (+) to_out                    model/Physics_Attention.py:116-119, :55-57
+//   MLP Linear/GELU/Linear                model/Transolver_Structured_Mesh_2D.py:26-37
+//   and all dgrad / wgrad contractions of SURVEY.md §8 (a-bwd).
+#include "common.cuh"
+
+namespace tbns {
+
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256, PAD = 4;
+
+// pointer to A(m,k) or nullptr for a structural zero (conv padding). Caller bounds-checks m,k.
+__device__ __forceinline__ const float* a_src(const tbns_gemm_desc& d, const float* A, int m, int k) {
+  if (d.conv_mode == 0) return d.a_kind == 0 ? A + (long long)m * d.lda + k : A + (long long)k * d.lda + m;
+  int token = d.conv_mode == 1 ? m : k;
+  int feat = d.conv_mode == 1 ? k : m;
+  int tap = feat / d.Cin, ci = feat - tap * d.Cin;
+  int dy = tap / 3 - 1, dx = tap % 3 - 1;
+  if (d.flip) { dy = -dy; dx = -dx; }
+  int hw = d.Hg * d.Wg;
+  int b = token / hw, r = token - b * hw;
+  int i = r / d.Wg, j = r - i * d.Wg;
+  int ii = i + dy, jj = j + dx;
+  if (ii < 0 || ii >= d.Hg || jj < 0 || jj >= d.Wg) return nullptr;
+  return A + (long long)(b * hw + ii * d.Wg + jj) * d.lda + ci;
+}
+__device__ __forceinline__ const float* b_src(const tbns_gemm_desc& d, const float* B, int k, int n) {
+  return d.b_kind == 0 ? B + (long long)n * d.ldb + k : B + (long long)k * d.ldb + n;
+}
+
+// KIND 0: elements (m, k..k+3) ; KIND 1: elements (m..m+3, k)
+template <int KIND>
+__device__ __forceinline__ float4 load_a4(const tbns_gemm_desc& d, const float* A, int m, int k, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (m >= d.M || k >= d.K) return v;
+  if (KIND == 0) {
+    if (vec) {
+      const float* p = a_src(d, A, m, k);
+      if (p) v = *reinterpret_cast<const float4*>(p);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k + j < d.K) {
+          const float* p = a_src(d, A, m, k + j);
+          if (p) (&v.x)[j] = *p;
+        }
+    }
+  } else {
+    if (vec && m + 3 < d.M) {
+      const float* p = a_src(d, A, m, k);
+      if (p) v = *reinterpret_cast<const float4*>(p);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (m + j < d.M) {
+          const float* p = a_src(d, A, m + j, k);
+          if (p) (&v.x)[j] = *p;
+        }
+    }
+  }
+  return v;
+}
+// KIND 0: elements (k..k+3, n) ; KIND 1: elements (k, n..n+3)
+template <int KIND>
+__device__ __forceinline__ float4 load_b4(const tbns_gemm_desc& d, const float* B, int k, int n, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n >= d.N || k >= d.K) return v;
+  if (KIND == 0) {
+    if (vec) {
+      v = *reinterpret_cast<const float4*>(b_src(d, B, k, n));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k + j < d.K) (&v.x)[j] = *b_src(d, B, k + j, n);
+    }
+  } else {
+    if (vec && n + 3 < d.N) {
+      v = *reinterpret_cast<const float4*>(b_src(d, B, k, n));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < d.N) (&v.x)[j] = *b_src(d, B, k, n + j);
+    }
+  }
+  return v;
+}
+
+__device__ __forceinline__ void epi_store1(const tbns_gemm_desc& d, int bidx, int m, int n, float v) {
+  if (d.bias) v += d.bias[n];
+  if (d.act == 1) {
+    if (d.aux_out) d.aux_out[bidx * d.sAux + (long long)m * d.ldaux + n] = v;
+    v = gelu_erf(v);
+  } else if (d.act == 2) {
+    v *= gelu_erf_grad(d.aux_in[bidx * d.sAux + (long long)m * d.ldaux + n]);
+  }
+  if (d.residual) v += d.residual[bidx * d.sR + (long long)m * d.ldr + n];
+  if (d.scatter) {
+    int tap = m / d.Cin, ci = m - tap * d.Cin;
+    float* base = n < d.I ? d.Cx : d.Cfx;
+    int co = n < d.I ? n : n - d.I;
+    base[((long long)co * d.Cin + ci) * d.taps + tap] = v;
+  } else {
+    d.C[bidx * d.sC + (long long)m * d.ldc + n] = v;
+  }
+}
+
+// 4 consecutive n. vec => all of bias/aux/residual/C rows are 16B aligned and n+3 < N.
+__device__ __forceinline__ void epi_store4(const tbns_gemm_desc& d, int bidx, int m, int n, float4 v, bool vec) {
+  if (m >= d.M || n >= d.N) return;
+  if (!vec || d.scatter) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < d.N) epi_store1(d, bidx, m, n + j, (&v.x)[j]);
+    return;
+  }
+  if (d.bias) {
+    float4 b = *reinterpret_cast<const float4*>(d.bias + n);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  if (d.act == 1) {
+    if (d.aux_out) *reinterpret_cast<float4*>(d.aux_out + bidx * d.sAux + (long long)m * d.ldaux + n) = v;
+    v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+  } else if (d.act == 2) {
+    float4 a = *reinterpret_cast<const float4*>(d.aux_in + bidx * d.sAux + (long long)m * d.ldaux + n);
+    v.x *= gelu_erf_grad(a.x); v.y *= gelu_erf_grad(a.y); v.z *= gelu_erf_grad(a.z); v.w *= gelu_erf_grad(a.w);
+  }
+  if (d.residual) {
+    float4 r = *reinterpret_cast<const float4*>(d.residual + bidx * d.sR + (long long)m * d.ldr + n);
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  }
+  *reinterpret_cast<float4*>(d.C + bidx * d.sC + (long long)m * d.ldc + n) = v;
+}
+
+template <int AK, int BKIND>
+__global__ void __launch_bounds__(NT) gemm_simt_kernel(const tbns_gemm_desc d, int vecA, int vecB, int vecC) {
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int split = blockIdx.z % d.split_k;
+  const int bidx = blockIdx.z / d.split_k;
+  const float* A = d.A + bidx * d.sA;
+  const float* B = d.B + bidx * d.sB;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nk = (d.K + BK - 1) / BK;
+  const int per = (nk + d.split_k - 1) / d.split_k;
+  const int kb0 = split * per;
+  const int kb1 = min(nk, kb0 + per);
+  const bool rb16 = d.precision == TBNS_PREC_BF16;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 ra[2], rb[2];
+  auto gload = [&](int kb) {
+    const int k0 = kb * BK;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * NT;
+      if (AK == 0) ra[i] = load_a4<0>(d, A, m0 + (idx >> 2), k0 + (idx & 3) * 4, vecA);
+      else         ra[i] = load_a4<1>(d, A, m0 + (idx & 31) * 4, k0 + (idx >> 5), vecA);
+      if (BKIND == 0) rb[i] = load_b4<0>(d, B, k0 + (idx & 3) * 4, n0 + (idx >> 2), vecB);
+      else            rb[i] = load_b4<1>(d, B, k0 + (idx >> 5), n0 + (idx & 31) * 4, vecB);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * NT;
+      float4 a = ra[i], b = rb[i];
+      if (rb16) {
+        a.x = round_bf16(a.x); a.y = round_bf16(a.y); a.z = round_bf16(a.z); a.w = round_bf16(a.w);
+        b.x = round_bf16(b.x); b.y = round_bf16(b.y); b.z = round_bf16(b.z); b.w = round_bf16(b.w);
+      }
+      if (AK == 0) {
+        const int row = idx >> 2, kc = (idx & 3) * 4;
+        As[buf][kc + 0][row] = a.x; As[buf][kc + 1][row] = a.y; As[buf][kc + 2][row] = a.z; As[buf][kc + 3][row] = a.w;
+      } else {
+        *reinterpret_cast<float4*>(&As[buf][idx >> 5][(idx & 31) * 4]) = a;
+      }
+      if (BKIND == 0) {
+        const int col = idx >> 2, kc = (idx & 3) * 4;
+        Bs[buf][kc + 0][col] = b.x; Bs[buf][kc + 1][col] = b.y; Bs[buf][kc + 2][col] = b.z; Bs[buf][kc + 3][col] = b.w;
+      } else {
+        *reinterpret_cast<float4*>(&Bs[buf][idx >> 5][(idx & 31) * 4]) = b;
+      }
+    }
+  };
+
+  const int tx = tid & 15, ty = tid >> 4;  // thread owns rows {ty*4..+3, 64+ty*4..+3} x cols {tx*4..+3, 64+tx*4..+3}
+  if (kb0 < kb1) {
+    gload(kb0);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int kb = kb0; kb < kb1; ++kb) {
+    const int buf = (kb - kb0) & 1;
+    if (kb + 1 < kb1) gload(kb + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kb + 1 < kb1) sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + jh * 64 + tx * 4;
+      const float4 v = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+      if (d.split_k > 1) {
+        if (m < d.M && n < d.N) {
+          float* p = d.ws + ((long long)(split * d.batch + bidx) * d.M + m) * d.N + n;
+          if ((d.N & 3) == 0) {
+            *reinterpret_cast<float4*>(p) = v;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < d.N) p[j] = (&v.x)[j];
+          }
+        }
+      } else {
+        epi_store4(d, bidx, m, n, v, vecC);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const tbns_gemm_desc d, int vecC) {
+  const long long n4 = (d.N + 3) / 4;
+  const long long total = (long long)d.batch * d.M * n4;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int nq = (int)(t % n4);
+    const long long rm = t / n4;
+    const int m = (int)(rm % d.M);
+    const int bidx = (int)(rm / d.M);
+    const int n = nq * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < d.split_k; ++s) {
+      const float* p = d.ws + ((long long)(s * d.batch + bidx) * d.M + m) * d.N + n;
+      if ((d.N & 3) == 0) {
+        const float4 u = *reinterpret_cast<const float4*>(p);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < d.N) (&v.x)[j] += p[j];
+      }
+    }
+    epi_store4(d, bidx, m, n, v, vecC);
+  }
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace tbns
+
+using namespace tbns;
+
+extern "C" int tbns_gemm(const tbns_gemm_desc* dp, void* stream) {
+  TBNS_REQUIRE(dp != nullptr, "tbns_gemm: null descriptor");
+  tbns_gemm_desc d = *dp;
+  if (d.batch < 1) d.batch = 1;
+  if (d.split_k < 1) d.split_k = 1;
+  if (d.M == 0 || d.N == 0) return TBNS_OK;
+  TBNS_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "tbns_gemm: bad dims M=%d N=%d K=%d", d.M, d.N, d.K);
+  TBNS_REQUIRE(d.A && d.B, "tbns_gemm: null operand");
+  TBNS_REQUIRE(d.scatter ? (d.Cx && d.Cfx && d.I > 0 && d.taps > 0 && d.Cin > 0) : (d.C != nullptr), "tbns_gemm: null output");
+  TBNS_REQUIRE(d.a_kind == 0 || d.a_kind == 1, "tbns_gemm: a_kind");
+  TBNS_REQUIRE(d.b_kind == 0 || d.b_kind == 1, "tbns_gemm: b_kind");
+  TBNS_REQUIRE(d.conv_mode >= 0 && d.conv_mode <= 2, "tbns_gemm: conv_mode");
+  if (d.conv_mode == 1) TBNS_REQUIRE(d.a_kind == 0 && d.K == 9 * d.Cin && d.M % (d.Hg * d.Wg) == 0 && d.batch == 1, "tbns_gemm: conv_mode 1 needs a_kind 0, K=9*Cin, M multiple of Hg*Wg");
+  if (d.conv_mode == 2) TBNS_REQUIRE(d.a_kind == 1 && d.M == 9 * d.Cin && d.K % (d.Hg * d.Wg) == 0 && d.batch == 1, "tbns_gemm: conv_mode 2 needs a_kind 1, M=9*Cin, K multiple of Hg*Wg");
+  TBNS_REQUIRE(d.split_k == 1 || d.ws != nullptr, "tbns_gemm: split_k needs a workspace");
+  TBNS_REQUIRE(d.act != 2 || d.aux_in, "tbns_gemm: act 2 needs aux_in");
+
+  const bool convA = d.conv_mode != 0;
+  int vecA = al16(d.A) && (d.lda % 4 == 0) && (d.sA % 4 == 0) && (!convA || d.Cin % 4 == 0) && (d.a_kind == 1 || d.K % 4 == 0);
+  int vecB = al16(d.B) && (d.ldb % 4 == 0) && (d.sB % 4 == 0) && (d.b_kind == 1 || d.K % 4 == 0);
+  int vecC = !d.scatter && al16(d.C) && (d.ldc % 4 == 0) && (d.sC % 4 == 0) && (d.N % 4 == 0) &&
+             (!d.bias || al16(d.bias)) && (!d.residual || (al16(d.residual) && d.ldr % 4 == 0 && d.sR % 4 == 0)) &&
+             (!(d.aux_out || d.aux_in) || (d.ldaux % 4 == 0 && d.sAux % 4 == 0 && (!d.aux_out || al16(d.aux_out)) && (!d.aux_in || al16(d.aux_in))));
+  if (d.split_k > 1) TBNS_REQUIRE(al16(d.ws), "tbns_gemm: workspace must be 16B aligned");
+
+  dim3 grid(cdiv(d.N, BN), cdiv(d.M, BM), d.batch * d.split_k);
+  TBNS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "tbns_gemm: grid too large");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d.a_kind == 0 && d.b_kind == 0) gemm_simt_kernel<0, 0><<<grid, NT, 0, st>>>(d, vecA, vecB, vecC);
+  else if (d.a_kind == 0 && d.b_kind == 1) gemm_simt_kernel<0, 1><<<grid, NT, 0, st>>>(d, vecA, vecB, vecC);
+  else if (d.a_kind == 1 && d.b_kind == 0) gemm_simt_kernel<1, 0><<<grid, NT, 0, st>>>(d, vecA, vecB, vecC);
+  else gemm_simt_kernel<1, 1><<<grid, NT, 0, st>>>(d, vecA, vecB, vecC);
+  TBNS_LAUNCH_CHECK();
+  if (d.split_k > 1) {
+    const long long total = (long long)d.batch * d.M * ((d.N + 3) / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gemm_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(d, vecC);
+    TBNS_LAUNCH_CHECK();
+  }
+  return TBNS_OK;
+}

@@ -1,0 +1,98 @@
+"""Drop-in replacements for the reference Physics-Attention modules.
+
+Same constructor arguments, attributes (`heads`, `dim_head`, `H`, `W`, `temperature`, ...), parameter
+names / shapes (so `state_dict()` round-trips with reference checkpoints) and `forward(x)` contract as
+  Physics_Attention_Irregular_Mesh        reference model/Physics_Attention.py:6-57
+  Physics_Attention_Structured_Mesh_2D    reference model/Physics_Attention.py:60-119
+but `forward` runs the sm_100a kernels of libtbns through `ops.PhysicsAttentionFn` (custom backward).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import config, ops
+
+
+class _PhysicsAttentionBase(nn.Module):
+    structured = False
+
+    def _build(self, dim, heads, dim_head, dropout, slice_num, proj_factory):
+        inner = dim_head * heads
+        self.dim_head = dim_head
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.softmax = nn.Softmax(dim=-1)   # kept only so module listings match the reference
+        self.dropout = nn.Dropout(dropout)
+        self.temperature = nn.Parameter(torch.full((1, heads, 1, 1), 0.5))
+        self.in_project_x = proj_factory(dim, inner)
+        self.in_project_fx = proj_factory(dim, inner)
+        self.in_project_slice = nn.Linear(dim_head, slice_num)
+        nn.init.orthogonal_(self.in_project_slice.weight)
+        self.to_q = nn.Linear(dim_head, dim_head, bias=False)
+        self.to_k = nn.Linear(dim_head, dim_head, bias=False)
+        self.to_v = nn.Linear(dim_head, dim_head, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout))
+        self.precision = None  # None -> config.get_default_precision()
+        self._pack_key = None
+        self._packed = None
+
+    # packed projection weights (fprop / dgrad operand layouts), refreshed when the masters change
+    def _packed_weights(self):
+        px, pfx = self.in_project_x, self.in_project_fx
+        key = (px.weight.data_ptr(), px.weight._version, px.bias._version, pfx.weight.data_ptr(), pfx.weight._version,
+               pfx.bias._version, px.weight.device)
+        if key != self._pack_key:
+            with torch.no_grad():
+                self._packed = ops.pack_proj_weights(px.weight.detach().contiguous(), px.bias.detach().contiguous(),
+                                                     pfx.weight.detach().contiguous(), pfx.bias.detach().contiguous())
+            self._pack_key = key
+        return self._packed
+
+    def _grid(self, N):
+        return None
+
+    def forward(self, x, residual=None):
+        """x [B,N,C] -> [B,N,dim].  `residual` (optional, extension used by Transolver_block) is added in the
+        output-projection epilogue."""
+        if not x.is_cuda:
+            raise RuntimeError("Physics-Attention (B200) has no CPU path: move the module and its input to a CUDA device")
+        if self.training and self.dropout.p > 0.0:
+            raise NotImplementedError("dropout > 0 in training mode is not supported by the fused kernels "
+                                      "(every reference script uses dropout=0.0)")
+        B, N, C = x.shape
+        grid = self._grid((B, N, C))
+        Wf, Wd, bcat = self._packed_weights()
+        prec = ops.PRECISIONS[self.precision or config.get_default_precision()]
+        lin = self.to_out[0]
+        return ops.PhysicsAttentionFn.apply(
+            x.float(), residual, self.temperature, self.in_project_x.weight, self.in_project_x.bias, self.in_project_fx.weight,
+            self.in_project_fx.bias, self.in_project_slice.weight, self.in_project_slice.bias, self.to_q.weight, self.to_k.weight,
+            self.to_v.weight, lin.weight, lin.bias, Wf, Wd, bcat, self.heads, grid, prec)
+
+
+class Physics_Attention_Irregular_Mesh(_PhysicsAttentionBase):
+    """for irregular meshes in 1D, 2D or 3D space (temperature is NOT clamped, reference :40)."""
+
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0., slice_num=64):
+        super().__init__()
+        self._build(dim, heads, dim_head, dropout, slice_num, lambda i, o: nn.Linear(i, o))
+
+
+class Physics_Attention_Structured_Mesh_2D(_PhysicsAttentionBase):
+    """for structured meshes in 2D space: 3x3 conv projections, temperature clamped to [0.1, 5] (reference :99)."""
+    structured = True
+
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0., slice_num=64, H=101, W=31, kernel=3):
+        super().__init__()
+        if kernel != 3:
+            raise NotImplementedError("only kernel=3 is supported (the reference never passes another value)")
+        self.H = H
+        self.W = W
+        self._build(dim, heads, dim_head, dropout, slice_num, lambda i, o: nn.Conv2d(i, o, kernel, 1, kernel // 2))
+
+    def _grid(self, shape):
+        B, N, C = shape
+        if N != self.H * self.W:
+            raise RuntimeError(f"shape '[{B}, {self.H}, {self.W}, {C}]' is invalid for input of size {B * N * C}")
+        return (self.H, self.W)

@@ -1,0 +1,66 @@
+"""Transolver on a structured 2D mesh — drop-in for reference model/Transolver_Structured_Mesh_2D.py:122-220.
+Same `Model(...)` keyword arguments, `forward(x, fx, T=None)` and state_dict keys; blocks run on libtbns."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ._blocks import MLP, Transolver_block as _Block, init_weights
+from .Physics_Attention import Physics_Attention_Structured_Mesh_2D  # noqa: F401  (re-exported like the reference)
+
+
+class Transolver_block(_Block):
+    def __init__(self, num_heads, hidden_dim, dropout, act='gelu', mlp_ratio=4, last_layer=False, out_dim=1, slice_num=32,
+                 H=85, W=85):
+        super().__init__(num_heads, hidden_dim, dropout, act=act, mlp_ratio=mlp_ratio, last_layer=last_layer, out_dim=out_dim,
+                         slice_num=slice_num, H=H, W=W, structured=True)
+
+
+class Model(nn.Module):
+    def __init__(self, space_dim=1, n_layers=5, n_hidden=256, dropout=0.0, n_head=8, Time_Input=False, act='gelu', mlp_ratio=1,
+                 fun_dim=1, out_dim=1, slice_num=32, ref=8, unified_pos=False, H=85, W=85):
+        super().__init__()
+        self.__name__ = 'Transolver_2D'
+        if Time_Input:
+            raise NotImplementedError("Time_Input=True (timestep embedding, exp_plas only) is outside the B200 hot path scope")
+        self.H, self.W, self.ref, self.unified_pos = H, W, ref, unified_pos
+        self.Time_Input, self.n_hidden, self.space_dim = Time_Input, n_hidden, space_dim
+        in_dim = fun_dim + (ref * ref if unified_pos else space_dim)
+        if unified_pos:
+            self.pos = self.get_grid()
+        self.preprocess = MLP(in_dim, n_hidden * 2, n_hidden, n_layers=0, res=False, act=act)
+        self.blocks = nn.ModuleList([
+            Transolver_block(num_heads=n_head, hidden_dim=n_hidden, dropout=dropout, act=act, mlp_ratio=mlp_ratio, out_dim=out_dim,
+                             slice_num=slice_num, H=H, W=W, last_layer=(i == n_layers - 1)) for i in range(n_layers)])
+        self.initialize_weights()
+        self.placeholder = nn.Parameter((1 / n_hidden) * torch.rand(n_hidden, dtype=torch.float))
+
+    def initialize_weights(self):
+        init_weights(self)
+
+    def get_grid(self, batchsize=1):
+        """distance of every mesh point to a ref x ref lattice on [0,1]^2 -> [batch, H, W, ref*ref]
+        (a plain tensor attribute like in the reference, which builds it on the GPU; here it follows the input's device)."""
+        gx = torch.tensor(np.linspace(0, 1, self.H), dtype=torch.float)
+        gy = torch.tensor(np.linspace(0, 1, self.W), dtype=torch.float)
+        mesh = torch.stack(torch.meshgrid(gx, gy, indexing="ij"), -1)            # [H, W, 2]
+        rx = torch.tensor(np.linspace(0, 1, self.ref), dtype=torch.float)
+        lattice = torch.stack(torch.meshgrid(rx, rx, indexing="ij"), -1)         # [ref, ref, 2]
+        d = torch.sqrt(((mesh[:, :, None, None, :] - lattice[None, None]) ** 2).sum(-1))
+        return d.reshape(1, self.H, self.W, self.ref * self.ref).repeat(batchsize, 1, 1, 1).contiguous()
+
+    def forward(self, x, fx, T=None):
+        if T is not None:
+            raise NotImplementedError("time-conditioned forward is outside the B200 hot path scope")
+        if self.unified_pos:
+            if self.pos.device != x.device:
+                self.pos = self.pos.to(x.device)
+            x = self.pos.repeat(x.shape[0], 1, 1, 1).reshape(x.shape[0], self.H * self.W, self.ref * self.ref)
+        if fx is not None:
+            fx = self.preprocess(torch.cat((x, fx), -1))
+        else:
+            fx = self.preprocess(x) + self.placeholder[None, None, :]
+        for block in self.blocks:
+            fx = block(fx)
+        return fx

@@ -1,0 +1,381 @@
+"""Host-side orchestration of the Physics-Attention path: autograd Functions over the libtbns C ABI.
+
+Every tensor handed to the library is a contiguous fp32 CUDA tensor; PyTorch only owns the memory, the
+stream and autograd bookkeeping.  Stage order and math follow the reference op by op:
+
+  forward   model/Physics_Attention.py:88-119 (structured) / :31-57 (irregular)
+  backward  SURVEY.md §8 (a-bwd); restated and checked in oracle/physics_attention.py
+
+No CPU path exists: non-CUDA inputs raise.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, TBNS_PREC_BF16, TBNS_PREC_FP32, check
+
+PRECISIONS = {"fp32": TBNS_PREC_FP32, "bf16": TBNS_PREC_BF16}
+_NUM_SMS = 148
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("transformerbasednavierstokesolver_b200 has no CPU path: tensors must live on a CUDA device")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"expected float32 tensor, got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError("expected a contiguous tensor")
+
+
+def _split_k(M: int, N: int, K: int, batch: int = 1) -> int:
+    """pick a split so that small-output / long-K contractions (wgrad) still fill the 148 SMs."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128) * batch
+    if tiles >= _NUM_SMS:
+        return 1
+    s = (2 * _NUM_SMS + tiles - 1) // tiles
+    s = min(s, max(1, K // 256))
+    return max(1, min(s, 64))
+
+
+def gemm(*, M, N, K, A, lda, a_kind, B, ldb, b_kind, C=None, ldc=0, batch=1, sA=0, sB=0, sC=0, sR=0, sAux=0,
+         conv_mode=0, Hg=0, Wg=0, Cin=0, flip=0, bias=None, residual=None, ldr=0, act=0, aux_out=None, aux_in=None,
+         ldaux=0, precision=TBNS_PREC_FP32, split_k=1, scatter=None, I=0, taps=0):
+    """thin wrapper over `tbns_gemm` (include/tbns.h)."""
+    lib = _lib.load()
+    d = GemmDesc()
+    d.M, d.N, d.K, d.batch = M, N, K, batch
+    d.sA, d.sB, d.sC, d.sR, d.sAux = sA, sB, sC, sR, sAux
+    d.A, d.lda, d.a_kind = _p(A), lda, a_kind
+    d.B, d.ldb, d.b_kind = _p(B), ldb, b_kind
+    d.C, d.ldc = _p(C), ldc
+    d.conv_mode, d.Hg, d.Wg, d.Cin, d.flip = conv_mode, Hg, Wg, Cin, flip
+    d.bias = _p(bias)
+    d.residual, d.ldr = _p(residual), ldr
+    d.act, d.aux_out, d.aux_in, d.ldaux = act, _p(aux_out), _p(aux_in), ldaux
+    d.precision = precision
+    ws = None
+    if split_k > 1:
+        ws = torch.empty(split_k * batch * M * N, device=A.device, dtype=torch.float32)
+    d.split_k, d.ws = split_k, _p(ws)
+    if scatter is not None:
+        d.scatter, d.I, d.taps = 1, I, taps
+        d.Cx, d.Cfx = _p(scatter[0]), _p(scatter[1])
+    check(lib.tbns_gemm(ct.byref(d), _stream()), "tbns_gemm")
+
+
+def reduce_rows(inp: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    out = torch.empty(cols, device=inp.device, dtype=torch.float32)
+    check(_lib.load().tbns_reduce_rows(_p(inp), _p(out), rows, cols, _stream()), "tbns_reduce_rows")
+    return out
+
+
+def colsum(inp: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(cols, device=inp.device, dtype=torch.float32)
+    ws = torch.empty(lib.tbns_colsum_ws_floats(cols), device=inp.device, dtype=torch.float32)
+    check(lib.tbns_colsum(_p(inp), cols, _p(out), _p(ws), rows, cols, _stream()), "tbns_colsum")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5):
+    _chk(x, gamma, beta)
+    C_ = x.shape[-1]
+    rows = x.numel() // C_
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    check(_lib.load().tbns_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C_, eps, _stream()),
+          "tbns_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None):
+    _chk(dy, x, mean, rstd, gamma, dres)
+    lib = _lib.load()
+    C_ = x.shape[-1]
+    rows = x.numel() // C_
+    dx = torch.empty_like(x)
+    dg = torch.empty(C_, device=x.device, dtype=torch.float32)
+    db = torch.empty(C_, device=x.device, dtype=torch.float32)
+    ws = torch.empty(lib.tbns_layernorm_bwd_ws_floats(C_), device=x.device, dtype=torch.float32)
+    check(lib.tbns_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dg), _p(db), _p(ws), rows, C_,
+                                 _stream()), "tbns_layernorm_bwd")
+    return dx, dg, db
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = x.contiguous()
+        y, mean, rstd = layernorm_fwd(x, gamma.contiguous(), beta.contiguous(), eps)
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        dx, dg, db = layernorm_bwd(dy.contiguous(), x, mean, rstd, gamma.contiguous())
+        return dx, dg, db, None
+
+
+# ------------------------------------------------------------------------------------------------
+# projection weight packing (cached by the modules; see model/Physics_Attention.py in this package)
+# ------------------------------------------------------------------------------------------------
+def pack_proj_weights(Wx, bx, Wfx, bfx):
+    """nn.Conv2d [I,C,3,3] / nn.Linear [I,C] pair -> (Wf [2I, taps*C], Wd [C, taps*2I], bcat [2I])."""
+    _chk(Wx, bx, Wfx, bfx)
+    I, C_ = Wx.shape[0], Wx.shape[1]
+    taps = 9 if Wx.dim() == 4 else 1
+    Wf = torch.empty(2 * I, taps * C_, device=Wx.device, dtype=torch.float32)
+    Wd = torch.empty(C_, taps * 2 * I, device=Wx.device, dtype=torch.float32)
+    bcat = torch.empty(2 * I, device=Wx.device, dtype=torch.float32)
+    check(_lib.load().tbns_pack_proj_weights(_p(Wx), _p(bx), _p(Wfx), _p(bfx), _p(Wf), _p(Wd), _p(bcat), I, C_, taps, _stream()),
+          "tbns_pack_proj_weights")
+    return Wf, Wd, bcat
+
+
+# ------------------------------------------------------------------------------------------------
+# Physics-Attention forward / backward
+# ------------------------------------------------------------------------------------------------
+def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, heads: int,
+               grid: Optional[Tuple[int, int]], precision: int):
+    """returns (out, saved tuple). x [B,N,C]; Wf/bcat packed projections; residual [B,N,Cout] or None."""
+    lib = _lib.load()
+    B, N, C_ = x.shape
+    I2 = Wf.shape[0]
+    I = I2 // 2
+    H = heads
+    D = I // H
+    G = Ws.shape[0]
+    Cout = Wo.shape[0]
+    dev = x.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    st = _stream()
+    structured = grid is not None
+    # (1a) projections: XF = [x_mid | fx_mid]   Physics_Attention.py:94-97 / :36-39
+    XF = torch.empty(B * N, I2, **f32)
+    if structured:
+        Hg, Wg = grid
+        gemm(M=B * N, N=I2, K=9 * C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=9 * C_, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Hg,
+             Wg=Wg, Cin=C_, bias=bcat, precision=precision)
+    else:
+        gemm(M=B * N, N=I2, K=C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=C_, b_kind=0, C=XF, ldc=I2, bias=bcat, precision=precision)
+    # (1b,1c) slice weights + partial slice tokens   :98-101 / :40-42
+    nchunk = lib.tbns_slice_nchunk(N)
+    w = torch.empty(B, N, H * G, **f32)
+    part = torch.empty(B * H * nchunk * G * (D + 1), **f32)
+    check(lib.tbns_pa_slice_fwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w), _p(part), B, N, H, D, G, int(structured), st),
+          "tbns_pa_slice_fwd")
+    # (2) token normalisation + attention among slice tokens + fold of to_out   :102-111 / :43-52
+    s = torch.empty(B, H, G, **f32)
+    Tt, tok, q, k, v, O = (torch.empty(B, H, G, D, **f32) for _ in range(6))
+    A = torch.empty(B, H, G, G, **f32)
+    P = torch.empty(B, H * G, Cout, **f32)
+    check(lib.tbns_pa_token_attn_fwd(_p(part), nchunk, _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(Tt), _p(tok), _p(q), _p(k), _p(v),
+                                     _p(A), _p(O), _p(P), B, H, D, G, Cout, st), "tbns_pa_token_attn_fwd")
+    # (3) deslice (+) to_out (+ bias, + residual)   :116-119 / :55-57
+    out = torch.empty(B, N, Cout, **f32)
+    gemm(M=N, N=Cout, K=H * G, A=w, lda=H * G, a_kind=0, B=P, ldb=Cout, b_kind=1, C=out, ldc=Cout, batch=B, sA=N * H * G,
+         sB=H * G * Cout, sC=N * Cout, sR=N * Cout, bias=bo, residual=residual, ldr=Cout, precision=precision)
+    return out, (XF, w, s, tok, q, k, v, A, O, P)
+
+
+def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, saved, heads: int,
+                grid: Optional[Tuple[int, int]], precision: int):
+    """returns dx and the parameter gradients in reference (state_dict) layouts."""
+    lib = _lib.load()
+    XF, w, s, tok, q, k, v, A, O, P = saved
+    B, N, C_ = x.shape
+    I2 = XF.shape[1]
+    I = I2 // 2
+    H = heads
+    D = I // H
+    G = Ws.shape[0]
+    Cout = Wo.shape[0]
+    HG = H * G
+    dev = x.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    st = _stream()
+    structured = grid is not None
+    taps = 9 if structured else 1
+    nchunk = lib.tbns_slice_nchunk(N)
+
+    # (3') deslice (+) to_out backward
+    dbo = colsum(dout, B * N, Cout)
+    dP = torch.empty(B, HG, Cout, **f32)
+    gemm(M=HG, N=Cout, K=N, A=w, lda=HG, a_kind=1, B=dout, ldb=Cout, b_kind=1, C=dP, ldc=Cout, batch=B, sA=N * HG, sB=N * Cout,
+         sC=HG * Cout, precision=precision, split_k=_split_k(HG, Cout, N, B))
+    dw = torch.empty(B, N, HG, **f32)
+    gemm(M=N, N=HG, K=Cout, A=dout, lda=Cout, a_kind=0, B=P, ldb=Cout, b_kind=0, C=dw, ldc=HG, batch=B, sA=N * Cout,
+         sB=HG * Cout, sC=N * HG, precision=precision)
+    # (2') token attention backward
+    dTt = torch.empty(B, H, G, D, **f32)
+    ds = torch.empty(B, H, G, **f32)
+    dWqkv_part = torch.empty(B * H, 3 * D * D, **f32)
+    dWo_part = torch.empty(B, Cout * I, **f32)
+    check(lib.tbns_pa_token_attn_bwd(_p(dP), _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(tok), _p(q), _p(k), _p(v), _p(A), _p(O),
+                                     _p(dTt), _p(ds), _p(dWqkv_part), _p(dWo_part), B, H, D, G, Cout, st), "tbns_pa_token_attn_bwd")
+    dWqkv = reduce_rows(dWqkv_part, B * H, 3 * D * D).view(3, D, D)
+    dWo = reduce_rows(dWo_part, B, Cout * I).view(Cout, I)
+    # (1') slice backward
+    dXF = torch.empty(B * N, I2, **f32)
+    dWs_part = torch.empty(B * H * nchunk, G * (D + 1), **f32)
+    dtau_part = torch.empty(B * H * nchunk, **f32)
+    check(lib.tbns_pa_slice_bwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw), _p(dTt), _p(ds), _p(dXF), _p(dWs_part),
+                                _p(dtau_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd")
+    dWsb = reduce_rows(dWs_part, B * H * nchunk, G * (D + 1)).view(G, D + 1)
+    dWs, dbs = dWsb[:, :D].contiguous(), dWsb[:, D].contiguous()
+    dtemp = torch.empty(H, **f32)
+    check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, nchunk, int(structured), st), "tbns_pa_dtau_finish")
+    # (1a') projections: dgrad, wgrad (scattered straight into Conv2d / Linear weight layout), bias
+    dx = torch.empty(B, N, C_, **f32)
+    dWx = torch.empty(Wx_shape, **f32)
+    dWfx = torch.empty(Wx_shape, **f32)
+    if structured:
+        Hg, Wg = grid
+        gemm(M=B * N, N=C_, K=9 * I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=dx, ldc=C_, conv_mode=1, Hg=Hg, Wg=Wg,
+             Cin=I2, flip=1, precision=precision)
+        gemm(M=9 * C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, conv_mode=2, Hg=Hg, Wg=Wg, Cin=C_,
+             precision=precision, split_k=_split_k(9 * C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=9)
+    else:
+        gemm(M=B * N, N=C_, K=I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=I2, b_kind=0, C=dx, ldc=C_, precision=precision)
+        gemm(M=C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, Cin=C_, precision=precision,
+             split_k=_split_k(C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=1)
+    dbcat = colsum(dXF, B * N, I2)
+    return dx, dict(temperature=dtemp.view(1, H, 1, 1), Wx=dWx, bx=dbcat[:I], Wfx=dWfx, bfx=dbcat[I:], Ws=dWs, bs=dbs,
+                    Wq=dWqkv[0], Wk=dWqkv[1], Wv=dWqkv[2], Wo=dWo, bo=dbo)
+
+
+class PhysicsAttentionFn(torch.autograd.Function):
+    """y = PhysicsAttention(x) (+ residual).  Parameters arrive in reference layout; Wf/Wd/bcat are the packed
+    copies (non-differentiable inputs, refreshed by the module when the masters change)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, Wf, Wd, bcat, heads, grid, precision):
+        x = x.contiguous()
+        if residual is not None:
+            residual = residual.contiguous()
+        _chk(x, residual, temperature, Ws, bs, Wq, Wk, Wv, Wo, bo, Wf, Wd, bcat)
+        temperature_c = temperature.contiguous()
+        out, saved = pa_forward(x, temperature_c, Wf, bcat, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
+                                Wv.contiguous(), Wo.contiguous(), bo.contiguous(), residual, heads, grid, precision)
+        ctx.save_for_backward(x, temperature_c, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved)
+        ctx.cfg = (heads, grid, precision, tuple(Wx.shape), residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        heads, grid, precision, wshape, has_res = ctx.cfg
+        x, temperature, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved = ctx.saved_tensors
+        dout = dout.contiguous()
+        dx, g = pa_backward(dout, x, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
+                            Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision)
+        return (dx, dout if has_res else None, g["temperature"], g["Wx"], g["bx"], g["Wfx"], g["bfx"], g["Ws"], g["bs"], g["Wq"],
+                g["Wk"], g["Wv"], g["Wo"], g["bo"], None, None, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm + MLP (+ residual)   model/Transolver_Structured_Mesh_2D.py:71 with MLP :13-38 (n_layers=0)
+# ------------------------------------------------------------------------------------------------
+class LnMlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fx, gamma, beta, W1, b1, W2, b2, eps, precision):
+        fx = fx.contiguous()
+        gamma, beta, W1, b1, W2, b2 = (t.contiguous() for t in (gamma, beta, W1, b1, W2, b2))
+        _chk(fx, gamma, beta, W1, b1, W2, b2)
+        C_ = fx.shape[-1]
+        M = fx.numel() // C_
+        R = W1.shape[0]
+        Cout = W2.shape[0]
+        x2, mean, rstd = layernorm_fwd(fx, gamma, beta, eps)
+        pre = torch.empty(M, R, device=fx.device, dtype=torch.float32)
+        hid = torch.empty(M, R, device=fx.device, dtype=torch.float32)
+        gemm(M=M, N=R, K=C_, A=x2, lda=C_, a_kind=0, B=W1, ldb=C_, b_kind=0, C=hid, ldc=R, bias=b1, act=1, aux_out=pre, ldaux=R,
+             precision=precision)
+        out = torch.empty(*fx.shape[:-1], Cout, device=fx.device, dtype=torch.float32)
+        gemm(M=M, N=Cout, K=R, A=hid, lda=R, a_kind=0, B=W2, ldb=R, b_kind=0, C=out, ldc=Cout, bias=b2, residual=fx, ldr=C_,
+             precision=precision)
+        ctx.save_for_backward(fx, gamma, W1, W2, x2, mean, rstd, pre, hid)
+        ctx.precision = precision
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        fx, gamma, W1, W2, x2, mean, rstd, pre, hid = ctx.saved_tensors
+        precision = ctx.precision
+        dout = dout.contiguous()
+        C_ = fx.shape[-1]
+        M = fx.numel() // C_
+        R = W1.shape[0]
+        Cout = W2.shape[0]
+        f32 = dict(device=fx.device, dtype=torch.float32)
+        db2 = colsum(dout, M, Cout)
+        dW2 = torch.empty(Cout, R, **f32)
+        gemm(M=Cout, N=R, K=M, A=dout, lda=Cout, a_kind=1, B=hid, ldb=R, b_kind=1, C=dW2, ldc=R, precision=precision,
+             split_k=_split_k(Cout, R, M))
+        dpre = torch.empty(M, R, **f32)
+        gemm(M=M, N=R, K=Cout, A=dout, lda=Cout, a_kind=0, B=W2, ldb=R, b_kind=1, C=dpre, ldc=R, act=2, aux_in=pre, ldaux=R,
+             precision=precision)
+        db1 = colsum(dpre, M, R)
+        dW1 = torch.empty(R, C_, **f32)
+        gemm(M=R, N=C_, K=M, A=dpre, lda=R, a_kind=1, B=x2, ldb=C_, b_kind=1, C=dW1, ldc=C_, precision=precision,
+             split_k=_split_k(R, C_, M))
+        dx2 = torch.empty(M, C_, **f32)
+        gemm(M=M, N=C_, K=R, A=dpre, lda=R, a_kind=0, B=W1, ldb=C_, b_kind=1, C=dx2, ldc=C_, precision=precision)
+        dfx, dg, db = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout)  # + residual branch
+        return dfx.view_as(fx), dg, db, dW1, db1, dW2, db2, None, None
+
+
+class LnLinearFn(torch.autograd.Function):
+    """last layer: mlp2(ln_3(fx))   model/Transolver_Structured_Mesh_2D.py:72-73"""
+
+    @staticmethod
+    def forward(ctx, fx, gamma, beta, W, b, eps, precision):
+        fx = fx.contiguous()
+        gamma, beta, W, b = (t.contiguous() for t in (gamma, beta, W, b))
+        _chk(fx, gamma, beta, W, b)
+        C_ = fx.shape[-1]
+        M = fx.numel() // C_
+        Od = W.shape[0]
+        x3, mean, rstd = layernorm_fwd(fx, gamma, beta, eps)
+        out = torch.empty(*fx.shape[:-1], Od, device=fx.device, dtype=torch.float32)
+        gemm(M=M, N=Od, K=C_, A=x3, lda=C_, a_kind=0, B=W, ldb=C_, b_kind=0, C=out, ldc=Od, bias=b, precision=precision)
+        ctx.save_for_backward(fx, gamma, W, x3, mean, rstd)
+        ctx.precision = precision
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        fx, gamma, W, x3, mean, rstd = ctx.saved_tensors
+        precision = ctx.precision
+        dout = dout.contiguous()
+        C_ = fx.shape[-1]
+        M = fx.numel() // C_
+        Od = W.shape[0]
+        f32 = dict(device=fx.device, dtype=torch.float32)
+        db = colsum(dout, M, Od)
+        dW = torch.empty(Od, C_, **f32)
+        gemm(M=Od, N=C_, K=M, A=dout, lda=Od, a_kind=1, B=x3, ldb=C_, b_kind=1, C=dW, ldc=C_, precision=precision,
+             split_k=_split_k(Od, C_, M))
+        dx3 = torch.empty(M, C_, **f32)
+        gemm(M=M, N=C_, K=Od, A=dout, lda=Od, a_kind=0, B=W, ldb=C_, b_kind=1, C=dx3, ldc=C_, precision=precision)
+        dfx, dg, dbeta = layernorm_bwd(dx3, fx, mean, rstd, gamma)
+        return dfx.view_as(fx), dg, dbeta, dW, db, None, None
