@@ -227,7 +227,7 @@ def test_model_fp32_matches_reference_golden(dev, golden, name):
         assert O.rel_l2(out.cpu(), fx["out"]) < FP32_OUT_TOL
         n = out.shape[0]
         loss = (torch.linalg.vector_norm(out.reshape(n, -1) - y.reshape(n, -1), dim=1) / torch.linalg.vector_norm(y.reshape(n, -1), dim=1)).sum()
-        assert abs(float(loss) - float(fx["loss"])) < 1e-5 * abs(float(fx["loss"]))
+        assert abs(float(loss.detach()) - float(fx["loss"])) < 1e-5 * abs(float(fx["loss"]))
         loss.backward()
         for k, p in m.named_parameters():
             if k in fx["grads"]:

@@ -82,3 +82,14 @@ def test_oracle_vs_live_reference_fp32(structured):
     assert O.rel_l2(dx, x.grad) < 2e-5
     for k, p in m.named_parameters():
         assert O.rel_l2(g[k], p.grad) < 5e-5, k
+
+
+def test_library_conv_switch_is_equivalent(golden):
+    fx = golden("pa_structured_small.pt")
+    a, _ = O.pa_forward(fx["inputs"][0], fx["state"], 4, _grid(fx))
+    O.USE_LIBRARY_CONV = True
+    try:
+        b, _ = O.pa_forward(fx["inputs"][0], fx["state"], 4, _grid(fx))
+    finally:
+        O.USE_LIBRARY_CONV = False
+    assert O.rel_l2(b, a) < 1e-12

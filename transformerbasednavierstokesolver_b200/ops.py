@@ -21,6 +21,32 @@ from ._lib import GemmDesc, TBNS_PREC_BF16, TBNS_PREC_FP32, check
 PRECISIONS = {"fp32": TBNS_PREC_FP32, "bf16": TBNS_PREC_BF16}
 _NUM_SMS = 148
 
+# bookkeeping for bench.py: number of libtbns kernels launched, and (when PROFILE is a dict) CUDA-event pairs around
+# tagged launches, recorded on the launching stream
+LAUNCHES = 0
+PROFILE = None
+
+
+def _count(n: int):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _Timed:
+    def __init__(self, tag):
+        self.tag = tag if (PROFILE is not None and tag is not None) else None
+
+    def __enter__(self):
+        if self.tag is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.tag is not None:
+            self.e1.record()
+            PROFILE.setdefault(self.tag, []).append((self.e0, self.e1))
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -54,7 +80,7 @@ def _split_k(M: int, N: int, K: int, batch: int = 1) -> int:
 
 def gemm(*, M, N, K, A, lda, a_kind, B, ldb, b_kind, C=None, ldc=0, batch=1, sA=0, sB=0, sC=0, sR=0, sAux=0,
          conv_mode=0, Hg=0, Wg=0, Cin=0, flip=0, bias=None, residual=None, ldr=0, act=0, aux_out=None, aux_in=None,
-         ldaux=0, precision=TBNS_PREC_FP32, split_k=1, scatter=None, I=0, taps=0):
+         ldaux=0, precision=TBNS_PREC_FP32, split_k=1, scatter=None, I=0, taps=0, tag=None):
     """thin wrapper over `tbns_gemm` (include/tbns.h)."""
     lib = _lib.load()
     d = GemmDesc()
@@ -75,12 +101,15 @@ def gemm(*, M, N, K, A, lda, a_kind, B, ldb, b_kind, C=None, ldc=0, batch=1, sA=
     if scatter is not None:
         d.scatter, d.I, d.taps = 1, I, taps
         d.Cx, d.Cfx = _p(scatter[0]), _p(scatter[1])
-    check(lib.tbns_gemm(ct.byref(d), _stream()), "tbns_gemm")
+    with _Timed(tag):
+        check(lib.tbns_gemm(ct.byref(d), _stream()), "tbns_gemm")
+    _count(2 if split_k > 1 else 1)
 
 
 def reduce_rows(inp: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
     out = torch.empty(cols, device=inp.device, dtype=torch.float32)
     check(_lib.load().tbns_reduce_rows(_p(inp), _p(out), rows, cols, _stream()), "tbns_reduce_rows")
+    _count(1)
     return out
 
 
@@ -89,6 +118,7 @@ def colsum(inp: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
     out = torch.empty(cols, device=inp.device, dtype=torch.float32)
     ws = torch.empty(lib.tbns_colsum_ws_floats(cols), device=inp.device, dtype=torch.float32)
     check(lib.tbns_colsum(_p(inp), cols, _p(out), _p(ws), rows, cols, _stream()), "tbns_colsum")
+    _count(2)
     return out
 
 
@@ -104,6 +134,7 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5):
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
     check(_lib.load().tbns_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C_, eps, _stream()),
           "tbns_layernorm_fwd")
+    _count(1)
     return y, mean, rstd
 
 
@@ -118,6 +149,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None):
     ws = torch.empty(lib.tbns_layernorm_bwd_ws_floats(C_), device=x.device, dtype=torch.float32)
     check(lib.tbns_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dg), _p(db), _p(ws), rows, C_,
                                  _stream()), "tbns_layernorm_bwd")
+    _count(3)
     return dx, dg, db
 
 
@@ -149,6 +181,7 @@ def pack_proj_weights(Wx, bx, Wfx, bfx):
     bcat = torch.empty(2 * I, device=Wx.device, dtype=torch.float32)
     check(_lib.load().tbns_pack_proj_weights(_p(Wx), _p(bx), _p(Wfx), _p(bfx), _p(Wf), _p(Wd), _p(bcat), I, C_, taps, _stream()),
           "tbns_pack_proj_weights")
+    _count(1)
     return Wf, Wd, bcat
 
 
@@ -175,15 +208,17 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
     if structured:
         Hg, Wg = grid
         gemm(M=B * N, N=I2, K=9 * C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=9 * C_, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Hg,
-             Wg=Wg, Cin=C_, bias=bcat, precision=precision)
+             Wg=Wg, Cin=C_, bias=bcat, precision=precision, tag="proj_fprop")
     else:
-        gemm(M=B * N, N=I2, K=C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=C_, b_kind=0, C=XF, ldc=I2, bias=bcat, precision=precision)
+        gemm(M=B * N, N=I2, K=C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=C_, b_kind=0, C=XF, ldc=I2, bias=bcat, precision=precision,
+             tag="proj_fprop")
     # (1b,1c) slice weights + partial slice tokens   :98-101 / :40-42
     nchunk = lib.tbns_slice_nchunk(N)
     w = torch.empty(B, N, H * G, **f32)
     part = torch.empty(B * H * nchunk * G * (D + 1), **f32)
     check(lib.tbns_pa_slice_fwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w), _p(part), B, N, H, D, G, int(structured), st),
           "tbns_pa_slice_fwd")
+    _count(2)  # + token_attn_fwd below
     # (2) token normalisation + attention among slice tokens + fold of to_out   :102-111 / :43-52
     s = torch.empty(B, H, G, **f32)
     Tt, tok, q, k, v, O = (torch.empty(B, H, G, D, **f32) for _ in range(6))
@@ -233,6 +268,7 @@ def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, save
     dWo_part = torch.empty(B, Cout * I, **f32)
     check(lib.tbns_pa_token_attn_bwd(_p(dP), _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(tok), _p(q), _p(k), _p(v), _p(A), _p(O),
                                      _p(dTt), _p(ds), _p(dWqkv_part), _p(dWo_part), B, H, D, G, Cout, st), "tbns_pa_token_attn_bwd")
+    _count(3)  # token_attn_bwd, slice_bwd, dtau_finish
     dWqkv = reduce_rows(dWqkv_part, B * H, 3 * D * D).view(3, D, D)
     dWo = reduce_rows(dWo_part, B, Cout * I).view(Cout, I)
     # (1') slice backward
@@ -252,9 +288,9 @@ def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, save
     if structured:
         Hg, Wg = grid
         gemm(M=B * N, N=C_, K=9 * I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=dx, ldc=C_, conv_mode=1, Hg=Hg, Wg=Wg,
-             Cin=I2, flip=1, precision=precision)
+             Cin=I2, flip=1, precision=precision, tag="proj_dgrad")
         gemm(M=9 * C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, conv_mode=2, Hg=Hg, Wg=Wg, Cin=C_,
-             precision=precision, split_k=_split_k(9 * C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=9)
+             precision=precision, split_k=_split_k(9 * C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=9, tag="proj_wgrad")
     else:
         gemm(M=B * N, N=C_, K=I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=I2, b_kind=0, C=dx, ldc=C_, precision=precision)
         gemm(M=C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, Cin=C_, precision=precision,
