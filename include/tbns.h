@@ -69,6 +69,20 @@ typedef struct tbns_gemm_desc {
 int tbns_gemm(const tbns_gemm_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Tensor-core path of the projections (tcgen05.mma + TMA + TMEM, bf16 operands, fp32 accumulate):
+ *   C[m, n] = sum_{tap,ci} A[shift(m,tap), ci] * W[n, tap*Cin + ci] (+ bias[n]),  m = token of a [Bimg,Hg,Wg] grid
+ *   A_bf16 [Bimg*Hg*Wg, Cin] bf16 (NHWC == the reference's [B,N,C]); W_bf16 [N, taps*Cin] bf16; C fp32 [.., ldc].
+ *   taps=9: 3x3/pad-1 conv pair in_project_x|in_project_fx (model/Physics_Attention.py:94-97) as one GEMM;
+ *   flip=1: its transposed convolution (dgrad); taps=1: nn.Linear (:36-39; use Hg=1, Wg=#tokens).
+ * Shapes: Cin % 64 == 0, N % 64 == 0 (tbns_gemm_tc_supported); other shapes go through tbns_gemm.
+ * ------------------------------------------------------------------------------------------- */
+int tbns_gemm_tc_supported(int Cin, int N, int taps);
+int tbns_gemm_tc(const void* A_bf16, const void* W_bf16, float* C, long long ldc, const float* bias, int Bimg, int Hg,
+                 int Wg, int Cin, int N, int taps, int flip, void* stream);
+/* fp32 -> bf16 (round-to-nearest-even) copy; in/out 16-byte aligned */
+int tbns_cast_bf16(const float* in, void* out, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (nn.LayerNorm(hidden_dim), eps 1e-5):
  *   model/Transolver_Structured_Mesh_2D.py:59,63,66 and forward :70-73
  * ------------------------------------------------------------------------------------------- */

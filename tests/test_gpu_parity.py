@@ -84,7 +84,7 @@ def test_gemm_conv_modes(dev, Bt, Hg, Wg, C, I2):
     Wx = torch.randn(I, C, 3, 3, generator=g)
     Wfx = torch.randn(I, C, 3, 3, generator=g)
     bx, bfx = torch.randn(I, generator=g), torch.randn(I, generator=g)
-    Wf, Wd, bcat = ops.pack_proj_weights(Wx.to(dev), bx.to(dev), Wfx.to(dev), bfx.to(dev))
+    Wf, Wd, bcat, _, _ = ops.pack_proj_weights(Wx.to(dev), bx.to(dev), Wfx.to(dev), bfx.to(dev))
     XF = torch.empty(Bt * N, I2, device=dev)
     ops.gemm(M=Bt * N, N=I2, K=9 * C, A=x.to(dev), lda=C, a_kind=0, B=Wf, ldb=9 * C, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Hg,
              Wg=Wg, Cin=C, bias=bcat)

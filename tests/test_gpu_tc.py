@@ -1,0 +1,80 @@
+"""GPU tests of the tcgen05/TMA/TMEM implicit-GEMM kernel (tbns_gemm_tc) against the already-verified fp32 SIMT
+engine run in bf16-operand mode (identical operand rounding, so only the fp32 summation order differs) and against
+the CPU oracle on bf16-rounded inputs."""
+import pytest
+import torch
+
+from oracle import physics_attention as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(t):
+    from transformerbasednavierstokesolver_b200 import _lib
+    out = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().tbns_cast_bf16(t.data_ptr(), out.data_ptr(), t.numel(), torch.cuda.current_stream().cuda_stream), "cast")
+    return out
+
+
+def _tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps, flip):
+    from transformerbasednavierstokesolver_b200 import _lib
+    _lib.check(_lib.load().tbns_gemm_tc(A16.data_ptr(), W16.data_ptr(), C.data_ptr(), C.shape[-1], None if bias is None else bias.data_ptr(),
+                                        Bimg, Hg, Wg, Cin, N, taps, flip, torch.cuda.current_stream().cuda_stream), "tbns_gemm_tc")
+
+
+def test_cast_bf16_matches_torch():
+    dev = torch.device("cuda:0")
+    x = torch.randn(1000003, device=dev)[:1000000 - 8].contiguous()  # odd length exercises the tail
+    x = torch.randn(999997 + 3, device=dev)
+    y = _bf16(x)
+    assert torch.equal(y, x.bfloat16())
+
+
+@pytest.mark.parametrize("Bimg,Hg,Wg,C,I2", [(2, 64, 64, 256, 512), (1, 85, 85, 128, 256), (1, 12, 10, 64, 128), (3, 7, 33, 64, 64)])
+def test_tc_conv_fprop_and_dgrad(Bimg, Hg, Wg, C, I2):
+    from transformerbasednavierstokesolver_b200 import ops
+    from transformerbasednavierstokesolver_b200._lib import TBNS_PREC_BF16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(Hg * Wg + C)
+    I = I2 // 2
+    N = Hg * Wg
+    x = torch.randn(Bimg, N, C, generator=g).to(dev)
+    Wx = (torch.randn(I, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(dev)
+    Wfx = (torch.randn(I, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(dev)
+    bx, bfx = torch.randn(I, generator=g).to(dev), torch.randn(I, generator=g).to(dev)
+    Wf, Wd, bcat, _, _ = ops.pack_proj_weights(Wx, bx, Wfx, bfx)
+    # fprop
+    ref = torch.empty(Bimg * N, I2, device=dev)
+    ops.gemm(M=Bimg * N, N=I2, K=9 * C, A=x, lda=C, a_kind=0, B=Wf, ldb=9 * C, b_kind=0, C=ref, ldc=I2, conv_mode=1, Hg=Hg, Wg=Wg,
+             Cin=C, bias=bcat, precision=TBNS_PREC_BF16)
+    out = torch.full((Bimg * N, I2), float("nan"), device=dev)
+    _tc(_bf16(x), _bf16(Wf), out, bcat, Bimg, Hg, Wg, C, I2, 9, 0)
+    torch.cuda.synchronize()
+    assert O.rel_l2(out.cpu(), ref.cpu()) < 1e-5
+    cpu = O.proj_fwd(x.cpu().bfloat16().double(), Wx.cpu().bfloat16().double(), bx.cpu().double(), Wfx.cpu().bfloat16().double(),
+                     bfx.cpu().double(), (Hg, Wg))
+    assert O.rel_l2(out.cpu().reshape(Bimg, N, I2), cpu) < 1e-5
+    # dgrad (transposed convolution): A = dXF [.., 2I], W = Wd [C, 9*2I]
+    if C % 64 == 0 and I2 % 64 == 0:
+        dXF = torch.randn(Bimg, N, I2, generator=g).to(dev)
+        ref2 = torch.empty(Bimg, N, C, device=dev)
+        ops.gemm(M=Bimg * N, N=C, K=9 * I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=ref2, ldc=C, conv_mode=1, Hg=Hg,
+                 Wg=Wg, Cin=I2, flip=1, precision=TBNS_PREC_BF16)
+        out2 = torch.full((Bimg, N, C), float("nan"), device=dev)
+        _tc(_bf16(dXF), _bf16(Wd), out2, None, Bimg, Hg, Wg, I2, C, 9, 1)
+        torch.cuda.synchronize()
+        assert O.rel_l2(out2.cpu(), ref2.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(972, 128, 256), (128, 64, 64), (5000, 256, 512), (81920, 256, 256)])
+def test_tc_linear(M, K, N):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + K + N)
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    out = torch.full((M, N), float("nan"), device=dev)
+    _tc(_bf16(A), _bf16(W), out, bias, 1, 1, M, K, N, 1, 0)
+    torch.cuda.synchronize()
+    ref = A.bfloat16().double() @ W.bfloat16().double().t() + bias.double()
+    assert O.rel_l2(out.cpu(), ref.cpu()) < 1e-5

@@ -48,6 +48,9 @@ _SIGS = {
     "tbns_version": (_i, []),
     "tbns_device_ok": (_i, []),
     "tbns_gemm": (_i, [C.POINTER(GemmDesc), _fp]),
+    "tbns_gemm_tc_supported": (_i, [_i, _i, _i]),
+    "tbns_gemm_tc": (_i, [_fp, _fp, _fp, _ll, _fp, _i, _i, _i, _i, _i, _i, _i, _fp]),
+    "tbns_cast_bf16": (_i, [_fp, _fp, _ll, _fp]),
     "tbns_layernorm_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, C.c_float, _fp]),
     "tbns_layernorm_bwd_ws_floats": (C.c_size_t, [_i]),
     "tbns_layernorm_bwd": (_i, [_fp] * 10 + [_i, _i, _fp]),

@@ -62,13 +62,13 @@ class _PhysicsAttentionBase(nn.Module):
                                       "(every reference script uses dropout=0.0)")
         B, N, C = x.shape
         grid = self._grid((B, N, C))
-        Wf, Wd, bcat = self._packed_weights()
+        packed = self._packed_weights()
         prec = ops.PRECISIONS[self.precision or config.get_default_precision()]
         lin = self.to_out[0]
         return ops.PhysicsAttentionFn.apply(
             x.float(), residual, self.temperature, self.in_project_x.weight, self.in_project_x.bias, self.in_project_fx.weight,
             self.in_project_fx.bias, self.in_project_slice.weight, self.in_project_slice.bias, self.to_q.weight, self.to_k.weight,
-            self.to_v.weight, lin.weight, lin.bias, Wf, Wd, bcat, self.heads, grid, prec)
+            self.to_v.weight, lin.weight, lin.bias, packed, self.heads, grid, prec)
 
 
 class Physics_Attention_Irregular_Mesh(_PhysicsAttentionBase):

@@ -122,6 +122,26 @@ def colsum(inp: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
     return out
 
 
+def cast_bf16(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 copy (round to nearest even) through libtbns"""
+    out = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    check(_lib.load().tbns_cast_bf16(_p(t), _p(out), t.numel(), _stream()), "tbns_cast_bf16")
+    _count(1)
+    return out
+
+
+def tc_supported(Cin: int, N: int, taps: int) -> bool:
+    return bool(_lib.load().tbns_gemm_tc_supported(Cin, N, taps))
+
+
+def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps, flip, tag=None):
+    """tcgen05 implicit GEMM (include/tbns.h: tbns_gemm_tc)"""
+    with _Timed(tag):
+        check(_lib.load().tbns_gemm_tc(_p(A16), _p(W16), _p(C), C.shape[-1], _p(bias), Bimg, Hg, Wg, Cin, N, taps, flip, _stream()),
+              "tbns_gemm_tc")
+    _count(1)
+
+
 # ------------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------------
@@ -182,14 +202,19 @@ def pack_proj_weights(Wx, bx, Wfx, bfx):
     check(_lib.load().tbns_pack_proj_weights(_p(Wx), _p(bx), _p(Wfx), _p(bfx), _p(Wf), _p(Wd), _p(bcat), I, C_, taps, _stream()),
           "tbns_pack_proj_weights")
     _count(1)
-    return Wf, Wd, bcat
+    Wf16 = Wd16 = None
+    if tc_supported(C_, 2 * I, taps):
+        Wf16 = cast_bf16(Wf)
+    if tc_supported(2 * I, C_, taps):
+        Wd16 = cast_bf16(Wd)
+    return Wf, Wd, bcat, Wf16, Wd16
 
 
 # ------------------------------------------------------------------------------------------------
 # Physics-Attention forward / backward
 # ------------------------------------------------------------------------------------------------
 def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, heads: int,
-               grid: Optional[Tuple[int, int]], precision: int):
+               grid: Optional[Tuple[int, int]], precision: int, Wf16=None):
     """returns (out, saved tuple). x [B,N,C]; Wf/bcat packed projections; residual [B,N,Cout] or None."""
     lib = _lib.load()
     B, N, C_ = x.shape
@@ -205,7 +230,11 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
     structured = grid is not None
     # (1a) projections: XF = [x_mid | fx_mid]   Physics_Attention.py:94-97 / :36-39
     XF = torch.empty(B * N, I2, **f32)
-    if structured:
+    if precision == TBNS_PREC_BF16 and Wf16 is not None:
+        # tensor-core path: bf16 operands through TMA, tcgen05.mma, fp32 accumulate in TMEM
+        Hg, Wg = grid if structured else (1, N)
+        gemm_tc(cast_bf16(x), Wf16, XF, bcat, B, Hg, Wg, C_, I2, 9 if structured else 1, 0, tag="proj_fprop")
+    elif structured:
         Hg, Wg = grid
         gemm(M=B * N, N=I2, K=9 * C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=9 * C_, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Hg,
              Wg=Wg, Cin=C_, bias=bcat, precision=precision, tag="proj_fprop")
@@ -234,7 +263,7 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
 
 
 def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, saved, heads: int,
-                grid: Optional[Tuple[int, int]], precision: int):
+                grid: Optional[Tuple[int, int]], precision: int, Wd16=None):
     """returns dx and the parameter gradients in reference (state_dict) layouts."""
     lib = _lib.load()
     XF, w, s, tok, q, k, v, A, O, P = saved
@@ -285,16 +314,21 @@ def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, save
     dx = torch.empty(B, N, C_, **f32)
     dWx = torch.empty(Wx_shape, **f32)
     dWfx = torch.empty(Wx_shape, **f32)
-    if structured:
-        Hg, Wg = grid
+    Hg, Wg = grid if structured else (1, N)
+    if precision == TBNS_PREC_BF16 and Wd16 is not None:
+        gemm_tc(cast_bf16(dXF), Wd16, dx, None, B, Hg, Wg, I2, C_, taps, 1, tag="proj_dgrad")
+    elif structured:
         gemm(M=B * N, N=C_, K=9 * I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=dx, ldc=C_, conv_mode=1, Hg=Hg, Wg=Wg,
              Cin=I2, flip=1, precision=precision, tag="proj_dgrad")
+    else:
+        gemm(M=B * N, N=C_, K=I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=I2, b_kind=0, C=dx, ldc=C_, precision=precision,
+             tag="proj_dgrad")
+    if structured:
         gemm(M=9 * C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, conv_mode=2, Hg=Hg, Wg=Wg, Cin=C_,
              precision=precision, split_k=_split_k(9 * C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=9, tag="proj_wgrad")
     else:
-        gemm(M=B * N, N=C_, K=I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=I2, b_kind=0, C=dx, ldc=C_, precision=precision)
         gemm(M=C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, Cin=C_, precision=precision,
-             split_k=_split_k(C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=1)
+             split_k=_split_k(C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=1, tag="proj_wgrad")
     dbcat = colsum(dXF, B * N, I2)
     return dx, dict(temperature=dtemp.view(1, H, 1, 1), Wx=dWx, bx=dbcat[:I], Wfx=dWfx, bfx=dbcat[I:], Ws=dWs, bs=dbs,
                     Wq=dWqkv[0], Wk=dWqkv[1], Wv=dWqkv[2], Wo=dWo, bo=dbo)
@@ -305,15 +339,17 @@ class PhysicsAttentionFn(torch.autograd.Function):
     copies (non-differentiable inputs, refreshed by the module when the masters change)."""
 
     @staticmethod
-    def forward(ctx, x, residual, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, Wf, Wd, bcat, heads, grid, precision):
+    def forward(ctx, x, residual, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, packed, heads, grid, precision):
         x = x.contiguous()
         if residual is not None:
             residual = residual.contiguous()
+        Wf, Wd, bcat, Wf16, Wd16 = packed
         _chk(x, residual, temperature, Ws, bs, Wq, Wk, Wv, Wo, bo, Wf, Wd, bcat)
         temperature_c = temperature.contiguous()
         out, saved = pa_forward(x, temperature_c, Wf, bcat, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
-                                Wv.contiguous(), Wo.contiguous(), bo.contiguous(), residual, heads, grid, precision)
+                                Wv.contiguous(), Wo.contiguous(), bo.contiguous(), residual, heads, grid, precision, Wf16)
         ctx.save_for_backward(x, temperature_c, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved)
+        ctx.Wd16 = Wd16
         ctx.cfg = (heads, grid, precision, tuple(Wx.shape), residual is not None)
         return out
 
@@ -323,9 +359,9 @@ class PhysicsAttentionFn(torch.autograd.Function):
         x, temperature, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved = ctx.saved_tensors
         dout = dout.contiguous()
         dx, g = pa_backward(dout, x, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
-                            Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision)
+                            Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16)
         return (dx, dout if has_res else None, g["temperature"], g["Wx"], g["bx"], g["Wfx"], g["bfx"], g["Ws"], g["bs"], g["Wq"],
-                g["Wk"], g["Wv"], g["Wo"], g["bo"], None, None, None, None, None, None)
+                g["Wk"], g["Wv"], g["Wo"], g["bo"], None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------
