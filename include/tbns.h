@@ -76,9 +76,38 @@ int tbns_gemm(const tbns_gemm_desc* d, void* stream);
  *   flip=1: its transposed convolution (dgrad); taps=1: nn.Linear (:36-39; use Hg=1, Wg=#tokens).
  * Shapes: Cin % 64 == 0, N % 64 == 0 (tbns_gemm_tc_supported); other shapes go through tbns_gemm.
  * ------------------------------------------------------------------------------------------- */
+typedef struct tbns_tc_desc {
+  const void* A16;              /* bf16 activations [Bimg*Hg*Wg, Cin]                                  */
+  int Bimg, Hg, Wg, Cin, taps, flip;
+  const void* W16;              /* bf16 weights [w_batched ? Bimg : 1][N][taps*Cin]                     */
+  int N, w_batched;             /* w_batched=1: image b uses its own weight matrix (deslice: P[b])      */
+  const float* bias;            /* [N] or NULL                                                          */
+  int act;                      /* as tbns_gemm_desc.act                                                */
+  float* aux_out; const float* aux_in; long long ldaux;
+  const float* residual; long long ldr;
+  float* C; long long ldc;      /* fp32 output or NULL                                                  */
+  void* C16; long long ldc16;   /* bf16 output or NULL (operand of the next tensor-core contraction)    */
+} tbns_tc_desc;
 int tbns_gemm_tc_supported(int Cin, int N, int taps);
-int tbns_gemm_tc(const void* A_bf16, const void* W_bf16, float* C, long long ldc, const float* bias, int Bimg, int Hg,
-                 int Wg, int Cin, int N, int taps, int flip, void* stream);
+int tbns_gemm_tc(const tbns_tc_desc* d, void* stream);
+
+/* Token-contraction ("wgrad") tensor-core GEMM, both operands token-major (MN-major UMMA descriptors):
+ *   D[(tap, a), n] = sum_token A[shift(token, tap), a] * B[token, n]
+ * conv/linear weight gradients (SURVEY §8 a-bwd: dW_x = corr(x, dX), dW_fx = corr(x, dF)), MLP weight gradients and
+ * dP = w^T dOut (batched=1: one output per image).  fp32 partials of `split_k` token ranges go to ws
+ * (split_k * batch * taps*Ma * Nb floats) and are reduced in a fixed order; the result is written to C
+ * ([batch][taps*Ma][Nb], ldc/sC) or, with scatter=1, straight into the Conv2d/Linear weight.grad layout
+ * (see tbns_gemm_desc.scatter).  Shapes: Ma % 128 == 0, Nb % 64 == 0. */
+typedef struct tbns_tc_wgrad_desc {
+  const void* A16; int Ma;      /* bf16 [Bimg*Hg*Wg, Ma]                                                */
+  const void* B16; int Nb;      /* bf16 [Bimg*Hg*Wg, Nb]                                                */
+  int Bimg, Hg, Wg, taps, batched;
+  int split_k; float* ws;
+  float* C; long long ldc, sC;
+  int scatter, I; float* Cx; float* Cfx;
+} tbns_tc_wgrad_desc;
+int tbns_gemm_tc_wgrad_supported(int Ma, int Nb, int taps);
+int tbns_gemm_tc_wgrad(const tbns_tc_wgrad_desc* d, void* stream);
 /* fp32 -> bf16 (round-to-nearest-even) copy; in/out 16-byte aligned */
 int tbns_cast_bf16(const float* in, void* out, long long n, void* stream);
 

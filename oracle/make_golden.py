@@ -109,6 +109,21 @@ def ckpt_block(name, seed, layer=3, Hg=12, Wg=10, B=1):
     torch.save(d, os.path.join(OUT, name))
 
 
+def _sharpen(m):
+    """trunc_normal(0.02) init leaves the slice softmax and the token attention numerically uniform, which makes
+    their gradients pure cancellation noise; give the fixture models trained-like magnitudes instead."""
+    with torch.no_grad():
+        for blk in m.blocks:
+            a = blk.Attn
+            a.in_project_slice.weight.mul_(40.0)
+            a.in_project_slice.bias.normal_(0, 0.3)
+            a.to_q.weight.mul_(20.0)
+            a.to_k.weight.mul_(20.0)
+            a.to_v.weight.mul_(5.0)
+            a.temperature.copy_(torch.linspace(0.3, 1.2, a.heads).reshape(1, -1, 1, 1))
+            a.in_project_x.weight.mul_(3.0)
+
+
 def model_2d(name, seed, unified_pos, rollout_steps=3):
     T = ref.transolver_2d()
     torch.manual_seed(seed)
@@ -116,6 +131,7 @@ def model_2d(name, seed, unified_pos, rollout_steps=3):
               out_dim=1, slice_num=8, ref=4, unified_pos=unified_pos, H=8, W=7)
     with ref.cpu_cuda_identity():
         m = T.Model(**kw).double()
+    _sharpen(m)
     if unified_pos:
         m.pos = m.pos.double()
     x = torch.rand(2, 56, 2).double()
@@ -146,6 +162,7 @@ def model_irregular(name, seed):
     kw = dict(space_dim=2, n_layers=2, n_hidden=32, dropout=0.0, n_head=4, Time_Input=False, mlp_ratio=2, fun_dim=0,
               out_dim=1, slice_num=8, ref=8, unified_pos=0)
     m = T.Model(**kw).double()
+    _sharpen(m)
     x = torch.rand(1, 45, 2).double()
     y = torch.randn(1, 45, 1).double()
     loss_fn = ref.testloss().TestLoss(size_average=False)

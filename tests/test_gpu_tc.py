@@ -16,10 +16,9 @@ def _bf16(t):
     return out
 
 
-def _tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps, flip):
-    from transformerbasednavierstokesolver_b200 import _lib
-    _lib.check(_lib.load().tbns_gemm_tc(A16.data_ptr(), W16.data_ptr(), C.data_ptr(), C.shape[-1], None if bias is None else bias.data_ptr(),
-                                        Bimg, Hg, Wg, Cin, N, taps, flip, torch.cuda.current_stream().cuda_stream), "tbns_gemm_tc")
+def _tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps, flip, **kw):
+    from transformerbasednavierstokesolver_b200 import ops
+    ops.gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps, flip, **kw)
 
 
 def test_cast_bf16_matches_torch():
@@ -77,4 +76,75 @@ def test_tc_linear(M, K, N):
     _tc(_bf16(A), _bf16(W), out, bias, 1, 1, M, K, N, 1, 0)
     torch.cuda.synchronize()
     ref = A.bfloat16().double() @ W.bfloat16().double().t() + bias.double()
+    assert O.rel_l2(out.cpu(), ref.cpu()) < 1e-5
+
+
+def test_tc_epilogues_and_batched_weights():
+    """bias + GELU (+pre side output) / GELU' multiply / residual / bf16 output / per-image weight matrices"""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    Bimg, Ntok, K, N = 3, 200, 128, 192
+    A = torch.randn(Bimg, Ntok, K, generator=g).to(dev)
+    W = (torch.randn(Bimg, N, K, generator=g) / K ** 0.5).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(Bimg, Ntok, N, generator=g).to(dev)
+    A64, W64 = A.bfloat16().double(), W.bfloat16().double()
+    base = torch.einsum("bmk,bnk->bmn", A64, W64)
+    # batched weights + bias + residual, fp32 and bf16 outputs
+    out = torch.full((Bimg, Ntok, N), float("nan"), device=dev)
+    out16 = torch.empty(Bimg, Ntok, N, device=dev, dtype=torch.bfloat16)
+    _tc(_bf16(A), _bf16(W), out, bias, Bimg, 1, Ntok, K, N, 1, 0, C16=out16, w_batched=1, residual=res)
+    ref = base + bias.double() + res.double()
+    assert O.rel_l2(out.cpu(), ref.cpu()) < 1e-5
+    assert torch.equal(out16, out.bfloat16())
+    # GELU with pre-activation side output (shared weights = image 0's matrix)
+    pre = torch.empty(Bimg, Ntok, N, device=dev)
+    _tc(_bf16(A), _bf16(W[0].contiguous()), out, bias, Bimg, 1, Ntok, K, N, 1, 0, act=1, aux_out=pre)
+    pre_ref = torch.einsum("bmk,nk->bmn", A64, W64[0]) + bias.double()
+    assert O.rel_l2(pre.cpu(), pre_ref.cpu()) < 1e-5
+    assert O.rel_l2(out.cpu(), O.gelu(pre_ref).cpu()) < 1e-5
+    # GELU' multiply
+    aux = (pre_ref / 3).float()
+    _tc(_bf16(A), _bf16(W[0].contiguous()), out, None, Bimg, 1, Ntok, K, N, 1, 0, act=2, aux_in=aux)
+    assert O.rel_l2(out.cpu(), (torch.einsum("bmk,nk->bmn", A64, W64[0]) * O.gelu_grad(aux.double())).cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("Bimg,Hg,Wg,C,I2", [(2, 64, 64, 256, 512), (1, 85, 85, 128, 256), (3, 7, 33, 128, 64)])
+def test_tc_conv_wgrad(Bimg, Hg, Wg, C, I2):
+    """conv weight gradient on tensor cores (MN-major operands) vs the SIMT engine in bf16-operand mode"""
+    from transformerbasednavierstokesolver_b200 import ops
+    from transformerbasednavierstokesolver_b200._lib import TBNS_PREC_BF16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(Hg + Wg + C)
+    I = I2 // 2
+    N = Hg * Wg
+    x = torch.randn(Bimg, N, C, generator=g).to(dev)
+    dXF = torch.randn(Bimg, N, I2, generator=g).to(dev)
+    rWx, rWfx = torch.empty(I, C, 3, 3, device=dev), torch.empty(I, C, 3, 3, device=dev)
+    ops.gemm(M=9 * C, N=I2, K=Bimg * N, A=x, lda=C, a_kind=1, B=dXF, ldb=I2, b_kind=1, conv_mode=2, Hg=Hg, Wg=Wg, Cin=C,
+             precision=TBNS_PREC_BF16, split_k=4, scatter=(rWx, rWfx), I=I, taps=9)
+    dWx = torch.full((I, C, 3, 3), float("nan"), device=dev)
+    dWfx = torch.full((I, C, 3, 3), float("nan"), device=dev)
+    ops.gemm_tc_wgrad(_bf16(x), _bf16(dXF), Bimg, Hg, Wg, C, I2, taps=9, scatter=(dWx, dWfx), I=I)
+    torch.cuda.synchronize()
+    assert O.rel_l2(dWx.cpu(), rWx.cpu()) < 1e-5
+    assert O.rel_l2(dWfx.cpu(), rWfx.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("Bimg,Ntok,Ma,Nb,batched", [(1, 5000, 256, 256, 0), (4, 972, 512, 128, 1), (2, 4096, 256, 256, 1), (20, 4096, 128, 64, 0)])
+def test_tc_plain_wgrad(Bimg, Ntok, Ma, Nb, batched):
+    """D = A^T B over tokens (MLP weight gradients; batched = dP = w^T dOut per image)"""
+    from transformerbasednavierstokesolver_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(Ntok + Ma)
+    A = torch.randn(Bimg, Ntok, Ma, generator=g).to(dev)
+    Bm = torch.randn(Bimg, Ntok, Nb, generator=g).to(dev)
+    batch = Bimg if batched else 1
+    out = torch.full((batch, Ma, Nb), float("nan"), device=dev)
+    ops.gemm_tc_wgrad(_bf16(A), _bf16(Bm), Bimg, 1, Ntok, Ma, Nb, taps=1, batched=batched, C=out)
+    torch.cuda.synchronize()
+    A64, B64 = A.bfloat16().double(), Bm.bfloat16().double()
+    ref = torch.einsum("bta,btn->ban", A64, B64)
+    if not batched:
+        ref = ref.sum(0, keepdim=True)
     assert O.rel_l2(out.cpu(), ref.cpu()) < 1e-5

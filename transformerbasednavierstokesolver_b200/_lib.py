@@ -39,6 +39,31 @@ class GemmDesc(C.Structure):
     ]
 
 
+class TcDesc(C.Structure):
+    """mirror of `tbns_tc_desc`"""
+    _fields_ = [
+        ("A16", _fp), ("Bimg", _i), ("Hg", _i), ("Wg", _i), ("Cin", _i), ("taps", _i), ("flip", _i),
+        ("W16", _fp), ("N", _i), ("w_batched", _i),
+        ("bias", _fp), ("act", _i),
+        ("aux_out", _fp), ("aux_in", _fp), ("ldaux", _ll),
+        ("residual", _fp), ("ldr", _ll),
+        ("C", _fp), ("ldc", _ll),
+        ("C16", _fp), ("ldc16", _ll),
+    ]
+
+
+class TcWgradDesc(C.Structure):
+    """mirror of `tbns_tc_wgrad_desc`"""
+    _fields_ = [
+        ("A16", _fp), ("Ma", _i),
+        ("B16", _fp), ("Nb", _i),
+        ("Bimg", _i), ("Hg", _i), ("Wg", _i), ("taps", _i), ("batched", _i),
+        ("split_k", _i), ("ws", _fp),
+        ("C", _fp), ("ldc", _ll), ("sC", _ll),
+        ("scatter", _i), ("I", _i), ("Cx", _fp), ("Cfx", _fp),
+    ]
+
+
 class TbnsError(RuntimeError):
     pass
 
@@ -49,7 +74,9 @@ _SIGS = {
     "tbns_device_ok": (_i, []),
     "tbns_gemm": (_i, [C.POINTER(GemmDesc), _fp]),
     "tbns_gemm_tc_supported": (_i, [_i, _i, _i]),
-    "tbns_gemm_tc": (_i, [_fp, _fp, _fp, _ll, _fp, _i, _i, _i, _i, _i, _i, _i, _fp]),
+    "tbns_gemm_tc": (_i, [C.POINTER(TcDesc), _fp]),
+    "tbns_gemm_tc_wgrad_supported": (_i, [_i, _i, _i]),
+    "tbns_gemm_tc_wgrad": (_i, [C.POINTER(TcWgradDesc), _fp]),
     "tbns_cast_bf16": (_i, [_fp, _fp, _ll, _fp]),
     "tbns_layernorm_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, C.c_float, _fp]),
     "tbns_layernorm_bwd_ws_floats": (C.c_size_t, [_i]),

@@ -11,6 +11,7 @@
 namespace tbns {
 
 void set_error(const char* fmt, ...);
+int splitk_reduce(const tbns_gemm_desc& d, cudaStream_t st);  // gemm_simt.cu
 
 #define TBNS_REQUIRE(cond, ...)          \
   do {                                   \

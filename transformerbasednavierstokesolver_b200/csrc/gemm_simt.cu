@@ -274,6 +274,18 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const tbns_gemm
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// fixed-order reduction of split-K partials ws[split][batch][M][N] followed by the descriptor's epilogue / scatter
+int splitk_reduce(const tbns_gemm_desc& d, cudaStream_t st) {
+  const int vecC = !d.scatter && al16(d.C) && (d.ldc % 4 == 0) && (d.sC % 4 == 0) && (d.N % 4 == 0) && (!d.bias || al16(d.bias)) &&
+                   (!d.residual || (al16(d.residual) && d.ldr % 4 == 0 && d.sR % 4 == 0)) && !(d.aux_out || d.aux_in);
+  const long long total = (long long)d.batch * d.M * ((d.N + 3) / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  gemm_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(d, vecC);
+  TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
+}
+
 }  // namespace tbns
 
 using namespace tbns;

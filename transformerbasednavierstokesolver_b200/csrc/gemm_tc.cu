@@ -26,13 +26,30 @@ constexpr int TC_UK = 16;       // UMMA K for 16-bit inputs
 constexpr int TC_THREADS = 192;
 
 struct TcParams {
-  float* C;
+  float* C;                 // fp32 output (or nullptr)
   long long ldc;
-  const float* bias;
+  __nv_bfloat16* C16;       // bf16 output (or nullptr)
+  long long ldc16;
+  const float* bias;        // [N]
+  const float* residual;    // [rows, ldr]
+  long long ldr;
+  int act;                  // 0 none, 1 GELU(erf) (pre-activation -> aux_out), 2 multiply by GELU'(aux_in)
+  float* aux_out;
+  const float* aux_in;
+  long long ldaux;
   int Bimg, Hg, Wg, Cin, taps, flip;
-  int BW, BH;          // the 128-token M tile is a BH x BW patch of the grid (BW*BH == 128)
+  int BW, BH;               // the 128-token M tile is a BH x BW patch of the grid (BW*BH == 128)
   int tiles_w, tiles_h;
-  int N;
+  int N, w_batched;
+};
+
+struct WgParams {
+  float* ws;                // [split][batch][Mtot][Nb] fp32 partials
+  int Mtot, Ma, Nb;
+  int Bimg, Hg, Wg, taps;
+  int BW, BH, tiles_w, tiles_h;  // the 64-token K block is a BH x BW patch (BW*BH == 64)
+  int m_chunks, n_chunks;
+  int batched, split_k;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -69,6 +86,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -82,9 +104,21 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                           // layout type SWIZZLE_128B [61,64)
   return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// MN-major, 128B-swizzled operand: panels of 64 MN-elements (128 B) x K rows; 8-row atoms of 1024 B along K (SBO),
+// `panel_bytes` between consecutive 64-element MN panels (LBO).  (cute/atom/mma_traits_sm100.hpp canonical MN layout)
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr, uint32_t panel_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((panel_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, M=128, N=n; mn_major=1 -> both operands MN-major (token-major wgrad operands)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int mn_major = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(TC_BM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -122,34 +156,13 @@ struct TcSmem {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
+// shared prologue: barrier init (one thread), TMEM allocation (warp 1), returns the TMEM base address
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using S = TcSmem<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t bar_full = base + S::BAR_OFF;
-  const uint32_t bar_empty = bar_full + STAGES * 8;
-  const uint32_t bar_acc = bar_empty + STAGES * 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR_OFF + (2 * STAGES + 1) * 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int mt = blockIdx.x;
-  const int tw = mt % p.tiles_w;
-  const int th = (mt / p.tiles_w) % p.tiles_h;
-  const int bimg = mt / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.BW, h0 = th * p.BH;
-  const int n0 = blockIdx.y * BN;
-  const int kc_per_tap = p.Cin / TC_BK;
-  const int nkb = p.taps * kc_per_tap;
-
+__device__ __forceinline__ uint32_t tc_prologue(uint32_t bar_full, uint32_t bar_empty, uint32_t bar_acc, volatile uint32_t* tmem_slot,
+                                                const CUtensorMap* tmA, const CUtensorMap* tmB, int warp, int lane) {
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + s * 8, 1);
       mbar_init(bar_empty + s * 8, 1);
@@ -166,11 +179,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  return *tmem_slot;
+}
+
+template <int BN>
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base, int warp) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TN kernel: C[token, n] = sum_k A[shift(token), k] W[n, k]   (both operands K-major)
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using S = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bar_full = base + S::BAR_OFF;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_acc = bar_empty + STAGES * 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR_OFF + (2 * STAGES + 1) * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int mt = blockIdx.x;
+  const int tw = mt % p.tiles_w;
+  const int th = (mt / p.tiles_w) % p.tiles_h;
+  const int bimg = mt / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.BW, h0 = th * p.BH;
+  const int n0 = blockIdx.y * BN;
+  const int kc_per_tap = p.Cin / TC_BK;
+  const int nkb = p.taps * kc_per_tap;
+
+  const uint32_t tmem_base = tc_prologue<BN, STAGES>(bar_full, bar_empty, bar_acc, tmem_slot, &tmA, &tmB, warp, lane);
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      const int wb = p.w_batched ? bimg : 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -186,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sb = sa + S::A_BYTES;
         mbar_expect_tx(bar_full + s * 8, S::STAGE_BYTES);
         tma_load_4d(sa, &tmA, bar_full + s * 8, kc * TC_BK, w0 + dx, h0 + dy, bimg);
-        tma_load_2d(sb, &tmB, bar_full + s * 8, kb * TC_BK, n0);
+        tma_load_3d(sb, &tmB, bar_full + s * 8, kb * TC_BK, n0, wb);
       }
     }
   } else if (warp == 1) {
@@ -218,7 +271,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int h = h0 + hh, w = w0 + ww;
     const bool valid = (h < p.Hg) && (w < p.Wg);
     const long long grow = ((long long)bimg * p.Hg + h) * p.Wg + w;
-    float* crow = p.C + grow * p.ldc + n0;
     mbar_wait(bar_acc, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -226,24 +278,173 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       if (valid) {
+        const int n = n0 + c0;
+        if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.bias) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
-          *reinterpret_cast<float4*>(crow + c0 + j) = o;
+        }
+        if (p.act == 1) {
+          if (p.aux_out) {
+            float* ao = p.aux_out + grow * p.ldaux + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ao + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == 2) {
+          const float* ai = p.aux_in + grow * p.ldaux + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(ai + j);
+            v[j] *= gelu_erf_grad(a.x); v[j + 1] *= gelu_erf_grad(a.y); v[j + 2] *= gelu_erf_grad(a.z); v[j + 3] *= gelu_erf_grad(a.w);
+          }
+        }
+        if (p.residual) {
+          const float* rr = p.residual + grow * p.ldr + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(rr + j);
+            v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+          }
+        }
+        if (p.C) {
+          float* cr = p.C + grow * p.ldc + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (p.C16) {
+          __nv_bfloat16* cr = p.C16 + grow * p.ldc16 + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __nv_bfloat162 o[4] = {__floats2bfloat162_rn(v[j], v[j + 1]), __floats2bfloat162_rn(v[j + 2], v[j + 3]),
+                                   __floats2bfloat162_rn(v[j + 4], v[j + 5]), __floats2bfloat162_rn(v[j + 6], v[j + 7])};
+            *reinterpret_cast<uint4*>(cr + j) = *reinterpret_cast<uint4*>(o);
+          }
         }
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  tc_teardown<BN>(tmem_base, warp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NT ("wgrad") kernel: D[(tap, a), n] = sum_token A[shift(token, tap), a] * B[token, n]
+// Both operands are token-major in HBM, i.e. MN-major for the MMA: the SAME TMA boxes as above ([tokens][64 feat],
+// 128B swizzle) are consumed through MN-major UMMA descriptors, so no transposed copy of activations is ever made.
+// One CTA: 128 (a) x BN (n) output tile of one tap, over a contiguous range of 64-token K blocks (split-K);
+// fp32 partials go to ws[split][batch][Mtot][Nb] and are reduced in a fixed order by gemm_splitk_reduce_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_BKT = 64;  // tokens per K block
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgParams p) {
+  using S = TcSmem<BN, STAGES>;  // A: 2 panels x [64 tok][64 a] = 16 KB ; B: BN/64 panels x 8 KB
+  constexpr uint32_t PANEL = WG_BKT * 128;  // bytes of one [64 tokens][64 features] panel
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bar_full = base + S::BAR_OFF;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_acc = bar_empty + STAGES * 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR_OFF + (2 * STAGES + 1) * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x;
+  const int ni = tile % p.n_chunks;
+  const int mi = (tile / p.n_chunks) % p.m_chunks;
+  const int tap = tile / (p.n_chunks * p.m_chunks);
+  const int kbpi = p.tiles_w * p.tiles_h;  // K blocks per image
+  int e0, e1, bidx, split;
+  if (p.batched) {
+    bidx = blockIdx.y / p.split_k;
+    split = blockIdx.y - bidx * p.split_k;
+    const int per = (kbpi + p.split_k - 1) / p.split_k;
+    e0 = bidx * kbpi + min(kbpi, split * per);
+    e1 = bidx * kbpi + min(kbpi, (split + 1) * per);
+  } else {
+    bidx = 0;
+    split = blockIdx.y;
+    const int total = p.Bimg * kbpi;
+    const int per = (total + p.split_k - 1) / p.split_k;
+    e0 = min(total, split * per);
+    e1 = min(total, (split + 1) * per);
   }
+  const int nkb = e1 - e0;
+  int dy = 0, dx = 0;
+  if (p.taps == 9) {
+    dy = tap / 3 - 1;
+    dx = tap % 3 - 1;
+  }
+
+  const uint32_t tmem_base = tc_prologue<BN, STAGES>(bar_full, bar_empty, bar_acc, tmem_slot, &tmA, &tmB, warp, lane);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(bar_empty + s * 8, ph ^ 1);
+        const int e = e0 + i;
+        const int b = e / kbpi, rem = e - b * kbpi;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        const int h0 = th * p.BH, w0 = tw * p.BW;
+        const uint32_t sa = base + s * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+        mbar_expect_tx(bar_full + s * 8, S::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_4d(sa + j * PANEL, &tmA, bar_full + s * 8, mi * TC_BM + j * 64, w0 + dx, h0 + dy, b);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_4d(sb + j * PANEL, &tmB, bar_full + s * 8, ni * BN + j * 64, w0, h0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BN, 1);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(bar_full + s * 8, ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_BKT / TC_UK; ++k) {
+          const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * TC_UK * 128, PANEL);
+          const uint64_t bd = umma_desc_mnmajor_sw128(sb + k * TC_UK * 128, PANEL);
+          umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_empty + s * 8);
+      }
+      if (nkb > 0) umma_commit(bar_acc);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int batch = p.batched ? p.Bimg : 1;
+    float* orow = p.ws + (((long long)split * batch + bidx) * p.Mtot + (long long)tap * p.Ma + mi * TC_BM + r) * p.Nb + ni * BN;
+    if (nkb > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      if (nkb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  tc_teardown<BN>(tmem_base, warp);
 }
 
 // fp32 -> bf16 (round to nearest even), 8 elements per thread
@@ -295,6 +496,26 @@ static int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64
   return TBNS_OK;
 }
 
+// NHWC activation map [Bimg, Hg, Wg, F] with a {64, BW, BH, 1} box
+static int encode_act(CUtensorMap* m, const void* ptr, int Bimg, int Hg, int Wg, int F, int BW, int BH) {
+  cuuint64_t dims[4] = {(cuuint64_t)F, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)Bimg};
+  cuuint64_t str[3] = {(cuuint64_t)F * 2, (cuuint64_t)Wg * F * 2, (cuuint64_t)Hg * Wg * F * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)BW, (cuuint32_t)BH, 1u};
+  return encode_bf16(m, ptr, 4, dims, str, box);
+}
+
+// choose the BH x BW token patch (BW*BH == tokens) that wastes the fewest rows
+static int pick_bw(int Hg, int Wg, int tokens) {
+  int best = tokens;
+  double bestU = -1.0;
+  for (int bw = (tokens >= 128 ? 8 : 4); bw <= tokens; bw *= 2) {
+    const int bh = tokens / bw;
+    const double u = (double)Wg * Hg / ((double)cdiv(Wg, bw) * bw * (double)cdiv(Hg, bh) * bh);
+    if (u > bestU + 1e-9) { bestU = u; best = bw; }
+  }
+  return best;
+}
+
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
@@ -305,6 +526,18 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
   return TBNS_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgParams& p, int tiles, int gy, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  TBNS_CUDA(cudaFuncSetAttribute(gemm_tc_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  dim3 grid(tiles, gy);
+  gemm_tc_wgrad_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(tmA, tmB, p);
+  TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
+}
+
+static bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 }  // namespace tbns
 
 using namespace tbns;
@@ -312,7 +545,7 @@ using namespace tbns;
 extern "C" int tbns_cast_bf16(const float* in, void* out, long long n, void* stream) {
   TBNS_REQUIRE(in && out && n >= 0, "tbns_cast_bf16: bad args");
   if (n == 0) return TBNS_OK;
-  TBNS_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tbns_cast_bf16: unaligned");
+  TBNS_REQUIRE(al16p(in) && al16p(out), "tbns_cast_bf16: unaligned");
   const long long threads = (n + 7) / 8;
   cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
   TBNS_LAUNCH_CHECK();
@@ -323,49 +556,88 @@ extern "C" int tbns_gemm_tc_supported(int Cin, int N, int taps) {
   return (Cin > 0 && Cin % TC_BK == 0 && N >= 64 && N % 64 == 0 && (taps == 1 || taps == 9)) ? 1 : 0;
 }
 
-extern "C" int tbns_gemm_tc(const void* A_bf16, const void* W_bf16, float* C, long long ldc, const float* bias, int Bimg, int Hg,
-                            int Wg, int Cin, int N, int taps, int flip, void* stream) {
-  TBNS_REQUIRE(A_bf16 && W_bf16 && C, "tbns_gemm_tc: null pointer");
-  TBNS_REQUIRE(tbns_gemm_tc_supported(Cin, N, taps), "tbns_gemm_tc: unsupported shape Cin=%d N=%d taps=%d (need Cin%%64==0, N%%64==0)", Cin, N, taps);
-  TBNS_REQUIRE(Bimg > 0 && Hg > 0 && Wg > 0, "tbns_gemm_tc: bad dims");
-  TBNS_REQUIRE((reinterpret_cast<uintptr_t>(A_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(W_bf16) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
+  TBNS_REQUIRE(dp != nullptr, "tbns_gemm_tc: null descriptor");
+  const tbns_tc_desc& d = *dp;
+  TBNS_REQUIRE(d.A16 && d.W16 && (d.C || d.C16), "tbns_gemm_tc: null pointer");
+  TBNS_REQUIRE(tbns_gemm_tc_supported(d.Cin, d.N, d.taps), "tbns_gemm_tc: unsupported shape Cin=%d N=%d taps=%d (need Cin%%64==0, N%%64==0)",
+               d.Cin, d.N, d.taps);
+  TBNS_REQUIRE(d.Bimg > 0 && d.Hg > 0 && d.Wg > 0, "tbns_gemm_tc: bad dims");
+  TBNS_REQUIRE(d.act >= 0 && d.act <= 2 && (d.act != 2 || d.aux_in), "tbns_gemm_tc: bad activation spec");
+  TBNS_REQUIRE(al16p(d.A16) && al16p(d.W16) && (!d.C || (al16p(d.C) && d.ldc % 4 == 0)) && (!d.C16 || (al16p(d.C16) && d.ldc16 % 8 == 0)) &&
+                   (!d.bias || al16p(d.bias)) && (!d.residual || (al16p(d.residual) && d.ldr % 4 == 0)) &&
+                   (!(d.aux_out || d.aux_in) || d.ldaux % 4 == 0) && (!d.aux_out || al16p(d.aux_out)) && (!d.aux_in || al16p(d.aux_in)),
                "tbns_gemm_tc: operands must be 16-byte aligned");
-  // pick the BH x BW token patch (BW*BH == 128) that wastes the fewest MMA rows
-  int bestBW = 128;
-  double bestU = -1.0;
-  for (int bw = 8; bw <= 128; bw *= 2) {
-    const int bh = TC_BM / bw;
-    const double u = (double)Wg * Hg / ((double)cdiv(Wg, bw) * bw * (double)cdiv(Hg, bh) * bh);
-    if (u > bestU + 1e-9) { bestU = u; bestBW = bw; }
-  }
   TcParams p;
-  p.C = C; p.ldc = ldc; p.bias = bias;
-  p.Bimg = Bimg; p.Hg = Hg; p.Wg = Wg; p.Cin = Cin; p.taps = taps; p.flip = flip;
-  p.BW = bestBW; p.BH = TC_BM / bestBW;
-  p.tiles_w = cdiv(Wg, p.BW); p.tiles_h = cdiv(Hg, p.BH);
-  p.N = N;
-  const long long m_tiles = (long long)Bimg * p.tiles_w * p.tiles_h;
+  p.C = d.C; p.ldc = d.ldc; p.C16 = reinterpret_cast<__nv_bfloat16*>(d.C16); p.ldc16 = d.ldc16;
+  p.bias = d.bias; p.residual = d.residual; p.ldr = d.ldr;
+  p.act = d.act; p.aux_out = d.aux_out; p.aux_in = d.aux_in; p.ldaux = d.ldaux;
+  p.Bimg = d.Bimg; p.Hg = d.Hg; p.Wg = d.Wg; p.Cin = d.Cin; p.taps = d.taps; p.flip = d.flip;
+  p.BW = pick_bw(d.Hg, d.Wg, TC_BM); p.BH = TC_BM / p.BW;
+  p.tiles_w = cdiv(d.Wg, p.BW); p.tiles_h = cdiv(d.Hg, p.BH);
+  p.N = d.N; p.w_batched = d.w_batched;
+  const long long m_tiles = (long long)d.Bimg * p.tiles_w * p.tiles_h;
   TBNS_REQUIRE(m_tiles <= 0x7fffffffLL, "tbns_gemm_tc: too many tiles");
 
   CUtensorMap tmA, tmB;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)Bimg};
-    cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wg * Cin * 2, (cuuint64_t)Hg * Wg * Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
-    int rc = encode_bf16(&tmA, A_bf16, 4, dims, str, box);
-    if (rc) return rc;
-  }
+  int rc = encode_act(&tmA, d.A16, d.Bimg, d.Hg, d.Wg, d.Cin, p.BW, p.BH);
+  if (rc) return rc;
+  const int N = d.N;
   const int BN = (N % 256 == 0 && m_tiles * (N / 256) >= 148) ? 256 : (N % 128 == 0 ? 128 : 64);
   {
-    cuuint64_t dims[2] = {(cuuint64_t)taps * Cin, (cuuint64_t)N};
-    cuuint64_t str[1] = {(cuuint64_t)taps * Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
-    int rc = encode_bf16(&tmB, W_bf16, 2, dims, str, box);
+    const cuuint64_t K = (cuuint64_t)d.taps * d.Cin;
+    cuuint64_t dims[3] = {K, (cuuint64_t)N, (cuuint64_t)(d.w_batched ? d.Bimg : 1)};
+    cuuint64_t str[2] = {K * 2, K * 2 * (cuuint64_t)N};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, 1u};
+    rc = encode_bf16(&tmB, d.W16, 3, dims, str, box);
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (BN == 256) return launch_tc<256, 4>(tmA, tmB, p, (int)m_tiles, st);
   if (BN == 128) return launch_tc<128, 6>(tmA, tmB, p, (int)m_tiles, st);
   return launch_tc<64, 8>(tmA, tmB, p, (int)m_tiles, st);
+}
+
+extern "C" int tbns_gemm_tc_wgrad_supported(int Ma, int Nb, int taps) {
+  return (Ma > 0 && Ma % TC_BM == 0 && Nb >= 64 && Nb % 64 == 0 && (taps == 1 || taps == 9)) ? 1 : 0;
+}
+
+extern "C" int tbns_gemm_tc_wgrad(const tbns_tc_wgrad_desc* dp, void* stream) {
+  TBNS_REQUIRE(dp != nullptr, "tbns_gemm_tc_wgrad: null descriptor");
+  const tbns_tc_wgrad_desc& d = *dp;
+  TBNS_REQUIRE(d.A16 && d.B16 && d.ws, "tbns_gemm_tc_wgrad: null pointer");
+  TBNS_REQUIRE(tbns_gemm_tc_wgrad_supported(d.Ma, d.Nb, d.taps), "tbns_gemm_tc_wgrad: unsupported shape Ma=%d Nb=%d taps=%d", d.Ma, d.Nb, d.taps);
+  TBNS_REQUIRE(d.Bimg > 0 && d.Hg > 0 && d.Wg > 0 && d.split_k >= 1, "tbns_gemm_tc_wgrad: bad dims");
+  TBNS_REQUIRE(d.scatter ? (d.Cx && d.Cfx && d.I > 0 && !d.batched) : (d.C != nullptr), "tbns_gemm_tc_wgrad: null output");
+  TBNS_REQUIRE(al16p(d.A16) && al16p(d.B16) && al16p(d.ws), "tbns_gemm_tc_wgrad: operands must be 16-byte aligned");
+  WgParams p;
+  p.ws = d.ws; p.Ma = d.Ma; p.Nb = d.Nb; p.Mtot = d.taps * d.Ma;
+  p.Bimg = d.Bimg; p.Hg = d.Hg; p.Wg = d.Wg; p.taps = d.taps;
+  p.BW = pick_bw(d.Hg, d.Wg, WG_BKT); p.BH = WG_BKT / p.BW;
+  p.tiles_w = cdiv(d.Wg, p.BW); p.tiles_h = cdiv(d.Hg, p.BH);
+  const int BN = d.Nb % 256 == 0 ? 256 : (d.Nb % 128 == 0 ? 128 : 64);
+  p.m_chunks = d.Ma / TC_BM; p.n_chunks = d.Nb / BN;
+  p.batched = d.batched; p.split_k = d.split_k;
+  const int batch = d.batched ? d.Bimg : 1;
+  const int tiles = d.taps * p.m_chunks * p.n_chunks;
+  const int gy = batch * d.split_k;
+  TBNS_REQUIRE(gy <= 65535, "tbns_gemm_tc_wgrad: grid too large");
+  CUtensorMap tmA, tmB;
+  int rc = encode_act(&tmA, d.A16, d.Bimg, d.Hg, d.Wg, d.Ma, p.BW, p.BH);
+  if (rc) return rc;
+  rc = encode_act(&tmB, d.B16, d.Bimg, d.Hg, d.Wg, d.Nb, p.BW, p.BH);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 256) rc = launch_wg<256, 4>(tmA, tmB, p, tiles, gy, st);
+  else if (BN == 128) rc = launch_wg<128, 6>(tmA, tmB, p, tiles, gy, st);
+  else rc = launch_wg<64, 8>(tmA, tmB, p, tiles, gy, st);
+  if (rc) return rc;
+  // fixed-order reduction over the splits (+ scatter into weight.grad layout)
+  tbns_gemm_desc g;
+  memset(&g, 0, sizeof(g));
+  g.M = p.Mtot; g.N = d.Nb; g.K = 1; g.batch = batch;
+  g.C = d.C; g.ldc = d.ldc; g.sC = d.sC;
+  g.split_k = d.split_k; g.ws = d.ws;
+  g.scatter = d.scatter; g.I = d.I; g.taps = d.taps; g.Cin = d.Ma; g.Cx = d.Cx; g.Cfx = d.Cfx;
+  return splitk_reduce(g, st);
 }

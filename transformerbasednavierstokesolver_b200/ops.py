@@ -134,12 +134,45 @@ def tc_supported(Cin: int, N: int, taps: int) -> bool:
     return bool(_lib.load().tbns_gemm_tc_supported(Cin, N, taps))
 
 
-def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps, flip, tag=None):
-    """tcgen05 implicit GEMM (include/tbns.h: tbns_gemm_tc)"""
+def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps=1, flip=0, tag=None, *, C16=None, w_batched=0, act=0, aux_out=None,
+            aux_in=None, residual=None):
+    """tcgen05 implicit GEMM, K-major operands (include/tbns.h: tbns_gemm_tc).  C fp32 and/or C16 bf16 outputs [.., N]."""
+    d = _lib.TcDesc()
+    d.A16, d.Bimg, d.Hg, d.Wg, d.Cin, d.taps, d.flip = _p(A16), Bimg, Hg, Wg, Cin, taps, flip
+    d.W16, d.N, d.w_batched = _p(W16), N, w_batched
+    d.bias, d.act = _p(bias), act
+    d.aux_out, d.aux_in, d.ldaux = _p(aux_out), _p(aux_in), N
+    d.residual, d.ldr = _p(residual), N
+    d.C, d.ldc = _p(C), N
+    d.C16, d.ldc16 = _p(C16), N
     with _Timed(tag):
-        check(_lib.load().tbns_gemm_tc(_p(A16), _p(W16), _p(C), C.shape[-1], _p(bias), Bimg, Hg, Wg, Cin, N, taps, flip, _stream()),
-              "tbns_gemm_tc")
+        check(_lib.load().tbns_gemm_tc(ct.byref(d), _stream()), "tbns_gemm_tc")
     _count(1)
+
+
+def wgrad_supported(Ma: int, Nb: int, taps: int) -> bool:
+    return bool(_lib.load().tbns_gemm_tc_wgrad_supported(Ma, Nb, taps))
+
+
+def gemm_tc_wgrad(A16, B16, Bimg, Hg, Wg, Ma, Nb, taps=1, batched=0, C=None, scatter=None, I=0, tag=None):
+    """tcgen05 token-contraction GEMM, MN-major operands (include/tbns.h: tbns_gemm_tc_wgrad):
+    D[(tap,a), n] = sum_token A16[shift(token,tap), a] * B16[token, n]; result in C ([batch][taps*Ma][Nb]) or scattered."""
+    BN = 256 if Nb % 256 == 0 else (128 if Nb % 128 == 0 else 64)
+    batch = Bimg if batched else 1
+    tiles = taps * (Ma // 128) * (Nb // BN) * batch
+    kblocks = ((Hg * Wg + 63) // 64) * (1 if batched else Bimg)
+    split = max(1, min((2 * _NUM_SMS + tiles - 1) // tiles, max(1, kblocks // 4), 64))
+    ws = torch.empty(split * batch * taps * Ma * Nb, device=A16.device, dtype=torch.float32)
+    d = _lib.TcWgradDesc()
+    d.A16, d.Ma, d.B16, d.Nb = _p(A16), Ma, _p(B16), Nb
+    d.Bimg, d.Hg, d.Wg, d.taps, d.batched = Bimg, Hg, Wg, taps, batched
+    d.split_k, d.ws = split, _p(ws)
+    d.C, d.ldc, d.sC = _p(C), Nb, taps * Ma * Nb
+    if scatter is not None:
+        d.scatter, d.I, d.Cx, d.Cfx = 1, I, _p(scatter[0]), _p(scatter[1])
+    with _Timed(tag):
+        check(_lib.load().tbns_gemm_tc_wgrad(ct.byref(d), _stream()), "tbns_gemm_tc_wgrad")
+    _count(2)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -315,15 +348,21 @@ def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, save
     dWx = torch.empty(Wx_shape, **f32)
     dWfx = torch.empty(Wx_shape, **f32)
     Hg, Wg = grid if structured else (1, N)
-    if precision == TBNS_PREC_BF16 and Wd16 is not None:
-        gemm_tc(cast_bf16(dXF), Wd16, dx, None, B, Hg, Wg, I2, C_, taps, 1, tag="proj_dgrad")
+    bf16 = precision == TBNS_PREC_BF16
+    use_tc_dgrad = bf16 and Wd16 is not None
+    use_tc_wgrad = bf16 and wgrad_supported(C_, I2, taps)
+    dXF16 = cast_bf16(dXF) if (use_tc_dgrad or use_tc_wgrad) else None
+    if use_tc_dgrad:
+        gemm_tc(dXF16, Wd16, dx, None, B, Hg, Wg, I2, C_, taps, 1, tag="proj_dgrad")
     elif structured:
         gemm(M=B * N, N=C_, K=9 * I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=dx, ldc=C_, conv_mode=1, Hg=Hg, Wg=Wg,
              Cin=I2, flip=1, precision=precision, tag="proj_dgrad")
     else:
         gemm(M=B * N, N=C_, K=I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=I2, b_kind=0, C=dx, ldc=C_, precision=precision,
              tag="proj_dgrad")
-    if structured:
+    if use_tc_wgrad:
+        gemm_tc_wgrad(cast_bf16(x), dXF16, B, Hg, Wg, C_, I2, taps=taps, scatter=(dWx, dWfx), I=I, tag="proj_wgrad")
+    elif structured:
         gemm(M=9 * C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, conv_mode=2, Hg=Hg, Wg=Wg, Cin=C_,
              precision=precision, split_k=_split_k(9 * C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=9, tag="proj_wgrad")
     else:
