@@ -290,8 +290,16 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
                                      _p(A), _p(O), _p(P), B, H, D, G, Cout, st), "tbns_pa_token_attn_fwd")
     # (3) deslice (+) to_out (+ bias, + residual)   :116-119 / :55-57
     out = torch.empty(B, N, Cout, **f32)
-    gemm(M=N, N=Cout, K=H * G, A=w, lda=H * G, a_kind=0, B=P, ldb=Cout, b_kind=1, C=out, ldc=Cout, batch=B, sA=N * H * G,
-         sB=H * G * Cout, sC=N * Cout, sR=N * Cout, bias=bo, residual=residual, ldr=Cout, precision=precision)
+    HG = H * G
+    if (precision == TBNS_PREC_BF16 and tc_supported(HG, Cout, 1) and tc_supported(Cout, HG, 1) and wgrad_supported(HG, Cout, 1)):
+        # tensor-core deslice: out[b] = w[b] (N x HG) . P[b] (HG x Cout); only bf16 copies of w and P are kept for backward
+        w16 = cast_bf16(w)
+        PT16 = cast_bf16(P.transpose(1, 2).contiguous())   # [B, Cout, HG]: K-major weight operand
+        P16 = cast_bf16(P)                                 # [B, HG, Cout]: K-major weight operand of the dw contraction
+        gemm_tc(w16, PT16, out, bo, B, 1, N, HG, Cout, w_batched=1, residual=residual, tag="deslice_out")
+        return out, (XF, w16, s, tok, q, k, v, A, O, P16)
+    gemm(M=N, N=Cout, K=HG, A=w, lda=HG, a_kind=0, B=P, ldb=Cout, b_kind=1, C=out, ldc=Cout, batch=B, sA=N * HG,
+         sB=HG * Cout, sC=N * Cout, sR=N * Cout, bias=bo, residual=residual, ldr=Cout, precision=precision, tag="deslice_out")
     return out, (XF, w, s, tok, q, k, v, A, O, P)
 
 
@@ -318,11 +326,16 @@ def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, save
     # (3') deslice (+) to_out backward
     dbo = colsum(dout, B * N, Cout)
     dP = torch.empty(B, HG, Cout, **f32)
-    gemm(M=HG, N=Cout, K=N, A=w, lda=HG, a_kind=1, B=dout, ldb=Cout, b_kind=1, C=dP, ldc=Cout, batch=B, sA=N * HG, sB=N * Cout,
-         sC=HG * Cout, precision=precision, split_k=_split_k(HG, Cout, N, B))
     dw = torch.empty(B, N, HG, **f32)
-    gemm(M=N, N=HG, K=Cout, A=dout, lda=Cout, a_kind=0, B=P, ldb=Cout, b_kind=0, C=dw, ldc=HG, batch=B, sA=N * Cout,
-         sB=HG * Cout, sC=N * HG, precision=precision)
+    if w.dtype == torch.bfloat16:   # tensor-core mode (forward kept bf16 copies)
+        dout16 = cast_bf16(dout)
+        gemm_tc_wgrad(w, dout16, B, 1, N, HG, Cout, batched=1, C=dP, tag="deslice_dP")
+        gemm_tc(dout16, P, dw, None, B, 1, N, Cout, HG, w_batched=1, tag="deslice_dw")
+    else:
+        gemm(M=HG, N=Cout, K=N, A=w, lda=HG, a_kind=1, B=dout, ldb=Cout, b_kind=1, C=dP, ldc=Cout, batch=B, sA=N * HG, sB=N * Cout,
+             sC=HG * Cout, precision=precision, split_k=_split_k(HG, Cout, N, B), tag="deslice_dP")
+        gemm(M=N, N=HG, K=Cout, A=dout, lda=Cout, a_kind=0, B=P, ldb=Cout, b_kind=0, C=dw, ldc=HG, batch=B, sA=N * Cout,
+             sB=HG * Cout, sC=N * HG, precision=precision, tag="deslice_dw")
     # (2') token attention backward
     dTt = torch.empty(B, H, G, D, **f32)
     ds = torch.empty(B, H, G, **f32)
@@ -418,6 +431,18 @@ class LnMlpFn(torch.autograd.Function):
         Cout = W2.shape[0]
         x2, mean, rstd = layernorm_fwd(fx, gamma, beta, eps)
         pre = torch.empty(M, R, device=fx.device, dtype=torch.float32)
+        use_tc = (precision == TBNS_PREC_BF16 and Cout == C_ and tc_supported(C_, R, 1) and tc_supported(R, Cout, 1)
+                  and wgrad_supported(Cout, R, 1) and wgrad_supported(R, C_, 1))
+        if use_tc:
+            # tensor-core MLP: bf16 operands, hidden activation only ever exists in bf16 (+ fp32 pre-activation for GELU')
+            x2_16 = cast_bf16(x2)
+            hid16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
+            gemm_tc(x2_16, cast_bf16(W1), None, b1, 1, 1, M, C_, R, act=1, aux_out=pre, C16=hid16, tag="mlp_fc1")
+            out = torch.empty(*fx.shape[:-1], Cout, device=fx.device, dtype=torch.float32)
+            gemm_tc(hid16, cast_bf16(W2), out, b2, 1, 1, M, R, Cout, residual=fx, tag="mlp_fc2")
+            ctx.save_for_backward(fx, gamma, W1, W2, x2_16, mean, rstd, pre, hid16)
+            ctx.precision = precision
+            return out
         hid = torch.empty(M, R, device=fx.device, dtype=torch.float32)
         gemm(M=M, N=R, K=C_, A=x2, lda=C_, a_kind=0, B=W1, ldb=C_, b_kind=0, C=hid, ldc=R, bias=b1, act=1, aux_out=pre, ldaux=R,
              precision=precision)
@@ -440,6 +465,19 @@ class LnMlpFn(torch.autograd.Function):
         f32 = dict(device=fx.device, dtype=torch.float32)
         db2 = colsum(dout, M, Cout)
         dW2 = torch.empty(Cout, R, **f32)
+        if hid.dtype == torch.bfloat16:   # tensor-core mode
+            dout16 = cast_bf16(dout)
+            gemm_tc_wgrad(dout16, hid, 1, 1, M, Cout, R, C=dW2, tag="mlp_dW2")
+            dpre = torch.empty(M, R, **f32)
+            dpre16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
+            gemm_tc(dout16, cast_bf16(W2.t().contiguous()), dpre, None, 1, 1, M, Cout, R, act=2, aux_in=pre, C16=dpre16, tag="mlp_dpre")
+            db1 = colsum(dpre, M, R)
+            dW1 = torch.empty(R, C_, **f32)
+            gemm_tc_wgrad(dpre16, x2, 1, 1, M, R, C_, C=dW1, tag="mlp_dW1")
+            dx2 = torch.empty(M, C_, **f32)
+            gemm_tc(dpre16, cast_bf16(W1.t().contiguous()), dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
+            dfx, dg, db = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout)
+            return dfx.view_as(fx), dg, db, dW1, db1, dW2, db2, None, None
         gemm(M=Cout, N=R, K=M, A=dout, lda=Cout, a_kind=1, B=hid, ldb=R, b_kind=1, C=dW2, ldc=R, precision=precision,
              split_k=_split_k(Cout, R, M))
         dpre = torch.empty(M, R, **f32)
