@@ -138,18 +138,20 @@ int tbns_pack_proj_weights(const float* Wx, const float* bx, const float* Wfx, c
  * Slice stage (model/Physics_Attention.py:40-42 / :98-101):
  *   w[b,n,h,g] = softmax_g((X[b,n,h,:].Ws[g,:] + bs[g]) / tau_h),  partial sums over token chunks of
  *   s = sum_n w and Tt = sum_n w (x) F.   XF = [X | F] is [B*N, 2I].  clamp=1 clamps tau to [0.1,5].
- *   part: [B,H,nchunk,G,D+1] with nchunk = tbns_slice_nchunk(N).
+ *   part: [B,H,groups,G,D+1] with groups = tbns_slice_groups(B,N,H); w fp32 and/or w16 bf16 (either may be NULL).
+ *   dim_head D in {8,16,32,64}, slice_num G in {4,8,16,32,64}.
  * ------------------------------------------------------------------------------------------- */
-int tbns_slice_nchunk(int N);
-int tbns_pa_slice_fwd(const float* XF, const float* Ws, const float* bs, const float* temperature, float* w,
+int tbns_slice_groups(int B, int N, int H);  /* partials per (batch, head) written by the slice kernels */
+int tbns_pa_slice_fwd(const float* XF, const float* Ws, const float* bs, const float* temperature, float* w, void* w16,
                       float* part, int B, int N, int H, int D, int G, int clamp, void* stream);
 
 /* Token stage (model/Physics_Attention.py:43-52 / :102-111) + fold of to_out into P:
  *   reduces `part` -> s[B,H,G], Tt[B,H,G,D]; tok = Tt/(s+1e-5); q,k,v; A = softmax(q k^T D^-1/2); O = A v;
- *   P[b,h*G+g,c] = sum_d O[b,h,g,d] * Wo[c,h*D+d].   Wo is [Cout, H*D]. */
+ *   P[b,h*G+g,c] = sum_d O[b,h,g,d] * Wo[c,h*D+d].   Wo is [Cout, H*D].
+ *   Optional bf16 copies for the tensor-core deslice: P16 [B,H*G,Cout] and PT16 [B,Cout,H*G] (NULL to skip). */
 int tbns_pa_token_attn_fwd(const float* part, int nchunk, const float* Wq, const float* Wk, const float* Wv,
                            const float* Wo, float* s, float* Tt, float* tok, float* q, float* k, float* v, float* A,
-                           float* O, float* P, int B, int H, int D, int G, int Cout, void* stream);
+                           float* O, float* P, void* P16, void* PT16, int B, int H, int D, int G, int Cout, void* stream);
 
 /* Backward of the token stage.  dP [B,H*G,Cout] ->  dTt [B,H,G,D], ds [B,H,G], and per-(b,h) partials
  *   dWqkv_part [B*H,3,D,D],  dWo_part [B,Cout,H*D]  (reduce over the leading dim with tbns_reduce_rows). */
@@ -159,11 +161,12 @@ int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const float* Wk, co
                            int B, int H, int D, int G, int Cout, void* stream);
 
 /* Backward of the slice stage (SURVEY §8 a-bwd): recomputes logits / softmax from XF.
- *   dw [B,N,H*G] (deslice gradient), dTt, ds  ->  dXF [B*N,2I],
- *   dWs_part [B*H*nchunk, G, D+1] (last column = dbs), dtau_part [B*H*nchunk]. */
+ *   dw [B,N,H*G] (deslice gradient), dTt, ds  ->  dXF [B*N,2I] (fp32 and/or bf16 copy dXF16; either may be NULL),
+ *   dWs_part [B*H*groups, G, D+1] (last column = dbs), dtau_part [B*H*groups],
+ *   dbcat_part [B*groups, H, 2, D] (bias gradients of in_project_x | in_project_fx), groups = tbns_slice_groups. */
 int tbns_pa_slice_bwd(const float* XF, const float* Ws, const float* bs, const float* temperature, const float* dw,
-                      const float* dTt, const float* ds, float* dXF, float* dWs_part, float* dtau_part, int B, int N,
-                      int H, int D, int G, int clamp, void* stream);
+                      const float* dTt, const float* ds, float* dXF, void* dXF16, float* dWs_part, float* dtau_part,
+                      float* dbcat_part, int B, int N, int H, int D, int G, int clamp, void* stream);
 /* dtau_part [B,H,nchunk] -> dtemperature [H], applying the clamp mask [0.1<=tau<=5] when clamp=1 */
 int tbns_pa_dtau_finish(const float* dtau_part, const float* temperature, float* dtemperature, int B, int H,
                         int nchunk, int clamp, void* stream);

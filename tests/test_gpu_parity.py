@@ -313,11 +313,13 @@ def test_slice_weights_partition_of_unity_full_size(dev):
     Ws = (torch.randn(G, D, generator=g) * 0.5).to(dev)
     bs = torch.randn(G, generator=g).to(dev)
     tau = torch.linspace(0.05, 6.0, H).to(dev)
-    nchunk = lib.tbns_slice_nchunk(N)
+    nchunk = lib.tbns_slice_groups(B, N, H)
     w = torch.empty(B, N, H * G, device=dev)
+    w16 = torch.empty(B, N, H * G, device=dev, dtype=torch.bfloat16)
     part = torch.empty(B * H * nchunk * G * (D + 1), device=dev)
-    _lib.check(lib.tbns_pa_slice_fwd(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), w.data_ptr(), part.data_ptr(), B, N,
-                                     H, D, G, 1, torch.cuda.current_stream().cuda_stream), "slice_fwd")
+    _lib.check(lib.tbns_pa_slice_fwd(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), w.data_ptr(), w16.data_ptr(),
+                                     part.data_ptr(), B, N, H, D, G, 1, torch.cuda.current_stream().cuda_stream), "slice_fwd")
+    assert torch.equal(w16, w.bfloat16())
     w4 = w.view(B, N, H, G)
     assert float((w4.sum(-1) - 1).abs().max()) < 1e-5
     p = part.view(B, H, nchunk, G, D + 1).sum(2)

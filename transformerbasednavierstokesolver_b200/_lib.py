@@ -82,11 +82,11 @@ _SIGS = {
     "tbns_layernorm_bwd_ws_floats": (C.c_size_t, [_i]),
     "tbns_layernorm_bwd": (_i, [_fp] * 10 + [_i, _i, _fp]),
     "tbns_pack_proj_weights": (_i, [_fp] * 7 + [_i, _i, _i, _fp]),
-    "tbns_slice_nchunk": (_i, [_i]),
-    "tbns_pa_slice_fwd": (_i, [_fp] * 6 + [_i] * 6 + [_fp]),
-    "tbns_pa_token_attn_fwd": (_i, [_fp, _i] + [_fp] * 13 + [_i] * 5 + [_fp]),
+    "tbns_slice_groups": (_i, [_i, _i, _i]),
+    "tbns_pa_slice_fwd": (_i, [_fp] * 7 + [_i] * 6 + [_fp]),
+    "tbns_pa_token_attn_fwd": (_i, [_fp, _i] + [_fp] * 15 + [_i] * 5 + [_fp]),
     "tbns_pa_token_attn_bwd": (_i, [_fp] * 16 + [_i] * 5 + [_fp]),
-    "tbns_pa_slice_bwd": (_i, [_fp] * 10 + [_i] * 6 + [_fp]),
+    "tbns_pa_slice_bwd": (_i, [_fp] * 12 + [_i] * 6 + [_fp]),
     "tbns_pa_dtau_finish": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp]),
     "tbns_reduce_rows": (_i, [_fp, _fp, _i, _ll, _fp]),
     "tbns_colsum_ws_floats": (C.c_size_t, [_ll]),

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     const float* __restrict__ gamma, const float* __restrict__ dres,
                                                                     float* __restrict__ dx, float* __restrict__ part, int rows, int C) {
-  extern __shared__ float sm[];  // [LN_WARPS][2][C]
+  extern __shared__ __align__(16) float sm[];  // [LN_WARPS][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* dg = sm + (long long)warp * 2 * C;
   float* db = dg + C;
@@ -83,6 +83,41 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
     const float* dyr = dy + (long long)row * C;
     const float mu = mean[row], rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
+    if ((C & 3) == 0) {
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dyr + c);
+        const float4 x4 = *reinterpret_cast<const float4*>(xr + c);
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + c);
+        const float gx = d4.x * g4.x, gy = d4.y * g4.y, gz = d4.z * g4.z, gw = d4.w * g4.w;
+        s1 += (gx + gy) + (gz + gw);
+        s2 += gx * ((x4.x - mu) * rs) + gy * ((x4.y - mu) * rs) + gz * ((x4.z - mu) * rs) + gw * ((x4.w - mu) * rs);
+      }
+      const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dyr + c);
+        const float4 x4 = *reinterpret_cast<const float4*>(xr + c);
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + c);
+        const float xh0 = (x4.x - mu) * rs, xh1 = (x4.y - mu) * rs, xh2 = (x4.z - mu) * rs, xh3 = (x4.w - mu) * rs;
+        float4 o;
+        o.x = (d4.x * g4.x - c1 - xh0 * c2) * rs;
+        o.y = (d4.y * g4.y - c1 - xh1 * c2) * rs;
+        o.z = (d4.z * g4.z - c1 - xh2 * c2) * rs;
+        o.w = (d4.w * g4.w - c1 - xh3 * c2) * rs;
+        if (dres) {
+          const float4 r4 = *reinterpret_cast<const float4*>(dres + (long long)row * C + c);
+          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+        }
+        *reinterpret_cast<float4*>(dx + (long long)row * C + c) = o;
+        float4* pg = reinterpret_cast<float4*>(dg + c);  // lane-private columns: no race
+        float4* pb = reinterpret_cast<float4*>(db + c);
+        float4 ag = *pg, ab = *pb;
+        ag.x += d4.x * xh0; ag.y += d4.y * xh1; ag.z += d4.z * xh2; ag.w += d4.w * xh3;
+        ab.x += d4.x; ab.y += d4.y; ab.z += d4.z; ab.w += d4.w;
+        *pg = ag;
+        *pb = ab;
+      }
+      continue;
+    }
     for (int c = lane; c < C; c += 32) {
       const float g = dyr[c] * gamma[c];
       const float xh = (xr[c] - mu) * rs;
@@ -109,6 +144,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
   }
 }
 
+__global__ void colsum_partial_kernel(const float* __restrict__ in, long long ld, float* __restrict__ ws, int rows, int cols,
+                                      int rows_per_chunk);
+
 __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, long long cols, long long ld) {
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < cols; j += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -117,13 +155,42 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restri
   }
 }
 
-constexpr int COLSUM_ROWS = 64;  // row groups
-__global__ void colsum_partial_kernel(const float* __restrict__ in, long long ld, float* __restrict__ ws, int rows, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float s = 0.f;
-  for (int r = blockIdx.y; r < rows; r += gridDim.y) s += in[(long long)r * ld + c];
-  ws[(long long)blockIdx.y * cols + c] = s;
+// Column sums (bias gradients): HBM-bound streaming reduction.  Each CTA owns a 128-column panel and a contiguous chunk of
+// rows; 32 float4-lanes x 8 row-lanes, fixed-order combine in shared memory, then a deterministic second stage.
+constexpr int COLSUM_ROWS = 592;  // max row chunks (4 x 148)
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ in, long long ld, float* __restrict__ ws, int rows,
+                                                            int cols, int rows_per_chunk) {
+  __shared__ float4 red[8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + cl * 4;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(rows, r0 + rows_per_chunk);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vec = (c + 3 < cols) && ((ld & 3) == 0);
+  if (vec) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(in + (long long)r * ld + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  } else {
+    for (int r = r0 + rl; r < r1; r += 8) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < cols) (&acc.x)[j] += in[(long long)r * ld + c + j];
+    }
+  }
+  red[rl][cl] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    float4 s = red[0][cl];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      s.x += red[i][cl].x; s.y += red[i][cl].y; s.z += red[i][cl].z; s.w += red[i][cl].w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c + j < cols) ws[(long long)blockIdx.y * cols + c + j] = (&s.x)[j];
+  }
 }
 
 }  // namespace tbns
@@ -145,9 +212,14 @@ extern "C" size_t tbns_layernorm_bwd_ws_floats(int C) { return (size_t)LN_MAX_CT
 extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long cols, void* stream) {
   TBNS_REQUIRE(in && out && rows >= 0 && cols >= 0, "tbns_reduce_rows: bad args");
   if (cols == 0) return TBNS_OK;
-  int blocks = (int)((cols + 127) / 128);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  reduce_rows_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(in, out, rows, cols, cols);
+  if (cols <= 0x7fffffffLL && (cols % 4 == 0) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && cols / 128 < 65535 * 32) {
+    // 8 row-lanes x 32 float4 column-lanes per CTA, fixed summation order
+    colsum_partial_kernel<<<dim3((unsigned)((cols + 127) / 128), 1), 256, 0, (cudaStream_t)stream>>>(in, cols, out, rows, (int)cols, rows);
+  } else {
+    int blocks = (int)((cols + 127) / 128);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    reduce_rows_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(in, out, rows, cols, cols);
+  }
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
@@ -171,9 +243,15 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
   layernorm_bwd_kernel<<<ctas, LN_WARPS * 32, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, ws, rows, C);
   TBNS_LAUNCH_CHECK();
   // ws rows are [dgamma | dbeta], width 2C
-  reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, dgamma, ctas, C, 2LL * C);
-  TBNS_LAUNCH_CHECK();
-  reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws + C, dbeta, ctas, C, 2LL * C);
+  if ((C & 3) == 0) {
+    colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws, 2LL * C, dgamma, ctas, C, ctas);
+    TBNS_LAUNCH_CHECK();
+    colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws + C, 2LL * C, dbeta, ctas, C, ctas);
+  } else {
+    reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, dgamma, ctas, C, 2LL * C);
+    TBNS_LAUNCH_CHECK();
+    reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws + C, dbeta, ctas, C, 2LL * C);
+  }
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
@@ -182,10 +260,14 @@ extern "C" size_t tbns_colsum_ws_floats(long long cols) { return (size_t)COLSUM_
 
 extern "C" int tbns_colsum(const float* in, long long ld, float* out, float* ws, int rows, int cols, void* stream) {
   TBNS_REQUIRE(in && out && ws && rows > 0 && cols > 0, "tbns_colsum: bad args");
+  TBNS_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0, "tbns_colsum: input must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  int groups = rows < COLSUM_ROWS ? rows : COLSUM_ROWS;
-  dim3 grid(cdiv(cols, 128), groups);
-  colsum_partial_kernel<<<grid, 128, 0, st>>>(in, ld, ws, rows, cols);
+  int chunks = cdiv(rows, 64);
+  if (chunks > COLSUM_ROWS) chunks = COLSUM_ROWS;
+  const int rows_per_chunk = cdiv(rows, chunks);
+  chunks = cdiv(rows, rows_per_chunk);
+  dim3 grid(cdiv(cols, 128), chunks);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(in, ld, ws, rows, cols, rows_per_chunk);
   TBNS_LAUNCH_CHECK();
-  return tbns_reduce_rows(ws, out, groups, cols, stream);
+  return tbns_reduce_rows(ws, out, chunks, cols, stream);
 }

@@ -246,8 +246,17 @@ def pack_proj_weights(Wx, bx, Wfx, bfx):
 # ------------------------------------------------------------------------------------------------
 # Physics-Attention forward / backward
 # ------------------------------------------------------------------------------------------------
+def _pa_tc_ok(precision, C_, I2, HG, Cout, taps, packed16) -> bool:
+    """bf16 mode runs every token contraction of the module on tcgen05 when all of them fit the tensor-core kernels'
+    shape rules (channel counts multiples of 64 / 128); otherwise the whole module uses the fp32 SIMT engine with
+    bf16-rounded operands (same numerics, slower)."""
+    return (precision == TBNS_PREC_BF16 and packed16 and tc_supported(C_, I2, taps) and tc_supported(I2, C_, taps)
+            and wgrad_supported(C_, I2, taps) and tc_supported(HG, Cout, 1) and tc_supported(Cout, HG, 1)
+            and wgrad_supported(HG, Cout, 1))
+
+
 def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, heads: int,
-               grid: Optional[Tuple[int, int]], precision: int, Wf16=None):
+               grid: Optional[Tuple[int, int]], precision: int, Wf16=None, x16=None):
     """returns (out, saved tuple). x [B,N,C]; Wf/bcat packed projections; residual [B,N,Cout] or None."""
     lib = _lib.load()
     B, N, C_ = x.shape
@@ -257,58 +266,63 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
     D = I // H
     G = Ws.shape[0]
     Cout = Wo.shape[0]
+    HG = H * G
     dev = x.device
     f32 = dict(device=dev, dtype=torch.float32)
+    bf = dict(device=dev, dtype=torch.bfloat16)
     st = _stream()
     structured = grid is not None
+    taps = 9 if structured else 1
+    Hg, Wg = grid if structured else (1, N)
+    tc = _pa_tc_ok(precision, C_, I2, HG, Cout, taps, Wf16 is not None)
     # (1a) projections: XF = [x_mid | fx_mid]   Physics_Attention.py:94-97 / :36-39
     XF = torch.empty(B * N, I2, **f32)
-    if precision == TBNS_PREC_BF16 and Wf16 is not None:
+    if tc:
         # tensor-core path: bf16 operands through TMA, tcgen05.mma, fp32 accumulate in TMEM
-        Hg, Wg = grid if structured else (1, N)
-        gemm_tc(cast_bf16(x), Wf16, XF, bcat, B, Hg, Wg, C_, I2, 9 if structured else 1, 0, tag="proj_fprop")
+        if x16 is None:
+            x16 = cast_bf16(x)
+        gemm_tc(x16, Wf16, XF, bcat, B, Hg, Wg, C_, I2, taps, 0, tag="proj_fprop")
     elif structured:
-        Hg, Wg = grid
         gemm(M=B * N, N=I2, K=9 * C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=9 * C_, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Hg,
              Wg=Wg, Cin=C_, bias=bcat, precision=precision, tag="proj_fprop")
     else:
         gemm(M=B * N, N=I2, K=C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=C_, b_kind=0, C=XF, ldc=I2, bias=bcat, precision=precision,
              tag="proj_fprop")
     # (1b,1c) slice weights + partial slice tokens   :98-101 / :40-42
-    nchunk = lib.tbns_slice_nchunk(N)
-    w = torch.empty(B, N, H * G, **f32)
-    part = torch.empty(B * H * nchunk * G * (D + 1), **f32)
-    check(lib.tbns_pa_slice_fwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w), _p(part), B, N, H, D, G, int(structured), st),
+    groups = lib.tbns_slice_groups(B, N, H)
+    w = None if tc else torch.empty(B, N, HG, **f32)
+    w16 = torch.empty(B, N, HG, **bf) if tc else None     # tensor-core mode keeps only the bf16 copy
+    part = torch.empty(B * H * groups * G * (D + 1), **f32)
+    check(lib.tbns_pa_slice_fwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w), _p(w16), _p(part), B, N, H, D, G, int(structured), st),
           "tbns_pa_slice_fwd")
     _count(2)  # + token_attn_fwd below
     # (2) token normalisation + attention among slice tokens + fold of to_out   :102-111 / :43-52
     s = torch.empty(B, H, G, **f32)
     Tt, tok, q, k, v, O = (torch.empty(B, H, G, D, **f32) for _ in range(6))
     A = torch.empty(B, H, G, G, **f32)
-    P = torch.empty(B, H * G, Cout, **f32)
-    check(lib.tbns_pa_token_attn_fwd(_p(part), nchunk, _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(Tt), _p(tok), _p(q), _p(k), _p(v),
-                                     _p(A), _p(O), _p(P), B, H, D, G, Cout, st), "tbns_pa_token_attn_fwd")
+    P = torch.empty(B, HG, Cout, **f32)
+    P16 = torch.empty(B, HG, Cout, **bf) if tc else None    # K-major operand of dw = dOut.P^T
+    PT16 = torch.empty(B, Cout, HG, **bf) if tc else None   # K-major operand of out = w.P
+    check(lib.tbns_pa_token_attn_fwd(_p(part), groups, _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(Tt), _p(tok), _p(q), _p(k), _p(v),
+                                     _p(A), _p(O), _p(P), _p(P16), _p(PT16), B, H, D, G, Cout, st), "tbns_pa_token_attn_fwd")
     # (3) deslice (+) to_out (+ bias, + residual)   :116-119 / :55-57
     out = torch.empty(B, N, Cout, **f32)
-    HG = H * G
-    if (precision == TBNS_PREC_BF16 and tc_supported(HG, Cout, 1) and tc_supported(Cout, HG, 1) and wgrad_supported(HG, Cout, 1)):
-        # tensor-core deslice: out[b] = w[b] (N x HG) . P[b] (HG x Cout); only bf16 copies of w and P are kept for backward
-        w16 = cast_bf16(w)
-        PT16 = cast_bf16(P.transpose(1, 2).contiguous())   # [B, Cout, HG]: K-major weight operand
-        P16 = cast_bf16(P)                                 # [B, HG, Cout]: K-major weight operand of the dw contraction
+    if tc:
         gemm_tc(w16, PT16, out, bo, B, 1, N, HG, Cout, w_batched=1, residual=residual, tag="deslice_out")
-        return out, (XF, w16, s, tok, q, k, v, A, O, P16)
+        return out, (XF, w16, s, tok, q, k, v, A, O, P16, x16)
     gemm(M=N, N=Cout, K=HG, A=w, lda=HG, a_kind=0, B=P, ldb=Cout, b_kind=1, C=out, ldc=Cout, batch=B, sA=N * HG,
          sB=HG * Cout, sC=N * Cout, sR=N * Cout, bias=bo, residual=residual, ldr=Cout, precision=precision, tag="deslice_out")
-    return out, (XF, w, s, tok, q, k, v, A, O, P)
+    return out, (XF, w, s, tok, q, k, v, A, O, P, x)
 
 
-def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, saved, heads: int,
-                grid: Optional[Tuple[int, int]], precision: int, Wd16=None):
-    """returns dx and the parameter gradients in reference (state_dict) layouts."""
+def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, saved, heads: int,
+                grid: Optional[Tuple[int, int]], precision: int, Wd16=None, dout16=None):
+    """returns dx and the parameter gradients in reference (state_dict) layouts.  `saved` is pa_forward's tuple; its last
+    entry is the module input (fp32 in SIMT mode, its bf16 copy in tensor-core mode)."""
     lib = _lib.load()
-    XF, w, s, tok, q, k, v, A, O, P = saved
-    B, N, C_ = x.shape
+    XF, w, s, tok, q, k, v, A, O, P, xs = saved
+    x = xs
+    B, N, C_ = xshape
     I2 = XF.shape[1]
     I = I2 // 2
     H = heads
@@ -316,19 +330,22 @@ def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, save
     G = Ws.shape[0]
     Cout = Wo.shape[0]
     HG = H * G
-    dev = x.device
+    dev = dout.device
     f32 = dict(device=dev, dtype=torch.float32)
     st = _stream()
     structured = grid is not None
     taps = 9 if structured else 1
-    nchunk = lib.tbns_slice_nchunk(N)
+    Hg, Wg = grid if structured else (1, N)
+    groups = lib.tbns_slice_groups(B, N, H)
+    tc = w.dtype == torch.bfloat16   # forward ran the tensor-core path and kept bf16 copies
 
     # (3') deslice (+) to_out backward
     dbo = colsum(dout, B * N, Cout)
     dP = torch.empty(B, HG, Cout, **f32)
     dw = torch.empty(B, N, HG, **f32)
-    if w.dtype == torch.bfloat16:   # tensor-core mode (forward kept bf16 copies)
-        dout16 = cast_bf16(dout)
+    if tc:
+        if dout16 is None:
+            dout16 = cast_bf16(dout)
         gemm_tc_wgrad(w, dout16, B, 1, N, HG, Cout, batched=1, C=dP, tag="deslice_dP")
         gemm_tc(dout16, P, dw, None, B, 1, N, Cout, HG, w_batched=1, tag="deslice_dw")
     else:
@@ -346,49 +363,44 @@ def pa_backward(dout, x, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, save
     _count(3)  # token_attn_bwd, slice_bwd, dtau_finish
     dWqkv = reduce_rows(dWqkv_part, B * H, 3 * D * D).view(3, D, D)
     dWo = reduce_rows(dWo_part, B, Cout * I).view(Cout, I)
-    # (1') slice backward
-    dXF = torch.empty(B * N, I2, **f32)
-    dWs_part = torch.empty(B * H * nchunk, G * (D + 1), **f32)
-    dtau_part = torch.empty(B * H * nchunk, **f32)
-    check(lib.tbns_pa_slice_bwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw), _p(dTt), _p(ds), _p(dXF), _p(dWs_part),
-                                _p(dtau_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd")
-    dWsb = reduce_rows(dWs_part, B * H * nchunk, G * (D + 1)).view(G, D + 1)
+    # (1') slice backward (+ bias gradients of the projections)
+    dXF = None if tc else torch.empty(B * N, I2, **f32)
+    dXF16 = torch.empty(B * N, I2, device=dev, dtype=torch.bfloat16) if tc else None
+    dWs_part = torch.empty(B * H * groups, G * (D + 1), **f32)
+    dtau_part = torch.empty(B * H * groups, **f32)
+    dbcat_part = torch.empty(B * groups, H * 2 * D, **f32)
+    check(lib.tbns_pa_slice_bwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw), _p(dTt), _p(ds), _p(dXF), _p(dXF16), _p(dWs_part),
+                                _p(dtau_part), _p(dbcat_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd")
+    dWsb = reduce_rows(dWs_part, B * H * groups, G * (D + 1)).view(G, D + 1)
     dWs, dbs = dWsb[:, :D].contiguous(), dWsb[:, D].contiguous()
+    dbc = reduce_rows(dbcat_part, B * groups, H * 2 * D).view(H, 2, D)
+    dbx, dbfx = dbc[:, 0, :].reshape(I), dbc[:, 1, :].reshape(I)
     dtemp = torch.empty(H, **f32)
-    check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, nchunk, int(structured), st), "tbns_pa_dtau_finish")
-    # (1a') projections: dgrad, wgrad (scattered straight into Conv2d / Linear weight layout), bias
+    check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, groups, int(structured), st), "tbns_pa_dtau_finish")
+    # (1a') projections: dgrad, wgrad (scattered straight into Conv2d / Linear weight layout)
     dx = torch.empty(B, N, C_, **f32)
     dWx = torch.empty(Wx_shape, **f32)
     dWfx = torch.empty(Wx_shape, **f32)
-    Hg, Wg = grid if structured else (1, N)
-    bf16 = precision == TBNS_PREC_BF16
-    use_tc_dgrad = bf16 and Wd16 is not None
-    use_tc_wgrad = bf16 and wgrad_supported(C_, I2, taps)
-    dXF16 = cast_bf16(dXF) if (use_tc_dgrad or use_tc_wgrad) else None
-    if use_tc_dgrad:
+    if tc:
         gemm_tc(dXF16, Wd16, dx, None, B, Hg, Wg, I2, C_, taps, 1, tag="proj_dgrad")
+        gemm_tc_wgrad(xs, dXF16, B, Hg, Wg, C_, I2, taps=taps, scatter=(dWx, dWfx), I=I, tag="proj_wgrad")
     elif structured:
         gemm(M=B * N, N=C_, K=9 * I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=dx, ldc=C_, conv_mode=1, Hg=Hg, Wg=Wg,
              Cin=I2, flip=1, precision=precision, tag="proj_dgrad")
-    else:
-        gemm(M=B * N, N=C_, K=I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=I2, b_kind=0, C=dx, ldc=C_, precision=precision,
-             tag="proj_dgrad")
-    if use_tc_wgrad:
-        gemm_tc_wgrad(cast_bf16(x), dXF16, B, Hg, Wg, C_, I2, taps=taps, scatter=(dWx, dWfx), I=I, tag="proj_wgrad")
-    elif structured:
         gemm(M=9 * C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, conv_mode=2, Hg=Hg, Wg=Wg, Cin=C_,
              precision=precision, split_k=_split_k(9 * C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=9, tag="proj_wgrad")
     else:
+        gemm(M=B * N, N=C_, K=I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=I2, b_kind=0, C=dx, ldc=C_, precision=precision,
+             tag="proj_dgrad")
         gemm(M=C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, Cin=C_, precision=precision,
              split_k=_split_k(C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=1, tag="proj_wgrad")
-    dbcat = colsum(dXF, B * N, I2)
-    return dx, dict(temperature=dtemp.view(1, H, 1, 1), Wx=dWx, bx=dbcat[:I], Wfx=dWfx, bfx=dbcat[I:], Ws=dWs, bs=dbs,
+    return dx, dict(temperature=dtemp.view(1, H, 1, 1), Wx=dWx, bx=dbx, Wfx=dWfx, bfx=dbfx, Ws=dWs, bs=dbs,
                     Wq=dWqkv[0], Wk=dWqkv[1], Wv=dWqkv[2], Wo=dWo, bo=dbo)
 
 
 class PhysicsAttentionFn(torch.autograd.Function):
-    """y = PhysicsAttention(x) (+ residual).  Parameters arrive in reference layout; Wf/Wd/bcat are the packed
-    copies (non-differentiable inputs, refreshed by the module when the masters change)."""
+    """y = PhysicsAttention(x) (+ residual).  Parameters arrive in reference layout; `packed` holds the packed projection
+    weights (fp32 and bf16 copies; non-differentiable, refreshed by the module when the masters change)."""
 
     @staticmethod
     def forward(ctx, x, residual, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, packed, heads, grid, precision):
@@ -400,17 +412,17 @@ class PhysicsAttentionFn(torch.autograd.Function):
         temperature_c = temperature.contiguous()
         out, saved = pa_forward(x, temperature_c, Wf, bcat, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
                                 Wv.contiguous(), Wo.contiguous(), bo.contiguous(), residual, heads, grid, precision, Wf16)
-        ctx.save_for_backward(x, temperature_c, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved)
+        ctx.save_for_backward(temperature_c, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved)
         ctx.Wd16 = Wd16
-        ctx.cfg = (heads, grid, precision, tuple(Wx.shape), residual is not None)
+        ctx.cfg = (heads, grid, precision, tuple(Wx.shape), residual is not None, tuple(x.shape))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        heads, grid, precision, wshape, has_res = ctx.cfg
-        x, temperature, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved = ctx.saved_tensors
+        heads, grid, precision, wshape, has_res, xshape = ctx.cfg
+        temperature, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved = ctx.saved_tensors
         dout = dout.contiguous()
-        dx, g = pa_backward(dout, x, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
+        dx, g = pa_backward(dout, xshape, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
                             Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16)
         return (dx, dout if has_res else None, g["temperature"], g["Wx"], g["bx"], g["Wfx"], g["bfx"], g["Ws"], g["bs"], g["Wq"],
                 g["Wk"], g["Wv"], g["Wo"], g["bo"], None, None, None, None)
