@@ -1,0 +1,5 @@
+// explicit instantiations of the slice kernels for dim_head = 8
+#include "slice_v2.cuh"
+namespace tbns {
+TBNS_SLICE_INSTANTIATE_D(8)
+}
