@@ -151,8 +151,13 @@ def run_ours(args):
     model = Model(**CFG).to(dev)
     train.broadcast_parameters(model)
     grads = train.FlatGradients(model.parameters())
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5, fused=True)
-    total_steps = 2 * (args.steps + args.warmup) + 8
+    graphed = bool(args.graph)
+    if args.precision == "bf16":
+        # the preprocess MLP (outside the Physics-Attention path, still PyTorch) may use TF32 tensor cores in bf16 mode
+        torch.backends.cuda.matmul.allow_tf32 = True
+    opt = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-3, device=dev) if graphed else 1e-3, weight_decay=1e-5,
+                            fused=True, capturable=graphed)
+    total_steps = 2 * (args.steps + args.warmup) + 16
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-3, total_steps=total_steps)
 
     h = CFG["H"]
@@ -160,12 +165,21 @@ def run_ours(args):
     pool = [train.synthetic_ns_batch(PER_GPU_BATCH, h, T_IN, T_OUT, seed=1000 * rank + i, pin=True) for i in range(4)]
     dev_pool = [tuple(t.to(dev) for t in b) for b in pool]
     batched = bool(args.batched)
+    gstep = None
+    if graphed:
+        ops.LAUNCHES = 0
+        gstep = train.GraphedTrainStep(model, opt, sched, grads, dev_pool[0], T_OUT, STEP, batched=batched, warmup=3)
+        launches_per_step = ops.LAUNCHES // 4   # 3 eager warm-ups + 1 capture pass
 
     def step_device(i):
         x, fx, yy = dev_pool[i % len(dev_pool)]
+        if graphed:
+            return gstep((x, fx, yy))           # device->device copy into the static buffers + graph replay
         return train.train_step(model, opt, sched, grads, x, fx, yy, T_OUT, STEP, batched=batched)
 
     def step_e2e(i):
+        if graphed:
+            return float(gstep(pool[i % len(pool)]).item())   # pinned host -> static device buffers, replay, D2H loss
         x, fx, yy = (t.to(dev, non_blocking=True) for t in pool[i % len(pool)])
         loss = train.train_step(model, opt, sched, grads, x, fx, yy, T_OUT, STEP, batched=batched)
         return float(loss.item())  # D2H read of the step's result
@@ -188,6 +202,8 @@ def run_ours(args):
         barrier()
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)
+        if graphed:
+            ops.LAUNCHES = launches_per_step * steps   # kernels inside the replayed graph
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -197,9 +213,24 @@ def run_ours(args):
     for i in range(args.warmup):
         step_device(i)
     # device-resident timing, with CUDA-event pairs around the dominant kernel (projection conv fprop)
-    ops.PROFILE = {}
+    if not graphed:
+        ops.PROFILE = {}
     ms_dev, launches, clocks = timed(step_device, args.steps, ClockSampler(local) if rank == 0 else None)
     prof, ops.PROFILE = ops.PROFILE, None
+    prof_ms = ms_dev
+    if graphed:
+        # kernels inside a replayed graph cannot be bracketed by events: time the dominant kernel in eager replays of the
+        # same step (same shapes, same buffers) right after the timed region
+        ops.PROFILE = {}
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for i in range(3):
+            x, fx, yy = dev_pool[i % len(dev_pool)]
+            train.train_step(model, opt, None, grads, x, fx, yy, T_OUT, STEP, batched=batched)
+        pe1.record()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        prof_ms = pe0.elapsed_time(pe1)
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
@@ -219,11 +250,12 @@ def run_ours(args):
             roof = {"kernel": "projection conv3x3 fprop (implicit GEMM, x|fx fused)", "bound": "tensor", "achieved": ach,
                     "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
                     "peak_source": pk["source"] + " (sustained bf16 cuBLAS)", "avg_launch_ms": avg_ms, "launches_timed": len(durs),
-                    "share_of_step": sum(durs) / ms_dev}
+                    "share_of_step": sum(durs) / prof_ms,
+                    "timed": "eager replays after the graph-timed region" if graphed else "inside the timed region"}
             for tag in ("proj_dgrad", "proj_wgrad"):
                 if prof.get(tag):
                     d2 = [a.elapsed_time(b) for a, b in prof[tag]]
-                    roof[tag + "_share_of_step"] = sum(d2) / ms_dev
+                    roof[tag + "_share_of_step"] = sum(d2) / prof_ms
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, t_call, cores = cpu_reference_run(3, 1)
@@ -235,7 +267,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": gb, "parallelism": f"dp{world}",
-                       "teacher_forced_calls_batched": batched,
+                       "teacher_forced_calls_batched": batched, "cuda_graph": graphed,
                        "l2": "activations written per step (>1 GB) exceed the 126 MB L2; fresh input batch every step"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": per_step_in, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -254,6 +286,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batched", type=int, default=1, help="evaluate the 10 teacher-forced calls as one batch (same math)")
+    ap.add_argument("--graph", type=int, default=0, help="capture the whole optimizer step into a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -32,6 +32,16 @@ int splitk_reduce(const tbns_gemm_desc& d, cudaStream_t st);  // gemm_simt.cu
 
 #define TBNS_LAUNCH_CHECK() TBNS_CUDA(cudaGetLastError())
 
+// opt in to large dynamic shared memory once per kernel (not a stream operation: keep it out of CUDA-graph capture)
+#define TBNS_SMEM_OPT_IN(kernel, bytes)                                                                      \
+  do {                                                                                                       \
+    static int _cur = -1;                                                                                    \
+    if (_cur < (int)(bytes)) {                                                                               \
+      TBNS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));    \
+      _cur = (int)(bytes);                                                                                   \
+    }                                                                                                        \
+  } while (0)
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float warp_sum(float v) {

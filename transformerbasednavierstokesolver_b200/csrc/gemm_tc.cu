@@ -519,7 +519,7 @@ static int pick_bw(int Hg, int Wg, int tokens) {
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
-  TBNS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  TBNS_SMEM_OPT_IN((gemm_tc_kernel<BN, STAGES>), S::TOTAL);
   dim3 grid(m_tiles, p.N / BN);
   gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(tmA, tmB, p);
   TBNS_LAUNCH_CHECK();
@@ -529,7 +529,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
 template <int BN, int STAGES>
 static int launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgParams& p, int tiles, int gy, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
-  TBNS_CUDA(cudaFuncSetAttribute(gemm_tc_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  TBNS_SMEM_OPT_IN((gemm_tc_wgrad_kernel<BN, STAGES>), S::TOTAL);
   dim3 grid(tiles, gy);
   gemm_tc_wgrad_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(tmA, tmB, p);
   TBNS_LAUNCH_CHECK();

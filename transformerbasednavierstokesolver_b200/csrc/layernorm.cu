@@ -233,7 +233,7 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
   TBNS_REQUIRE(smem <= 200 * 1024, "tbns_layernorm_bwd: C=%d too large", C);
   static bool attr_set = false;
   if (!attr_set) {
-    TBNS_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TBNS_SMEM_OPT_IN((layernorm_bwd_kernel), 200 * 1024);
     attr_set = true;
   }
   int ctas = cdiv(rows, LN_WARPS * 4);

@@ -400,7 +400,7 @@ extern "C" int tbns_pa_token_attn_fwd(const float* part, int nchunk, const float
     stage = 1;
     smem += token_fwd_stage_smem(D, G, Cout);
   }
-  TBNS_CUDA(cudaFuncSetAttribute(token_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+  TBNS_SMEM_OPT_IN((token_attn_fwd_kernel), (int)SMEM_LIMIT);
   dim3 grid(H, B);
   token_attn_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(part, nchunk, Wq, Wk, Wv, Wo, s, Tt, tok, q, k, v, A, O, P,
                                                                    reinterpret_cast<__nv_bfloat16*>(P16),
@@ -418,7 +418,7 @@ extern "C" int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const fl
   TBNS_REQUIRE(B > 0 && H > 0 && D > 0 && G > 0 && Cout > 0, "tbns_pa_token_attn_bwd: bad dims");
   const size_t smem = token_bwd_smem(D, G);
   TBNS_REQUIRE(smem <= SMEM_LIMIT, "tbns_pa_token_attn_bwd: dim_head=%d slice_num=%d exceed shared memory", D, G);
-  TBNS_CUDA(cudaFuncSetAttribute(token_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+  TBNS_SMEM_OPT_IN((token_attn_bwd_kernel), (int)SMEM_LIMIT);
   dim3 grid(H, B);
   token_attn_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part,
                                                                    dWo_part, H, D, G, Cout);

@@ -361,7 +361,7 @@ template <int D, int G>
 int launch_slice_fwd(const float* XF, const float* Ws, const float* bs, const float* temperature, float* w, __nv_bfloat16* w16,
                             float* part, int B, int N, int H, int groups, int clamp, cudaStream_t st) {
   const size_t smem = slice_fwd_v2_smem<D, G>();
-  TBNS_CUDA(cudaFuncSetAttribute(slice_fwd_v2_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TBNS_SMEM_OPT_IN((slice_fwd_v2_kernel<D, G>), (int)smem);
   dim3 grid(groups, H, B);
   slice_fwd_v2_kernel<D, G><<<grid, TOK, smem, st>>>(XF, Ws, bs, temperature, w, w16, part, N, H, cdiv(N, TOK), clamp);
   TBNS_LAUNCH_CHECK();
@@ -372,7 +372,7 @@ int launch_slice_bwd(const float* XF, const float* Ws, const float* bs, const fl
                             const float* dTt, const float* ds, float* dXF, __nv_bfloat16* dXF16, float* dWs_part, float* dtau_part,
                             float* dbcat_part, int B, int N, int H, int groups, int clamp, cudaStream_t st) {
   const size_t smem = slice_bwd_v2_smem<D, G>();
-  TBNS_CUDA(cudaFuncSetAttribute(slice_bwd_v2_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TBNS_SMEM_OPT_IN((slice_bwd_v2_kernel<D, G>), (int)smem);
   dim3 grid(groups, H, B);
   slice_bwd_v2_kernel<D, G><<<grid, TOK, smem, st>>>(XF, Ws, bs, temperature, dw, dTt, ds, dXF, dXF16, dWs_part, dtau_part, dbcat_part, N,
                                                      H, cdiv(N, TOK), clamp);

@@ -144,3 +144,45 @@ def synthetic_ns_batch(batch: int, h: int, T_in: int, T: int, seed: int, device=
     if device != "cpu":
         out = tuple(t.to(device, non_blocking=True) for t in out)
     return out
+
+
+class GraphedTrainStep:
+    """Whole optimizer step (forward, backward, gradient all-reduce, AdamW, LR schedule) captured ONCE into a CUDA graph and
+    replayed: at cfg 1 a step is ~3500 kernel launches of 5-200 us each, so launch latency, not FLOPs, bounds the eager
+    loop.  Inputs live in static device buffers (`load` copies a host/device batch in, asynchronously); libtbns kernels
+    are plain stream launches with caller-owned memory, so they capture like any other kernel — TMA descriptors are
+    kernel parameters and are frozen into the graph together with the (static) buffer addresses.
+    The optimizer must be constructed with capturable=True (lr lives on the device, the scheduler updates it in place)."""
+
+    def __init__(self, model, optimizer, scheduler, grads: Optional[FlatGradients], example, T: int, step: int = 1,
+                 batched: bool = True, warmup: int = 3):
+        self.model, self.opt, self.sched, self.grads = model, optimizer, scheduler, grads
+        self.T, self.step_, self.batched = T, step, batched
+        self.static = tuple(torch.empty_like(t, device=next(model.parameters()).device) for t in example)
+        self.load(example)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):      # warm-up outside capture: allocator pools, packed-weight caches, cuFuncSetAttribute
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+
+    def _eager(self):
+        x, fx, yy = self.static
+        return train_step(self.model, self.opt, None, self.grads, x, fx, yy, self.T, self.step_, batched=self.batched)
+
+    def load(self, batch):
+        for dst, src in zip(self.static, batch):
+            dst.copy_(src, non_blocking=True)
+
+    def __call__(self, batch=None) -> torch.Tensor:
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        if self.sched is not None:
+            self.sched.step()     # host-side schedule; writes the new lr into the device tensor the graph reads
+        return self.loss
