@@ -153,7 +153,9 @@ struct TcSmem {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int EPI_OFF = (BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 15) & ~15;  // 4 x [32][33] fp32 epilogue transpose tiles
+  static_assert(EPI_OFF % 16 == 0, "epilogue tile alignment");
+  static constexpr int TOTAL = EPI_OFF + 4 * 32 * 33 * 4 + 1024;            // + alignment slack
 };
 
 // shared prologue: barrier init (one thread), TMEM allocation (warp 1), returns the TMEM base address
@@ -265,66 +267,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    // tcgen05.ld hands every thread one accumulator ROW (32 columns per chunk); a per-warp padded shared-memory tile
+    // transposes that to row-cooperative order, so every global access of the fused epilogue (bias, GELU side output,
+    // GELU' input, residual, fp32 / bf16 stores) is a full 128-byte (64-byte for bf16) line per warp instruction.
     const int q = warp & 3;
     const int r = q * 32 + lane;                 // tile row == TMEM lane
     const int hh = r / p.BW, ww = r - hh * p.BW;
     const int h = h0 + hh, w = w0 + ww;
     const bool valid = (h < p.Hg) && (w < p.Wg);
-    const long long grow = ((long long)bimg * p.Hg + h) * p.Wg + w;
+    const long long grow = valid ? ((long long)bimg * p.Hg + h) * p.Wg + w : -1;   // global row of this lane's tile row
+    float* T = reinterpret_cast<float*>(gen + S::EPI_OFF) + q * (32 * 33);
     mbar_wait(bar_acc, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (valid) {
-        const int n = n0 + c0;
-        if (p.bias) {
+      {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (p.act == 1) {
-          if (p.aux_out) {
-            float* ao = p.aux_out + grow * p.ldaux + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ao + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (p.act == 2) {
-          const float* ai = p.aux_in + grow * p.ldaux + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 a = *reinterpret_cast<const float4*>(ai + j);
-            v[j] *= gelu_erf_grad(a.x); v[j + 1] *= gelu_erf_grad(a.y); v[j + 2] *= gelu_erf_grad(a.z); v[j + 3] *= gelu_erf_grad(a.w);
-          }
-        }
-        if (p.residual) {
-          const float* rr = p.residual + grow * p.ldr + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 a = *reinterpret_cast<const float4*>(rr + j);
-            v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
-          }
-        }
-        if (p.C) {
-          float* cr = p.C + grow * p.ldc + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        if (p.C16) {
-          __nv_bfloat16* cr = p.C16 + grow * p.ldc16 + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __nv_bfloat162 o[4] = {__floats2bfloat162_rn(v[j], v[j + 1]), __floats2bfloat162_rn(v[j + 2], v[j + 3]),
-                                   __floats2bfloat162_rn(v[j + 4], v[j + 5]), __floats2bfloat162_rn(v[j + 6], v[j + 7])};
-            *reinterpret_cast<uint4*>(cr + j) = *reinterpret_cast<uint4*>(o);
-          }
-        }
+        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = v[j];
       }
+      __syncwarp();
+      const int n = n0 + c0 + lane;             // this lane's column in stage 2
+      const float bias = p.bias ? p.bias[n] : 0.f;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const long long gr = __shfl_sync(0xffffffffu, grow, rr);
+        if (gr < 0) continue;                   // warp-uniform
+        float x = T[rr * 33 + lane] + bias;
+        if (p.act == 1) {
+          if (p.aux_out) p.aux_out[gr * p.ldaux + n] = x;
+          x = gelu_erf(x);
+        } else if (p.act == 2) {
+          x *= gelu_erf_grad(p.aux_in[gr * p.ldaux + n]);
+        }
+        if (p.residual) x += p.residual[gr * p.ldr + n];
+        if (p.C) p.C[gr * p.ldc + n] = x;
+        if (p.C16) p.C16[gr * p.ldc16 + n] = __float2bfloat16_rn(x);
+      }
+      __syncwarp();
     }
   }
   tc_teardown<BN>(tmem_base, warp);
@@ -424,24 +405,31 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else {
     const int q = warp & 3;
-    const int r = q * 32 + lane;
     const int batch = p.batched ? p.Bimg : 1;
-    float* orow = p.ws + (((long long)split * batch + bidx) * p.Mtot + (long long)tap * p.Ma + mi * TC_BM + r) * p.Nb + ni * BN;
+    // rows q*32 .. q*32+31 of this CTA's 128 x BN tile; stores go through the per-warp transpose tile (coalesced rows)
+    float* obase = p.ws + (((long long)split * batch + bidx) * p.Mtot + (long long)tap * p.Ma + mi * TC_BM + q * 32) * p.Nb + ni * BN;
+    float* T = reinterpret_cast<float*>(gen + S::EPI_OFF) + q * (32 * 33);
     if (nkb > 0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
     }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      if (nkb > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      } else {
+      {
+        float v[32];
+        if (nkb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = v[j];
       }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) obase[(long long)rr * p.Nb + c0 + lane] = T[rr * 33 + lane];
+      __syncwarp();
     }
   }
   tc_teardown<BN>(tmem_base, warp);

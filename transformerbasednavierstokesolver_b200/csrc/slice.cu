@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) token_attn_bwd_kernel(const float* __rest
                                                              const float* __restrict__ A_in, const float* __restrict__ O_in,
                                                              float* __restrict__ dTt, float* __restrict__ ds,
                                                              float* __restrict__ dWqkv_part, float* __restrict__ dWo_part, int H, int D,
-                                                             int G, int Cout) {
+                                                             int G, int Cout, int stage) {
   extern __shared__ float sm[];
   const int DS = D + 1, GD = G * D, GS = G * DS, AS = G + 1;
   float* tok = sm;
@@ -189,6 +189,9 @@ __global__ void __launch_bounds__(256) token_attn_bwd_kernel(const float* __rest
   float* Wqs = ssum + G;      // [D][DS] x3
   float* Wks = Wqs + D * DS;
   float* Wvs = Wks + D * DS;
+  float* dPs = Wvs + D * DS;  // [G][Cout]  (stage != 0) this (b,h)'s rows of dP
+  float* Wos = dPs + G * Cout;  // [Cout][D]  (stage != 0) this head's slice of to_out.weight
+  float* Os = Wos + Cout * D;   // [G][D]     (stage != 0)
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
   const long long bh = (long long)b * H + h;
   const int I = H * D;
@@ -209,20 +212,46 @@ __global__ void __launch_bounds__(256) token_attn_bwd_kernel(const float* __rest
     Wvs[r * DS + c] = Wv[i];
   }
   const float* dPh = dP + ((long long)b * H * G + (long long)h * G) * Cout;  // [G][Cout]
-  // dO[g,d] = sum_c dP[g,c] Wo[c,h*D+d]
-  for (int o = tid; o < GD; o += nt) {
-    const int g = o / D, dd = o - g * D;
-    float acc = 0.f;
-    for (int c = 0; c < Cout; ++c) acc = fmaf(dPh[(long long)g * Cout + c], Wo[(long long)c * I + h * D + dd], acc);
-    dO[g * DS + dd] = acc;
-  }
-  // dWo_part[b, c, h*D+d] = sum_g dP[g,c] O[g,d]
   const float* Oh = O_in + bh * GD;
-  for (int o = tid; o < Cout * D; o += nt) {
-    const int c = o / D, dd = o - c * D;
-    float acc = 0.f;
-    for (int g = 0; g < G; ++g) acc = fmaf(dPh[(long long)g * Cout + c], Oh[g * D + dd], acc);
-    dWo_part[((long long)b * Cout + c) * I + h * D + dd] = acc;
+  if (stage) {
+    for (int o = tid; o < G * Cout; o += nt) dPs[o] = dPh[o];
+    for (int o = tid; o < Cout * D; o += nt) {
+      const int c = o / D, dd = o - c * D;
+      Wos[o] = Wo[(long long)c * I + h * D + dd];
+    }
+    for (int o = tid; o < GD; o += nt) Os[o] = Oh[o];
+    __syncthreads();
+    // dO[g,d] = sum_c dP[g,c] Wo[c,h*D+d]
+    for (int o = tid; o < GD; o += nt) {
+      const int g = o / D, dd = o - g * D;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < Cout; ++c) acc = fmaf(dPs[g * Cout + c], Wos[c * D + dd], acc);
+      dO[g * DS + dd] = acc;
+    }
+    // dWo_part[b, c, h*D+d] = sum_g dP[g,c] O[g,d]
+    for (int o = tid; o < Cout * D; o += nt) {
+      const int c = o / D, dd = o - c * D;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int g = 0; g < G; ++g) acc = fmaf(dPs[g * Cout + c], Os[g * D + dd], acc);
+      dWo_part[((long long)b * Cout + c) * I + h * D + dd] = acc;
+    }
+  } else {
+    // dO[g,d] = sum_c dP[g,c] Wo[c,h*D+d]
+    for (int o = tid; o < GD; o += nt) {
+      const int g = o / D, dd = o - g * D;
+      float acc = 0.f;
+      for (int c = 0; c < Cout; ++c) acc = fmaf(dPh[(long long)g * Cout + c], Wo[(long long)c * I + h * D + dd], acc);
+      dO[g * DS + dd] = acc;
+    }
+    // dWo_part[b, c, h*D+d] = sum_g dP[g,c] O[g,d]
+    for (int o = tid; o < Cout * D; o += nt) {
+      const int c = o / D, dd = o - c * D;
+      float acc = 0.f;
+      for (int g = 0; g < G; ++g) acc = fmaf(dPh[(long long)g * Cout + c], Oh[g * D + dd], acc);
+      dWo_part[((long long)b * Cout + c) * I + h * D + dd] = acc;
+    }
   }
   __syncthreads();
   // dA = dO v^T ; dv = A^T dO
@@ -416,12 +445,18 @@ extern "C" int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const fl
   TBNS_REQUIRE(dP && Wq && Wk && Wv && Wo && s && tok && q && k && v && A && O && dTt && ds && dWqkv_part && dWo_part,
                "tbns_pa_token_attn_bwd: null pointer");
   TBNS_REQUIRE(B > 0 && H > 0 && D > 0 && G > 0 && Cout > 0, "tbns_pa_token_attn_bwd: bad dims");
-  const size_t smem = token_bwd_smem(D, G);
+  size_t smem = token_bwd_smem(D, G);
   TBNS_REQUIRE(smem <= SMEM_LIMIT, "tbns_pa_token_attn_bwd: dim_head=%d slice_num=%d exceed shared memory", D, G);
+  int stage = 0;
+  const size_t extra = sizeof(float) * ((size_t)G * Cout + (size_t)Cout * D + (size_t)G * D);
+  if (smem + extra <= SMEM_LIMIT) {
+    stage = 1;
+    smem += extra;
+  }
   TBNS_SMEM_OPT_IN((token_attn_bwd_kernel), (int)SMEM_LIMIT);
   dim3 grid(H, B);
   token_attn_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part,
-                                                                   dWo_part, H, D, G, Cout);
+                                                                   dWo_part, H, D, G, Cout, stage);
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
