@@ -15,6 +15,7 @@
 //              tcgen05.commit releases ring slots / publishes the accumulator
 //   warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns per warp), + bias, fp32 stores
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -153,9 +154,7 @@ struct TcSmem {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFF = (BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 15) & ~15;  // 4 x [32][33] fp32 epilogue transpose tiles
-  static_assert(EPI_OFF % 16 == 0, "epilogue tile alignment");
-  static constexpr int TOTAL = EPI_OFF + 4 * 32 * 33 * 4 + 1024;            // + alignment slack
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
 // shared prologue: barrier init (one thread), TMEM allocation (warp 1), returns the TMEM base address
@@ -267,48 +266,304 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
-    // tcgen05.ld hands every thread one accumulator ROW (32 columns per chunk); a per-warp padded shared-memory tile
-    // transposes that to row-cooperative order, so every global access of the fused epilogue (bias, GELU side output,
-    // GELU' input, residual, fp32 / bf16 stores) is a full 128-byte (64-byte for bf16) line per warp instruction.
     const int q = warp & 3;
     const int r = q * 32 + lane;                 // tile row == TMEM lane
     const int hh = r / p.BW, ww = r - hh * p.BW;
     const int h = h0 + hh, w = w0 + ww;
     const bool valid = (h < p.Hg) && (w < p.Wg);
-    const long long grow = valid ? ((long long)bimg * p.Hg + h) * p.Wg + w : -1;   // global row of this lane's tile row
-    float* T = reinterpret_cast<float*>(gen + S::EPI_OFF) + q * (32 * 33);
+    const long long grow = ((long long)bimg * p.Hg + h) * p.Wg + w;
     mbar_wait(bar_acc, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (valid) {
+        const int n = n0 + c0;
+        if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = v[j];
-      }
-      __syncwarp();
-      const int n = n0 + c0 + lane;             // this lane's column in stage 2
-      const float bias = p.bias ? p.bias[n] : 0.f;
-#pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        const long long gr = __shfl_sync(0xffffffffu, grow, rr);
-        if (gr < 0) continue;                   // warp-uniform
-        float x = T[rr * 33 + lane] + bias;
-        if (p.act == 1) {
-          if (p.aux_out) p.aux_out[gr * p.ldaux + n] = x;
-          x = gelu_erf(x);
-        } else if (p.act == 2) {
-          x *= gelu_erf_grad(p.aux_in[gr * p.ldaux + n]);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
         }
-        if (p.residual) x += p.residual[gr * p.ldr + n];
-        if (p.C) p.C[gr * p.ldc + n] = x;
-        if (p.C16) p.C16[gr * p.ldc16 + n] = __float2bfloat16_rn(x);
+        if (p.act == 1) {
+          if (p.aux_out) {
+            float* ao = p.aux_out + grow * p.ldaux + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ao + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == 2) {
+          const float* ai = p.aux_in + grow * p.ldaux + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(ai + j);
+            v[j] *= gelu_erf_grad(a.x); v[j + 1] *= gelu_erf_grad(a.y); v[j + 2] *= gelu_erf_grad(a.z); v[j + 3] *= gelu_erf_grad(a.w);
+          }
+        }
+        if (p.residual) {
+          const float* rr = p.residual + grow * p.ldr + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(rr + j);
+            v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+          }
+        }
+        if (p.C) {
+          float* cr = p.C + grow * p.ldc + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (p.C16) {
+          __nv_bfloat16* cr = p.C16 + grow * p.ldc16 + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __nv_bfloat162 o[4] = {__floats2bfloat162_rn(v[j], v[j + 1]), __floats2bfloat162_rn(v[j + 2], v[j + 3]),
+                                   __floats2bfloat162_rn(v[j + 4], v[j + 5]), __floats2bfloat162_rn(v[j + 6], v[j + 7])};
+            *reinterpret_cast<uint4*>(cr + j) = *reinterpret_cast<uint4*>(o);
+          }
+        }
       }
-      __syncwarp();
     }
   }
   tc_teardown<BN>(tmem_base, warp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent TN kernel: one CTA per SM loops over output tiles; the fp32 accumulator is double-buffered in TMEM
+// (2 x BN columns) so the fused epilogue of tile i (8 warps: tcgen05.ld -> bias / GELU / GELU' / residual -> fp32 / bf16
+// stores) overlaps the TMA + tcgen05.mma main loop of tile i+1.  Roles: warp 0 TMA producer, warp 1 TMEM allocator +
+// MMA issuer, warps 2-9 epilogue (warp%4 = TMEM lane quadrant, (warp-2)/4 = which half of the 32-column chunks).
+// ------------------------------------------------------------------------------------------------
+constexpr int TCP_THREADS = 320;
+
+// GELU / GELU' for the tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16
+// rounding applied to the result), one exp shared between erf and the Gaussian density.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-z * z);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * e;
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  pdf = e * 0.39894228040143267794f;   // exp(-x^2/2)/sqrt(2 pi)
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float c, d;
+  gelu_parts(x, c, d);
+  return x * c;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float c, d;
+  gelu_parts(x, c, d);
+  return fmaf(x, d, c);
+}
+
+// fused epilogue of one accumulator row segment: 32 consecutive columns starting at n of global row `grow`
+__device__ __forceinline__ void tc_epi_store(const TcParams& p, float (&v)[32], long long grow, int n) {
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (p.act == 1) {
+    if (p.aux_out) {
+      float* ao = p.aux_out + grow * p.ldaux + n;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ao + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+  } else if (p.act == 2) {
+    const float* ai = p.aux_in + grow * p.ldaux + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(ai + j);
+      v[j] *= gelu_grad_fast(a.x); v[j + 1] *= gelu_grad_fast(a.y); v[j + 2] *= gelu_grad_fast(a.z); v[j + 3] *= gelu_grad_fast(a.w);
+    }
+  }
+  if (p.residual) {
+    const float* rr = p.residual + grow * p.ldr + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(rr + j);
+      v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+    }
+  }
+  if (p.C) {
+    float* cr = p.C + grow * p.ldc + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  if (p.C16) {
+    __nv_bfloat16* cr = p.C16 + grow * p.ldc16 + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      __nv_bfloat162 o[4] = {__floats2bfloat162_rn(v[j], v[j + 1]), __floats2bfloat162_rn(v[j + 2], v[j + 3]),
+                             __floats2bfloat162_rn(v[j + 4], v[j + 5]), __floats2bfloat162_rn(v[j + 6], v[j + 7])};
+      *reinterpret_cast<uint4*>(cr + j) = *reinterpret_cast<uint4*>(o);
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN, int STAGES>
+struct TcpSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int NBAR = 2 * STAGES + 4;  // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
+  static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
+                          int total_tiles) {
+  using S = TcpSmem<BN, STAGES>;
+  constexpr int TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bar_full = base + S::BAR_OFF;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_accf = bar_empty + STAGES * 8;   // [2] accumulator ready (MMA -> epilogue)
+  const uint32_t bar_acce = bar_accf + 16;            // [2] accumulator drained (epilogue -> MMA)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR_OFF + S::NBAR * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.N / BN;
+  const int kc_per_tap = p.Cin / TC_BK;
+  const int nkb = p.taps * kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_accf + a * 8, 1);
+      mbar_init(bar_acce + a * 8, TCP_THREADS - 64);  // every epilogue thread arrives
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;   // running k-block counter across tiles -> ring slot / phase
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles, mt = tile / n_tiles;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, bimg = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH, n0 = nt * BN;
+        const int wb = p.w_batched ? bimg : 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(bar_empty + s * 8, ph ^ 1);
+          const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
+          int dy = 0, dx = 0;
+          if (p.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+            if (p.flip) { dy = -dy; dx = -dx; }
+          }
+          const uint32_t sa = base + s * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
+          mbar_expect_tx(bar_full + s * 8, S::STAGE_BYTES);
+          tma_load_4d(sa, &tmA, bar_full + s * 8, kc * TC_BK, w0 + dx, h0 + dy, bimg);
+          tma_load_3d(sb, &tmB, bar_full + s * 8, kb * TC_BK, n0, wb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16(BN);
+      uint32_t it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+        const uint32_t as = j & 1;
+        mbar_wait(bar_acce + as * 8, ((j >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t dtmem = tmem_base + as * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(bar_full + s * 8, ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UK; ++k) {
+            const uint64_t ad = umma_desc_kmajor_sw128(sa + k * TC_UK * 2);
+            const uint64_t bd = umma_desc_kmajor_sw128(sb + k * TC_UK * 2);
+            umma_bf16(dtmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + s * 8);
+        }
+        umma_commit(bar_accf + as * 8);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..9 =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int hh = r / p.BW, ww = r - hh * p.BW;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const int nt = tile % n_tiles, mt = tile / n_tiles;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, bimg = mt / (p.tiles_w * p.tiles_h);
+      const int h = th * p.BH + hh, w = tw * p.BW + ww;
+      const bool valid = (h < p.Hg) && (w < p.Wg);
+      const long long grow = ((long long)bimg * p.Hg + h) * p.Wg + w;
+      const int n0 = nt * BN;
+      const uint32_t as = j & 1;
+      mbar_wait(bar_accf + as * 8, (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        if (c0 + 64 >= BN) {
+          // last TMEM read of this tile by this thread: hand the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(bar_acce + as * 8);
+        }
+        if (valid) tc_epi_store(p, v, grow, n0 + c0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -405,31 +660,24 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else {
     const int q = warp & 3;
+    const int r = q * 32 + lane;
     const int batch = p.batched ? p.Bimg : 1;
-    // rows q*32 .. q*32+31 of this CTA's 128 x BN tile; stores go through the per-warp transpose tile (coalesced rows)
-    float* obase = p.ws + (((long long)split * batch + bidx) * p.Mtot + (long long)tap * p.Ma + mi * TC_BM + q * 32) * p.Nb + ni * BN;
-    float* T = reinterpret_cast<float*>(gen + S::EPI_OFF) + q * (32 * 33);
+    float* orow = p.ws + (((long long)split * batch + bidx) * p.Mtot + (long long)tap * p.Ma + mi * TC_BM + r) * p.Nb + ni * BN;
     if (nkb > 0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
     }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      {
-        float v[32];
-        if (nkb > 0) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        } else {
+      float v[32];
+      if (nkb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = v[j];
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      __syncwarp();
-#pragma unroll 8
-      for (int rr = 0; rr < 32; ++rr) obase[(long long)rr * p.Nb + c0 + lane] = T[rr * 33 + lane];
-      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
   tc_teardown<BN>(tmem_base, warp);
@@ -515,6 +763,23 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
 }
 
 template <int BN, int STAGES>
+static int launch_tcp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
+  using S = TcpSmem<BN, STAGES>;
+  TBNS_SMEM_OPT_IN((gemm_tc_persistent_kernel<BN, STAGES>), S::TOTAL);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    TBNS_CUDA(cudaGetDevice(&dev));
+    TBNS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int total = m_tiles * (p.N / BN);
+  const int grid = total < sms ? total : sms;
+  gemm_tc_persistent_kernel<BN, STAGES><<<grid, TCP_THREADS, S::TOTAL, st>>>(tmA, tmB, p, total);
+  TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
+}
+
+template <int BN, int STAGES>
 static int launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgParams& p, int tiles, int gy, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
   TBNS_SMEM_OPT_IN((gemm_tc_wgrad_kernel<BN, STAGES>), S::TOTAL);
@@ -571,7 +836,11 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
   int rc = encode_act(&tmA, d.A16, d.Bimg, d.Hg, d.Wg, d.Cin, p.BW, p.BH);
   if (rc) return rc;
   const int N = d.N;
-  const int BN = (N % 256 == 0 && m_tiles * (N / 256) >= 148) ? 256 : (N % 128 == 0 ? 128 : 64);
+  // short K (<= 8 k-blocks: Linear / deslice / MLP contractions): the fused epilogue (GELU, residual, 1-3 output streams)
+  // outweighs the main loop, so run 128-wide tiles with a 3-stage ring (~99 KB) and let TWO CTAs share an SM: one CTA's
+  // epilogue overlaps the other's TMA/MMA phase and twice as many epilogue warps are resident.
+  const bool short_k = (d.taps * d.Cin) / TC_BK <= 8 && N % 128 == 0;
+  const int BN = short_k ? 128 : ((N % 256 == 0 && m_tiles * (N / 256) >= 148) ? 256 : (N % 128 == 0 ? 128 : 64));
   {
     const cuuint64_t K = (cuuint64_t)d.taps * d.Cin;
     cuuint64_t dims[3] = {K, (cuuint64_t)N, (cuuint64_t)(d.w_batched ? d.Bimg : 1)};
@@ -581,8 +850,30 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  static int persist = -1;
+  if (persist < 0) {
+    const char* e = getenv("TBNS_TC_PERSIST");
+    persist = e ? atoi(e) : 1;
+  }
+  if (persist) {
+    // persistent kernel: one CTA per SM, double-buffered TMEM accumulator, 8 epilogue warps
+    const char* e128 = getenv("TBNS_TC_SHORTK_BN128");
+    const bool bn128 = short_k && (e128 ? atoi(e128) != 0 : false);
+    const int BNp = (N % 256 == 0 && !bn128) ? 256 : (N % 128 == 0 ? 128 : 64);
+    if (BNp != BN) {
+      const cuuint64_t K = (cuuint64_t)d.taps * d.Cin;
+      cuuint64_t dims[3] = {K, (cuuint64_t)N, (cuuint64_t)(d.w_batched ? d.Bimg : 1)};
+      cuuint64_t str[2] = {K * 2, K * 2 * (cuuint64_t)N};
+      cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BNp, 1u};
+      rc = encode_bf16(&tmB, d.W16, 3, dims, str, box);
+      if (rc) return rc;
+    }
+    if (BNp == 256) return launch_tcp<256, 4>(tmA, tmB, p, (int)m_tiles, st);
+    if (BNp == 128) return launch_tcp<128, 6>(tmA, tmB, p, (int)m_tiles, st);
+    return launch_tcp<64, 8>(tmA, tmB, p, (int)m_tiles, st);
+  }
   if (BN == 256) return launch_tc<256, 4>(tmA, tmB, p, (int)m_tiles, st);
-  if (BN == 128) return launch_tc<128, 6>(tmA, tmB, p, (int)m_tiles, st);
+  if (BN == 128) return short_k ? launch_tc<128, 3>(tmA, tmB, p, (int)m_tiles, st) : launch_tc<128, 6>(tmA, tmB, p, (int)m_tiles, st);
   return launch_tc<64, 8>(tmA, tmB, p, (int)m_tiles, st);
 }
 
