@@ -170,6 +170,7 @@ def run_ours(args):
         ops.LAUNCHES = 0
         gstep = train.GraphedTrainStep(model, opt, sched, grads, dev_pool[0], T_OUT, STEP, batched=batched, warmup=3)
         launches_per_step = ops.LAUNCHES // 4   # 3 eager warm-ups + 1 capture pass
+        torch.cuda.synchronize()
 
     def step_device(i):
         x, fx, yy = dev_pool[i % len(dev_pool)]
@@ -286,7 +287,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batched", type=int, default=1, help="evaluate the 10 teacher-forced calls as one batch (same math)")
-    ap.add_argument("--graph", type=int, default=0, help="capture the whole optimizer step into a CUDA graph")
+    ap.add_argument("--graph", type=int, default=1, help="replay the optimizer step from CUDA graphs (fwd+bwd graph, eager NCCL "
+                    "all-reduce, optimizer graph); 0 = eager launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -47,7 +47,7 @@ def _worker(rank, world, port, out):
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     if rank == 0:
-        out.put((gathered[0], gathered[1], float(loss)))
+        out.put((gathered[0].tolist(), gathered[1].tolist(), float(loss)))   # plain lists: no shared-memory handles to outlive the worker
     dist.destroy_process_group()
 
 
@@ -59,6 +59,7 @@ def test_dp2_equals_single_process_global_batch():
     for p in procs:
         p.start()
     p0, p1, _ = q.get(timeout=120)
+    p0, p1 = torch.tensor(p0), torch.tensor(p1)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0

@@ -59,16 +59,11 @@ def teacher_forced_inputs(fx: torch.Tensor, yy: torch.Tensor, T: int, step: int 
     return torch.cat([full[..., t:t + T_in] for t in range(0, T, step)], dim=0)
 
 
-def train_step(model, optimizer, scheduler, grads: Optional[FlatGradients], x, fx, yy, T: int, step: int = 1,
-               batched: bool = True, max_grad_norm: Optional[float] = None) -> torch.Tensor:
-    """One optimizer step with exp_ns.py:191-218 semantics; returns the (local) summed step loss as a 0-d tensor.
-    batched=True evaluates the T/step teacher-forced calls as one batch of T/step*B samples — same math (the calls are
-    independent given the ground truth), 1/T as many kernel launches and T x more tokens per launch."""
+def step_loss(model, x, fx, yy, T: int, step: int = 1, batched: bool = True) -> torch.Tensor:
+    """summed relative-L2 loss of the T/step teacher-forced calls (exp_ns.py:197-208).
+    batched=True evaluates them as one batch of T/step*B samples — same math (the calls are independent given the ground
+    truth), 1/T as many kernel launches and T x more tokens per launch."""
     bsz = x.shape[0]
-    if grads is not None:
-        grads.zero()
-    else:
-        optimizer.zero_grad(set_to_none=True)
     if batched:
         calls = T // step
         fx_all = teacher_forced_inputs(fx, yy, T, step)
@@ -83,6 +78,17 @@ def train_step(model, optimizer, scheduler, grads: Optional[FlatGradients], x, f
             im = model(x, fx=fx)
             loss = loss + rel_l2_sum(im.reshape(bsz, -1), y.reshape(bsz, -1))
             fx = torch.cat((fx[..., step:], y), dim=-1)
+    return loss
+
+
+def train_step(model, optimizer, scheduler, grads: Optional[FlatGradients], x, fx, yy, T: int, step: int = 1,
+               batched: bool = True, max_grad_norm: Optional[float] = None) -> torch.Tensor:
+    """One optimizer step with exp_ns.py:191-218 semantics; returns the (local) summed step loss as a 0-d tensor."""
+    if grads is not None:
+        grads.zero()
+    else:
+        optimizer.zero_grad(set_to_none=True)
+    loss = step_loss(model, x, fx, yy, T, step, batched)
     loss.backward()
     if grads is not None:
         grads.all_reduce()
@@ -147,14 +153,17 @@ def synthetic_ns_batch(batch: int, h: int, T_in: int, T: int, seed: int, device=
 
 
 class GraphedTrainStep:
-    """Whole optimizer step (forward, backward, gradient all-reduce, AdamW, LR schedule) captured ONCE into a CUDA graph and
-    replayed: at cfg 1 a step is ~3500 kernel launches of 5-200 us each, so launch latency, not FLOPs, bounds the eager
-    loop.  Inputs live in static device buffers (`load` copies a host/device batch in, asynchronously); libtbns kernels
-    are plain stream launches with caller-owned memory, so they capture like any other kernel — TMA descriptors are
-    kernel parameters and are frozen into the graph together with the (static) buffer addresses.
-    The optimizer must be constructed with capturable=True (lr lives on the device, the scheduler updates it in place)."""
+    """Optimizer step replayed from CUDA graphs: at cfg 1 a step is ~3900 kernel launches of 5-200 us each, so launch
+    latency matters for the eager loop (and dominates it when the teacher-forced calls are not batched).
+    Two graphs are captured once: (1) zero-grad + forward + backward, (2) AdamW; the NCCL gradient all-reduce runs
+    eagerly between them (collectives are kept out of capture on purpose: replicas replay independently and a captured
+    collective can deadlock against host-side scheduling).  Inputs live in static device buffers (`load` copies a host
+    or device batch in, asynchronously).  libtbns kernels are plain stream launches on caller-owned memory, so they
+    capture like any other kernel: TMA descriptors are kernel parameters and are frozen into the graph together with the
+    static buffer addresses.  The optimizer must be built with capturable=True and a tensor lr (the host-side scheduler
+    writes the new lr into that tensor after each replay)."""
 
-    def __init__(self, model, optimizer, scheduler, grads: Optional[FlatGradients], example, T: int, step: int = 1,
+    def __init__(self, model, optimizer, scheduler, grads: FlatGradients, example, T: int, step: int = 1,
                  batched: bool = True, warmup: int = 3):
         self.model, self.opt, self.sched, self.grads = model, optimizer, scheduler, grads
         self.T, self.step_, self.batched = T, step, batched
@@ -163,17 +172,25 @@ class GraphedTrainStep:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):      # warm-up outside capture: allocator pools, packed-weight caches, cuFuncSetAttribute
-                self._eager()
+            for _ in range(warmup):      # warm-up outside capture: allocator pools, packed-weight caches, smem opt-ins
+                self._fwd_bwd()
+                self.grads.all_reduce()
+                self.opt.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._eager()
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self.loss = self._fwd_bwd()
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+            self.opt.step()
 
-    def _eager(self):
+    def _fwd_bwd(self):
         x, fx, yy = self.static
-        return train_step(self.model, self.opt, None, self.grads, x, fx, yy, self.T, self.step_, batched=self.batched)
+        self.grads.zero()
+        loss = step_loss(self.model, x, fx, yy, self.T, self.step_, self.batched)
+        loss.backward()
+        return loss.detach()
 
     def load(self, batch):
         for dst, src in zip(self.static, batch):
@@ -182,7 +199,9 @@ class GraphedTrainStep:
     def __call__(self, batch=None) -> torch.Tensor:
         if batch is not None:
             self.load(batch)
-        self.graph.replay()
+        self.g_fb.replay()
+        self.grads.all_reduce()
+        self.g_opt.replay()
         if self.sched is not None:
             self.sched.step()     # host-side schedule; writes the new lr into the device tensor the graph reads
         return self.loss
