@@ -87,6 +87,7 @@ typedef struct tbns_tc_desc {
   const float* residual; long long ldr;
   float* C; long long ldc;      /* fp32 output or NULL                                                  */
   void* C16; long long ldc16;   /* bf16 output or NULL (operand of the next tensor-core contraction)    */
+  int round_tf32;               /* 1: round the fp32 output to TF32 (RNA): it feeds kind::tf32 MMAs downstream */
 } tbns_tc_desc;
 int tbns_gemm_tc_supported(int Cin, int N, int taps);
 int tbns_gemm_tc(const tbns_tc_desc* d, void* stream);
@@ -144,6 +145,18 @@ int tbns_pack_proj_weights(const float* Wx, const float* bx, const float* Wfx, c
 int tbns_slice_groups(int B, int N, int H);  /* partials per (batch, head) written by the slice kernels */
 int tbns_pa_slice_fwd(const float* XF, const float* Ws, const float* bs, const float* temperature, float* w, void* w16,
                       float* part, int B, int N, int H, int D, int G, int clamp, void* stream);
+
+/* Tensor-core variant of the slice stage (tcgen05.mma kind::tf32 on 128-token x one-head tiles, softmax fused between the
+ * two contractions); bf16 mode, dim_head == 32 and slice_num in {32, 64} (tbns_pa_slice_tc_supported).  Same outputs as
+ * tbns_pa_slice_fwd with w16 only. */
+int tbns_pa_slice_tc_supported(int D, int G);
+int tbns_pa_slice_fwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, void* w16, float* part,
+                         int B, int N, int H, int D, int G, int clamp, void* stream);
+/* backward twin: dXF16 (bf16) only; the projection-bias gradients follow from dbs and s on the host side
+ * (db_x = dbs.Ws, db_fx = s.dTt), so no dbcat_part is produced. */
+int tbns_pa_slice_bwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, const float* dw,
+                         const float* dTt, const float* ds, void* dXF16, float* dWs_part, float* dtau_part, int B, int N,
+                         int H, int D, int G, int clamp, void* stream);
 
 /* Token stage (model/Physics_Attention.py:43-52 / :102-111) + fold of to_out into P:
  *   reduces `part` -> s[B,H,G], Tt[B,H,G,D]; tok = Tt/(s+1e-5); q,k,v; A = softmax(q k^T D^-1/2); O = A v;

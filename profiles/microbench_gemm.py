@@ -46,3 +46,36 @@ for name, (fn, flops) in cases.items():
     ts.sort()
     med = ts[len(ts) // 2]
     print(f"{name:45s} median {med*1e3:8.1f} us   {flops/med/1e9:8.1f} TFLOP/s")
+
+# slice stage: exact SIMT kernels vs the tcgen05 (tf32) kernels
+from transformerbasednavierstokesolver_b200 import _lib
+lib = _lib.load()
+H, D, G = 8, 32, 32
+N = Hg * Wg
+XFs = torch.randn(M, I2, generator=g).to(dev)
+Ws = (torch.randn(G, D, generator=g) * 0.3).to(dev); bs = torch.randn(G, generator=g).to(dev); tau = torch.full((H,), 0.5, device=dev)
+groups = lib.tbns_slice_groups(B, N, H)
+w16 = torch.empty(B, N, H * G, device=dev, dtype=torch.bfloat16)
+part = torch.empty(B * H * groups * G * (D + 1), device=dev)
+dw = torch.randn(B, N, H * G, generator=g).to(dev); dTt = torch.randn(B, H, G, D, generator=g).to(dev); ds = torch.randn(B, H, G, generator=g).to(dev)
+dXF16o = torch.empty(M, I2, device=dev, dtype=torch.bfloat16)
+dWs_p = torch.empty(B * H * groups, G * (D + 1), device=dev); dtau_p = torch.empty(B * H * groups, device=dev); dbc = torch.empty(B * groups, H * 2 * D, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+P = lambda t: t.data_ptr()
+cases2 = {
+    "slice_fwd SIMT": lambda: lib.tbns_pa_slice_fwd(P(XFs), P(Ws), P(bs), P(tau), None, P(w16), P(part), B, N, H, D, G, 1, st),
+    "slice_fwd tcgen05": lambda: lib.tbns_pa_slice_fwd_tc(P(XFs), P(Ws), P(bs), P(tau), P(w16), P(part), B, N, H, D, G, 1, st),
+    "slice_bwd SIMT": lambda: lib.tbns_pa_slice_bwd(P(XFs), P(Ws), P(bs), P(tau), P(dw), P(dTt), P(ds), None, P(dXF16o), P(dWs_p), P(dtau_p), P(dbc), B, N, H, D, G, 1, st),
+    "slice_bwd tcgen05": lambda: lib.tbns_pa_slice_bwd_tc(P(XFs), P(Ws), P(bs), P(tau), P(dw), P(dTt), P(ds), P(dXF16o), P(dWs_p), P(dtau_p), B, N, H, D, G, 1, st),
+}
+for name, fn in cases2.items():
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    print(f"{name:45s} median {ts[len(ts)//2]*1e3:8.1f} us")

@@ -148,3 +148,75 @@ def test_tc_plain_wgrad(Bimg, Ntok, Ma, Nb, batched):
     if not batched:
         ref = ref.sum(0, keepdim=True)
     assert O.rel_l2(out.cpu(), ref.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,H,G", [(2, 4096, 8, 32), (1, 1000, 4, 64), (3, 130, 2, 32)])
+def test_tc_slice_fwd_matches_simt(B, N, H, G):
+    """tensor-core slice forward (tf32 MMAs) vs the exact fp32 SIMT kernel: slice weights and token partials"""
+    from transformerbasednavierstokesolver_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    D = 32
+    g = torch.Generator().manual_seed(B * N + G)
+    XF = torch.randn(B * N, 2 * H * D, generator=g).to(dev)
+    Ws = (torch.randn(G, D, generator=g) * 0.4).to(dev)
+    bs = torch.randn(G, generator=g).to(dev)
+    tau = torch.linspace(0.3, 1.5, H).to(dev)
+    groups = lib.tbns_slice_groups(B, N, H)
+    st = torch.cuda.current_stream().cuda_stream
+    w_ref = torch.empty(B, N, H * G, device=dev)
+    part_ref = torch.empty(B * H * groups * G * (D + 1), device=dev)
+    _lib.check(lib.tbns_pa_slice_fwd(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), w_ref.data_ptr(), None,
+                                     part_ref.data_ptr(), B, N, H, D, G, 1, st), "slice_fwd")
+    w16 = torch.full((B, N, H * G), float("nan"), device=dev, dtype=torch.bfloat16)
+    part = torch.full((B * H * groups * G * (D + 1),), float("nan"), device=dev)
+    _lib.check(lib.tbns_pa_slice_fwd_tc(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), w16.data_ptr(), part.data_ptr(),
+                                        B, N, H, D, G, 1, st), "slice_fwd_tc")
+    torch.cuda.synchronize()
+    assert O.rel_l2(w16.float().cpu(), w_ref.cpu()) < 5e-3          # bf16 storage (4e-3) + tf32 logits
+    p = part.view(B, H, groups, G, D + 1).sum(2).cpu()
+    pr = part_ref.view(B, H, groups, G, D + 1).sum(2).cpu()
+    assert O.rel_l2(p, pr) < 2e-3
+    assert O.rel_l2(p[..., D], pr[..., D]) < 1e-3                     # sum_n w (fp32 SIMT column sums)
+
+
+@pytest.mark.parametrize("B,N,H,G", [(2, 4096, 8, 32), (1, 1000, 4, 64), (3, 130, 2, 32)])
+def test_tc_slice_bwd_matches_simt(B, N, H, G):
+    """tensor-core slice backward (tf32 MMAs) vs the exact fp32 SIMT kernel"""
+    from transformerbasednavierstokesolver_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    D = 32
+    I = H * D
+    g = torch.Generator().manual_seed(B * N + G + 1)
+    XF = torch.randn(B * N, 2 * I, generator=g)
+    XF = ((XF.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).to(dev)   # tf32-representable, as the projection GEMM emits it
+    Ws = (torch.randn(G, D, generator=g) * 0.4).to(dev)
+    bs = torch.randn(G, generator=g).to(dev)
+    tau = torch.linspace(0.3, 1.5, H).to(dev)
+    dw = torch.randn(B, N, H * G, generator=g).to(dev)
+    dTt = torch.randn(B, H, G, D, generator=g).to(dev)
+    ds = torch.randn(B, H, G, generator=g).to(dev)
+    groups = lib.tbns_slice_groups(B, N, H)
+    st = torch.cuda.current_stream().cuda_stream
+    dXF_ref = torch.empty(B * N, 2 * I, device=dev)
+    dWs_ref = torch.empty(B * H * groups, G * (D + 1), device=dev)
+    dtau_ref = torch.empty(B * H * groups, device=dev)
+    dbc_ref = torch.empty(B * groups, H * 2 * D, device=dev)
+    _lib.check(lib.tbns_pa_slice_bwd(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), dw.data_ptr(), dTt.data_ptr(),
+                                     ds.data_ptr(), dXF_ref.data_ptr(), None, dWs_ref.data_ptr(), dtau_ref.data_ptr(), dbc_ref.data_ptr(),
+                                     B, N, H, D, G, 1, st), "slice_bwd")
+    dXF16 = torch.full((B * N, 2 * I), float("nan"), device=dev, dtype=torch.bfloat16)
+    dWs_p = torch.full((B * H * groups, G * (D + 1)), float("nan"), device=dev)
+    dtau_p = torch.full((B * H * groups,), float("nan"), device=dev)
+    _lib.check(lib.tbns_pa_slice_bwd_tc(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), dw.data_ptr(), dTt.data_ptr(),
+                                        ds.data_ptr(), dXF16.data_ptr(), dWs_p.data_ptr(), dtau_p.data_ptr(), B, N, H, D, G, 1, st),
+               "slice_bwd_tc")
+    torch.cuda.synchronize()
+    assert O.rel_l2(dXF16.float().cpu(), dXF_ref.cpu()) < 6e-3          # bf16 storage + tf32 operands
+    a = dWs_p.view(B, H, groups, G, D + 1).sum((0, 1, 2)).cpu()
+    r = dWs_ref.view(B, H, groups, G, D + 1).sum((0, 1, 2)).cpu()
+    assert O.rel_l2(a, r) < 3e-3
+    ta = dtau_p.view(B, H, groups).sum((0, 2)).cpu()
+    tr = dtau_ref.view(B, H, groups).sum((0, 2)).cpu()
+    assert O.rel_l2(ta, tr) < 1e-2     # sum of signed dL'*L terms: cancellation amplifies the tf32 operand rounding

@@ -49,6 +49,7 @@ class TcDesc(C.Structure):
         ("residual", _fp), ("ldr", _ll),
         ("C", _fp), ("ldc", _ll),
         ("C16", _fp), ("ldc16", _ll),
+        ("round_tf32", _i),
     ]
 
 
@@ -84,6 +85,9 @@ _SIGS = {
     "tbns_pack_proj_weights": (_i, [_fp] * 7 + [_i, _i, _i, _fp]),
     "tbns_slice_groups": (_i, [_i, _i, _i]),
     "tbns_pa_slice_fwd": (_i, [_fp] * 7 + [_i] * 6 + [_fp]),
+    "tbns_pa_slice_tc_supported": (_i, [_i, _i]),
+    "tbns_pa_slice_fwd_tc": (_i, [_fp] * 6 + [_i] * 6 + [_fp]),
+    "tbns_pa_slice_bwd_tc": (_i, [_fp] * 10 + [_i] * 6 + [_fp]),
     "tbns_pa_token_attn_fwd": (_i, [_fp, _i] + [_fp] * 15 + [_i] * 5 + [_fp]),
     "tbns_pa_token_attn_bwd": (_i, [_fp] * 16 + [_i] * 5 + [_fp]),
     "tbns_pa_slice_bwd": (_i, [_fp] * 12 + [_i] * 6 + [_fp]),

@@ -14,16 +14,12 @@
 //   warp 1   : allocates TMEM, one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
 //              tcgen05.commit releases ring slots / publishes the accumulator
 //   warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns per warp), + bias, fp32 stores
-#include <cuda.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tbns {
 
-constexpr int TC_BM = 128;      // UMMA M
-constexpr int TC_BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int TC_UK = 16;       // UMMA K for 16-bit inputs
 constexpr int TC_THREADS = 192;
 
 struct TcParams {
@@ -42,6 +38,7 @@ struct TcParams {
   int BW, BH;               // the 128-token M tile is a BH x BW patch of the grid (BW*BH == 128)
   int tiles_w, tiles_h;
   int N, w_batched;
+  int round_tf32;           // round the fp32 output to TF32 (round-to-nearest): it is the operand of tf32 MMAs downstream
 };
 
 struct WgParams {
@@ -52,101 +49,6 @@ struct WgParams {
   int m_chunks, n_chunks;
   int batched, split_k;
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-               "l"(map), "r"(bar), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address  [0,14)
-  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major) [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset = 1024 B between 8-row groups [32,46)
-  d |= (uint64_t)1 << 46;                           // descriptor version 1 [46,48)
-  d |= (uint64_t)2 << 61;                           // layout type SWIZZLE_128B [61,64)
-  return d;
-}
-// MN-major, 128B-swizzled operand: panels of 64 MN-elements (128 B) x K rows; 8-row atoms of 1024 B along K (SBO),
-// `panel_bytes` between consecutive 64-element MN panels (LBO).  (cute/atom/mma_traits_sm100.hpp canonical MN layout)
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr, uint32_t panel_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((panel_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor: D=f32, A=B=bf16, M=128, N=n; mn_major=1 -> both operands MN-major (token-major wgrad operands)
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int mn_major = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(TC_BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 template <int BN, int STAGES>
 struct TcSmem {
@@ -311,6 +213,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
           }
         }
+        if (p.round_tf32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j]));
+            v[j] = __uint_as_float(u);
+          }
+        }
         if (p.C) {
           float* cr = p.C + grow * p.ldc + n;
 #pragma unroll
@@ -395,6 +305,14 @@ __device__ __forceinline__ void tc_epi_store(const TcParams& p, float (&v)[32], 
     for (int j = 0; j < 32; j += 4) {
       const float4 a = *reinterpret_cast<const float4*>(rr + j);
       v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+    }
+  }
+  if (p.round_tf32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j]));
+      v[j] = __uint_as_float(u);
     }
   }
   if (p.C) {
@@ -697,41 +615,6 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
   }
 }
 
-// ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
-static int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                       const cuuint32_t* box) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) {
-    set_error("cuTensorMapEncodeTiled not available from the driver");
-    return TBNS_ERR_CUDA;
-  }
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return TBNS_ERR_CUDA;
-  }
-  return TBNS_OK;
-}
-
 // NHWC activation map [Bimg, Hg, Wg, F] with a {64, BW, BH, 1} box
 static int encode_act(CUtensorMap* m, const void* ptr, int Bimg, int Hg, int Wg, int F, int BW, int BH) {
   cuuint64_t dims[4] = {(cuuint64_t)F, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)Bimg};
@@ -828,7 +711,7 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
   p.Bimg = d.Bimg; p.Hg = d.Hg; p.Wg = d.Wg; p.Cin = d.Cin; p.taps = d.taps; p.flip = d.flip;
   p.BW = pick_bw(d.Hg, d.Wg, TC_BM); p.BH = TC_BM / p.BW;
   p.tiles_w = cdiv(d.Wg, p.BW); p.tiles_h = cdiv(d.Hg, p.BH);
-  p.N = d.N; p.w_batched = d.w_batched;
+  p.N = d.N; p.w_batched = d.w_batched; p.round_tf32 = d.round_tf32;
   const long long m_tiles = (long long)d.Bimg * p.tiles_w * p.tiles_h;
   TBNS_REQUIRE(m_tiles <= 0x7fffffffLL, "tbns_gemm_tc: too many tiles");
 

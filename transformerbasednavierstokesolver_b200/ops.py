@@ -135,7 +135,7 @@ def tc_supported(Cin: int, N: int, taps: int) -> bool:
 
 
 def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps=1, flip=0, tag=None, *, C16=None, w_batched=0, act=0, aux_out=None,
-            aux_in=None, residual=None):
+            aux_in=None, residual=None, round_tf32=0):
     """tcgen05 implicit GEMM, K-major operands (include/tbns.h: tbns_gemm_tc).  C fp32 and/or C16 bf16 outputs [.., N]."""
     d = _lib.TcDesc()
     d.A16, d.Bimg, d.Hg, d.Wg, d.Cin, d.taps, d.flip = _p(A16), Bimg, Hg, Wg, Cin, taps, flip
@@ -145,6 +145,7 @@ def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps=1, flip=0, tag=None, *
     d.residual, d.ldr = _p(residual), N
     d.C, d.ldc = _p(C), N
     d.C16, d.ldc16 = _p(C16), N
+    d.round_tf32 = round_tf32
     with _Timed(tag):
         check(_lib.load().tbns_gemm_tc(ct.byref(d), _stream()), "tbns_gemm_tc")
     _count(1)
@@ -281,7 +282,8 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
         # tensor-core path: bf16 operands through TMA, tcgen05.mma, fp32 accumulate in TMEM
         if x16 is None:
             x16 = cast_bf16(x)
-        gemm_tc(x16, Wf16, XF, bcat, B, Hg, Wg, C_, I2, taps, 0, tag="proj_fprop")
+        slice_tc = bool(lib.tbns_pa_slice_tc_supported(D, G))
+        gemm_tc(x16, Wf16, XF, bcat, B, Hg, Wg, C_, I2, taps, 0, tag="proj_fprop", round_tf32=int(slice_tc))
     elif structured:
         gemm(M=B * N, N=I2, K=9 * C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=9 * C_, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Hg,
              Wg=Wg, Cin=C_, bias=bcat, precision=precision, tag="proj_fprop")
@@ -293,8 +295,14 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
     w = None if tc else torch.empty(B, N, HG, **f32)
     w16 = torch.empty(B, N, HG, **bf) if tc else None     # tensor-core mode keeps only the bf16 copy
     part = torch.empty(B * H * groups * G * (D + 1), **f32)
-    check(lib.tbns_pa_slice_fwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w), _p(w16), _p(part), B, N, H, D, G, int(structured), st),
-          "tbns_pa_slice_fwd")
+    if tc and slice_tc:
+        with _Timed("slice_fwd"):
+            check(lib.tbns_pa_slice_fwd_tc(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w16), _p(part), B, N, H, D, G, int(structured), st),
+                  "tbns_pa_slice_fwd_tc")
+    else:
+        with _Timed("slice_fwd"):
+            check(lib.tbns_pa_slice_fwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w), _p(w16), _p(part), B, N, H, D, G,
+                                        int(structured), st), "tbns_pa_slice_fwd")
     _count(2)  # + token_attn_fwd below
     # (2) token normalisation + attention among slice tokens + fold of to_out   :102-111 / :43-52
     s = torch.empty(B, H, G, **f32)
@@ -368,13 +376,25 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
     dXF16 = torch.empty(B * N, I2, device=dev, dtype=torch.bfloat16) if tc else None
     dWs_part = torch.empty(B * H * groups, G * (D + 1), **f32)
     dtau_part = torch.empty(B * H * groups, **f32)
-    dbcat_part = torch.empty(B * groups, H * 2 * D, **f32)
-    check(lib.tbns_pa_slice_bwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw), _p(dTt), _p(ds), _p(dXF), _p(dXF16), _p(dWs_part),
-                                _p(dtau_part), _p(dbcat_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd")
+    slice_tc = tc and bool(lib.tbns_pa_slice_tc_supported(D, G))
+    if slice_tc:
+        with _Timed("slice_bwd"):
+            check(lib.tbns_pa_slice_bwd_tc(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw), _p(dTt), _p(ds), _p(dXF16), _p(dWs_part),
+                                           _p(dtau_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd_tc")
+        # projection-bias gradients from token-reduced quantities: db_x = (sum_t dL).Ws, db_fx = (sum_t w).dTt
+        dbs_bh = dWs_part.view(B, H, groups, G, D + 1)[..., D].sum(2)
+        dbx = (dbs_bh.sum(0) @ Ws).reshape(I)
+        dbfx = torch.einsum("bhg,bhgd->hd", s, dTt).reshape(I)
+    else:
+        dbcat_part = torch.empty(B * groups, H * 2 * D, **f32)
+        with _Timed("slice_bwd"):
+            check(lib.tbns_pa_slice_bwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw), _p(dTt), _p(ds), _p(dXF), _p(dXF16),
+                                        _p(dWs_part), _p(dtau_part), _p(dbcat_part), B, N, H, D, G, int(structured), st),
+                  "tbns_pa_slice_bwd")
+        dbc = reduce_rows(dbcat_part, B * groups, H * 2 * D).view(H, 2, D)
+        dbx, dbfx = dbc[:, 0, :].reshape(I), dbc[:, 1, :].reshape(I)
     dWsb = reduce_rows(dWs_part, B * H * groups, G * (D + 1)).view(G, D + 1)
     dWs, dbs = dWsb[:, :D].contiguous(), dWsb[:, D].contiguous()
-    dbc = reduce_rows(dbcat_part, B * groups, H * 2 * D).view(H, 2, D)
-    dbx, dbfx = dbc[:, 0, :].reshape(I), dbc[:, 1, :].reshape(I)
     dtemp = torch.empty(H, **f32)
     check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, groups, int(structured), st), "tbns_pa_dtau_finish")
     # (1a') projections: dgrad, wgrad (scattered straight into Conv2d / Linear weight layout)
