@@ -116,14 +116,15 @@ int tbns_cast_bf16(const float* in, void* out, long long n, void* stream);
  * LayerNorm over the last dim (nn.LayerNorm(hidden_dim), eps 1e-5):
  *   model/Transolver_Structured_Mesh_2D.py:59,63,66 and forward :70-73
  * ------------------------------------------------------------------------------------------- */
-int tbns_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+/* y (fp32) and/or y16 (bf16 copy: TMA operand of the next tensor-core contraction); either may be NULL */
+int tbns_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, void* y16, float* mean, float* rstd,
                        int rows, int C, float eps, void* stream);
 /* dx = LN'(dy) + (dres ? dres : 0); dgamma/dbeta reduced deterministically through ws
  * (tbns_layernorm_bwd_ws_floats(C) floats). */
 size_t tbns_layernorm_bwd_ws_floats(int C);
 int tbns_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       const float* dres, float* dx, float* dgamma, float* dbeta, float* ws, int rows, int C,
-                       void* stream);
+                       const float* dres, float* dx, void* dx16 /* optional bf16 copy of dx */, float* dgamma, float* dbeta,
+                       float* ws, int rows, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Weight packing for the projections (nn.Conv2d 3x3 / nn.Linear pair in_project_x, in_project_fx:

@@ -130,10 +130,12 @@ def test_layernorm(dev, rows, C):
     gam, bet = torch.randn(C, generator=g), torch.randn(C, generator=g)
     dy = torch.randn(rows, C, generator=g)
     dres = torch.randn(rows, C, generator=g)
-    y, mean, rstd = ops.layernorm_fwd(x.to(dev), gam.to(dev), bet.to(dev))
+    y, y16, mean, rstd = ops.layernorm_fwd(x.to(dev), gam.to(dev), bet.to(dev), want16=True)
+    assert torch.equal(y16, y.bfloat16())
     ry, rmean, rrstd = O.layernorm_fwd(x.double(), gam.double(), bet.double())
     assert O.rel_l2(y.cpu(), ry) < 2e-6
-    dx, dg, db = ops.layernorm_bwd(dy.to(dev), x.to(dev), mean, rstd, gam.to(dev), dres.to(dev))
+    dx, dx16, dg, db = ops.layernorm_bwd(dy.to(dev), x.to(dev), mean, rstd, gam.to(dev), dres.to(dev), want16=True)
+    assert torch.equal(dx16, dx.bfloat16())
     rdx, rdg, rdb = O.layernorm_bwd(dy.double(), x.double(), rmean, rrstd, gam.double())
     assert O.rel_l2(dx.cpu(), rdx + dres.double()) < 5e-6
     assert O.rel_l2(dg.cpu(), rdg) < 5e-6

@@ -64,7 +64,7 @@ def test_invalid_arguments_fail_loudly(lib):
     d.M, d.N, d.K = 4, 4, 4
     assert lib.tbns_gemm(ctypes.byref(d), None) == -1  # null operands
     with pytest.raises(_lib.TbnsError):
-        _lib.check(lib.tbns_layernorm_fwd(None, None, None, None, None, None, 4, 4, 1e-5, None), "ln")
+        _lib.check(lib.tbns_layernorm_fwd(None, None, None, None, None, None, None, 4, 4, 1e-5, None), "ln")
 
 
 def test_no_cpu_path():

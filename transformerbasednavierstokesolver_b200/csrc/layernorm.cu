@@ -10,13 +10,14 @@ constexpr int LN_MAX_CTAS = 296;  // 2 x 148 SMs
 
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, float* __restrict__ y,
-                                                                    float* __restrict__ mean, float* __restrict__ rstd, int rows,
-                                                                    int C, float eps) {
+                                                                    __nv_bfloat16* __restrict__ y16, float* __restrict__ mean,
+                                                                    float* __restrict__ rstd, int rows, int C, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= rows) return;
   const float* xr = x + (long long)row * C;
-  float* yr = y + (long long)row * C;
+  float* yr = y ? y + (long long)row * C : nullptr;
+  __nv_bfloat16* yr16 = y16 ? y16 + (long long)row * C : nullptr;
   const bool vec = (C & 3) == 0;
   float s = 0.f;
   if (vec) {
@@ -52,10 +53,18 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const floa
       o.y = (v.y - mu) * rs * g.y + b.y;
       o.z = (v.z - mu) * rs * g.z + b.z;
       o.w = (v.w - mu) * rs * g.w + b.w;
-      *reinterpret_cast<float4*>(yr + c) = o;
+      if (yr) *reinterpret_cast<float4*>(yr + c) = o;
+      if (yr16) {
+        __nv_bfloat162 h2[2] = {__floats2bfloat162_rn(o.x, o.y), __floats2bfloat162_rn(o.z, o.w)};
+        *reinterpret_cast<uint2*>(yr16 + c) = *reinterpret_cast<uint2*>(h2);
+      }
     }
   } else {
-    for (int c = lane; c < C; c += 32) yr[c] = (xr[c] - mu) * rs * gamma[c] + beta[c];
+    for (int c = lane; c < C; c += 32) {
+      const float o = (xr[c] - mu) * rs * gamma[c] + beta[c];
+      if (yr) yr[c] = o;
+      if (yr16) yr16[c] = __float2bfloat16_rn(o);
+    }
   }
   if (lane == 0) {
     mean[row] = mu;
@@ -67,7 +76,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const floa
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     const float* __restrict__ gamma, const float* __restrict__ dres,
-                                                                    float* __restrict__ dx, float* __restrict__ part, int rows, int C) {
+                                                                    float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
+                                                                    float* __restrict__ part, int rows, int C) {
   extern __shared__ __align__(16) float sm[];  // [LN_WARPS][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* dg = sm + (long long)warp * 2 * C;
@@ -108,6 +118,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
           o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
         }
         *reinterpret_cast<float4*>(dx + (long long)row * C + c) = o;
+        if (dx16) {
+          __nv_bfloat162 h2[2] = {__floats2bfloat162_rn(o.x, o.y), __floats2bfloat162_rn(o.z, o.w)};
+          *reinterpret_cast<uint2*>(dx16 + (long long)row * C + c) = *reinterpret_cast<uint2*>(h2);
+        }
         float4* pg = reinterpret_cast<float4*>(dg + c);  // lane-private columns: no race
         float4* pb = reinterpret_cast<float4*>(db + c);
         float4 ag = *pg, ab = *pb;
@@ -131,6 +145,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
       float o = (d * gamma[c] - c1 - xh * c2) * rs;
       if (dres) o += dres[(long long)row * C + c];
       dx[(long long)row * C + c] = o;
+      if (dx16) dx16[(long long)row * C + c] = __float2bfloat16_rn(o);
       dg[c] += d * xh;  // lane-private columns: no race
       db[c] += d;
     }
@@ -197,12 +212,12 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
 
 using namespace tbns;
 
-extern "C" int tbns_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
-                                  int rows, int C, float eps, void* stream) {
-  TBNS_REQUIRE(x && gamma && beta && y && mean && rstd, "tbns_layernorm_fwd: null pointer");
+extern "C" int tbns_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, void* y16, float* mean,
+                                  float* rstd, int rows, int C, float eps, void* stream) {
+  TBNS_REQUIRE(x && gamma && beta && (y || y16) && mean && rstd, "tbns_layernorm_fwd: null pointer");
   TBNS_REQUIRE(rows >= 0 && C > 0, "tbns_layernorm_fwd: bad dims");
   if (rows == 0) return TBNS_OK;
-  layernorm_fwd_kernel<<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, rstd, rows, C, eps);
+  layernorm_fwd_kernel<<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, reinterpret_cast<__nv_bfloat16*>(y16), mean, rstd, rows, C, eps);
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
@@ -225,8 +240,8 @@ extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long
 }
 
 extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                                  const float* dres, float* dx, float* dgamma, float* dbeta, float* ws, int rows, int C,
-                                  void* stream) {
+                                  const float* dres, float* dx, void* dx16, float* dgamma, float* dbeta, float* ws, int rows,
+                                  int C, void* stream) {
   TBNS_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws, "tbns_layernorm_bwd: null pointer");
   TBNS_REQUIRE(rows > 0 && C > 0, "tbns_layernorm_bwd: bad dims");
   const size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
@@ -240,7 +255,7 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
   if (ctas > LN_MAX_CTAS) ctas = LN_MAX_CTAS;
   if (ctas < 1) ctas = 1;
   cudaStream_t st = (cudaStream_t)stream;
-  layernorm_bwd_kernel<<<ctas, LN_WARPS * 32, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, ws, rows, C);
+  layernorm_bwd_kernel<<<ctas, LN_WARPS * 32, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx16), ws, rows, C);
   TBNS_LAUNCH_CHECK();
   // ws rows are [dgamma | dbeta], width 2C
   if ((C & 3) == 0) {

@@ -71,6 +71,25 @@ class _PhysicsAttentionBase(nn.Module):
             self.to_v.weight, lin.weight, lin.bias, packed, self.heads, grid, prec)
 
 
+def _forward_block(self, fx, ln):
+    """fx + self(ln(fx)) as ONE fused autograd stage (used by Transolver_block): LayerNorm, attention, residual."""
+    if not fx.is_cuda:
+        raise RuntimeError("Physics-Attention (B200) has no CPU path: move the module and its input to a CUDA device")
+    if self.training and self.dropout.p > 0.0:
+        raise NotImplementedError("dropout > 0 in training mode is not supported by the fused kernels")
+    grid = self._grid(tuple(fx.shape))
+    packed = self._packed_weights()
+    prec = ops.PRECISIONS[self.precision or config.get_default_precision()]
+    lin = self.to_out[0]
+    return ops.AttnBlockFn.apply(
+        fx.float(), ln.weight, ln.bias, ln.eps, self.temperature, self.in_project_x.weight, self.in_project_x.bias,
+        self.in_project_fx.weight, self.in_project_fx.bias, self.in_project_slice.weight, self.in_project_slice.bias,
+        self.to_q.weight, self.to_k.weight, self.to_v.weight, lin.weight, lin.bias, packed, self.heads, grid, prec)
+
+
+_PhysicsAttentionBase.forward_block = _forward_block
+
+
 class Physics_Attention_Irregular_Mesh(_PhysicsAttentionBase):
     """for irregular meshes in 1D, 2D or 3D space (temperature is NOT clamped, reference :40)."""
 

@@ -61,9 +61,7 @@ class Transolver_block(nn.Module):
 
     def forward(self, fx):
         prec = ops.PRECISIONS[self.Attn.precision or config.get_default_precision()]
-        fx = fx.contiguous()
-        x1 = ops.LayerNormFn.apply(fx, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps)
-        fx = self.Attn(x1, residual=fx)
+        fx = self.Attn.forward_block(fx.contiguous(), self.ln_1)
         pre, post = self.mlp.linear_pre[0], self.mlp.linear_post
         fx = ops.LnMlpFn.apply(fx, self.ln_2.weight, self.ln_2.bias, pre.weight, pre.bias, post.weight, post.bias, self.ln_2.eps, prec)
         if self.last_layer:

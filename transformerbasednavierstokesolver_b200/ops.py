@@ -179,46 +179,69 @@ def gemm_tc_wgrad(A16, B16, Bimg, Hg, Wg, Ma, Nb, taps=1, batched=0, C=None, sca
 # ------------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------------
-def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5):
+def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5, want32: bool = True, want16: bool = False):
+    """returns (y fp32 | None, y16 bf16 | None, mean, rstd)"""
     _chk(x, gamma, beta)
     C_ = x.shape[-1]
     rows = x.numel() // C_
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if want32 else None
+    y16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want16 else None
     mean = torch.empty(rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
-    check(_lib.load().tbns_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C_, eps, _stream()),
+    check(_lib.load().tbns_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(y16), _p(mean), _p(rstd), rows, C_, eps, _stream()),
           "tbns_layernorm_fwd")
     _count(1)
-    return y, mean, rstd
+    return y, y16, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, want16: bool = False):
+    """returns (dx, dx16 | None, dgamma, dbeta); dx = LN'(dy) + dres"""
     _chk(dy, x, mean, rstd, gamma, dres)
     lib = _lib.load()
     C_ = x.shape[-1]
     rows = x.numel() // C_
     dx = torch.empty_like(x)
+    dx16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want16 else None
     dg = torch.empty(C_, device=x.device, dtype=torch.float32)
     db = torch.empty(C_, device=x.device, dtype=torch.float32)
     ws = torch.empty(lib.tbns_layernorm_bwd_ws_floats(C_), device=x.device, dtype=torch.float32)
-    check(lib.tbns_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dg), _p(db), _p(ws), rows, C_,
-                                 _stream()), "tbns_layernorm_bwd")
+    check(lib.tbns_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), _p(dg), _p(db), _p(ws),
+                                 rows, C_, _stream()), "tbns_layernorm_bwd")
     _count(3)
-    return dx, dg, db
+    return dx, dx16, dg, db
+
+
+# bf16 copies of gradients handed from one fused backward stage to the next (producer: LayerNorm backward, consumer: the
+# tensor-core contractions of the stage autograd runs next on the very same tensor).  Keyed by storage address.
+_GRAD16 = {}
+
+
+def _stash_grad16(t: torch.Tensor, t16: Optional[torch.Tensor]):
+    if t16 is not None:
+        if len(_GRAD16) > 64:
+            _GRAD16.clear()
+        _GRAD16[t.data_ptr()] = (t16, tuple(t.shape), t._version)
+
+
+def _take_grad16(t: torch.Tensor) -> Optional[torch.Tensor]:
+    e = _GRAD16.pop(t.data_ptr(), None)
+    if e is not None and e[1] == tuple(t.shape) and e[2] == t._version:
+        return e[0]
+    return None
 
 
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):
         x = x.contiguous()
-        y, mean, rstd = layernorm_fwd(x, gamma.contiguous(), beta.contiguous(), eps)
+        y, _, mean, rstd = layernorm_fwd(x, gamma.contiguous(), beta.contiguous(), eps)
         ctx.save_for_backward(x, mean, rstd, gamma)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, mean, rstd, gamma = ctx.saved_tensors
-        dx, dg, db = layernorm_bwd(dy.contiguous(), x, mean, rstd, gamma.contiguous())
+        dx, _, dg, db = layernorm_bwd(dy.contiguous(), x, mean, rstd, gamma.contiguous())
         return dx, dg, db, None
 
 
@@ -260,7 +283,7 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
                grid: Optional[Tuple[int, int]], precision: int, Wf16=None, x16=None):
     """returns (out, saved tuple). x [B,N,C]; Wf/bcat packed projections; residual [B,N,Cout] or None."""
     lib = _lib.load()
-    B, N, C_ = x.shape
+    B, N, C_ = (x if x is not None else x16).shape
     I2 = Wf.shape[0]
     I = I2 // 2
     H = heads
@@ -268,7 +291,7 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
     G = Ws.shape[0]
     Cout = Wo.shape[0]
     HG = H * G
-    dev = x.device
+    dev = (x if x is not None else x16).device
     f32 = dict(device=dev, dtype=torch.float32)
     bf = dict(device=dev, dtype=torch.bfloat16)
     st = _stream()
@@ -448,6 +471,43 @@ class PhysicsAttentionFn(torch.autograd.Function):
                 g["Wk"], g["Wv"], g["Wo"], g["bo"], None, None, None, None)
 
 
+class AttnBlockFn(torch.autograd.Function):
+    """fx + PhysicsAttention(LayerNorm(fx))  — first half of Transolver_block.forward (Transolver_Structured_Mesh_2D.py:70).
+    In tensor-core mode ln_1's output exists only as the bf16 TMA operand; backward fuses the residual branch into the
+    LayerNorm backward kernel and hands a bf16 copy of its result to the previous block's MLP backward."""
+
+    @staticmethod
+    def forward(ctx, fx, ln_w, ln_b, eps, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, packed, heads, grid, precision):
+        fx = fx.contiguous()
+        Wf, Wd, bcat, Wf16, Wd16 = packed
+        ln_w, ln_b = ln_w.contiguous(), ln_b.contiguous()
+        _chk(fx, ln_w, ln_b, temperature, Ws, bs, Wq, Wk, Wv, Wo, bo, Wf, Wd, bcat)
+        B, N, C_ = fx.shape
+        structured = grid is not None
+        tc = _pa_tc_ok(precision, C_, Wf.shape[0], heads * Ws.shape[0], Wo.shape[0], 9 if structured else 1, Wf16 is not None)
+        x1, x1_16, mean, rstd = layernorm_fwd(fx, ln_w, ln_b, eps, want32=not tc, want16=tc)
+        temperature_c = temperature.contiguous()
+        out, saved = pa_forward(x1, temperature_c, Wf, bcat, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
+                                Wv.contiguous(), Wo.contiguous(), bo.contiguous(), fx, heads, grid, precision, Wf16, x16=x1_16)
+        ctx.save_for_backward(fx, ln_w, mean, rstd, temperature_c, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved)
+        ctx.Wd16 = Wd16
+        ctx.cfg = (heads, grid, precision, tuple(Wx.shape), tuple(fx.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        heads, grid, precision, wshape, xshape = ctx.cfg
+        fx, ln_w, mean, rstd, temperature, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved = ctx.saved_tensors
+        dout = dout.contiguous()
+        dout16 = _take_grad16(dout)
+        dx1, g = pa_backward(dout, xshape, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
+                             Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16, dout16=dout16)
+        dfx, dfx16, dlw, dlb = layernorm_bwd(dx1, fx, mean, rstd, ln_w, dres=dout, want16=precision == TBNS_PREC_BF16)
+        _stash_grad16(dfx, dfx16)
+        return (dfx, dlw, dlb, None, g["temperature"], g["Wx"], g["bx"], g["Wfx"], g["bfx"], g["Ws"], g["bs"], g["Wq"], g["Wk"],
+                g["Wv"], g["Wo"], g["bo"], None, None, None, None)
+
+
 # ------------------------------------------------------------------------------------------------
 # LayerNorm + MLP (+ residual)   model/Transolver_Structured_Mesh_2D.py:71 with MLP :13-38 (n_layers=0)
 # ------------------------------------------------------------------------------------------------
@@ -461,13 +521,13 @@ class LnMlpFn(torch.autograd.Function):
         M = fx.numel() // C_
         R = W1.shape[0]
         Cout = W2.shape[0]
-        x2, mean, rstd = layernorm_fwd(fx, gamma, beta, eps)
-        pre = torch.empty(M, R, device=fx.device, dtype=torch.float32)
         use_tc = (precision == TBNS_PREC_BF16 and Cout == C_ and tc_supported(C_, R, 1) and tc_supported(R, Cout, 1)
                   and wgrad_supported(Cout, R, 1) and wgrad_supported(R, C_, 1))
+        x2, x2_16, mean, rstd = layernorm_fwd(fx, gamma, beta, eps, want32=not use_tc, want16=use_tc)
+        pre = torch.empty(M, R, device=fx.device, dtype=torch.float32)
         if use_tc:
-            # tensor-core MLP: bf16 operands, hidden activation only ever exists in bf16 (+ fp32 pre-activation for GELU')
-            x2_16 = cast_bf16(x2)
+            # tensor-core MLP: bf16 operands; LN output and hidden activation only ever exist in bf16 (+ fp32 pre-activation
+            # for GELU')
             hid16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
             gemm_tc(x2_16, cast_bf16(W1), None, b1, 1, 1, M, C_, R, act=1, aux_out=pre, C16=hid16, tag="mlp_fc1")
             out = torch.empty(*fx.shape[:-1], Cout, device=fx.device, dtype=torch.float32)
@@ -498,7 +558,9 @@ class LnMlpFn(torch.autograd.Function):
         db2 = colsum(dout, M, Cout)
         dW2 = torch.empty(Cout, R, **f32)
         if hid.dtype == torch.bfloat16:   # tensor-core mode
-            dout16 = cast_bf16(dout)
+            dout16 = _take_grad16(dout)
+            if dout16 is None:
+                dout16 = cast_bf16(dout)
             gemm_tc_wgrad(dout16, hid, 1, 1, M, Cout, R, C=dW2, tag="mlp_dW2")
             dpre = torch.empty(M, R, **f32)
             dpre16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
@@ -508,8 +570,10 @@ class LnMlpFn(torch.autograd.Function):
             gemm_tc_wgrad(dpre16, x2, 1, 1, M, R, C_, C=dW1, tag="mlp_dW1")
             dx2 = torch.empty(M, C_, **f32)
             gemm_tc(dpre16, cast_bf16(W1.t().contiguous()), dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
-            dfx, dg, db = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout)
-            return dfx.view_as(fx), dg, db, dW1, db1, dW2, db2, None, None
+            dfx, dfx16, dg, db = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout, want16=True)
+            dfx = dfx.view_as(fx)
+            _stash_grad16(dfx, dfx16)     # the attention stage's backward consumes dfx next: hand it the bf16 copy
+            return dfx, dg, db, dW1, db1, dW2, db2, None, None
         gemm(M=Cout, N=R, K=M, A=dout, lda=Cout, a_kind=1, B=hid, ldb=R, b_kind=1, C=dW2, ldc=R, precision=precision,
              split_k=_split_k(Cout, R, M))
         dpre = torch.empty(M, R, **f32)
@@ -521,7 +585,7 @@ class LnMlpFn(torch.autograd.Function):
              split_k=_split_k(R, C_, M))
         dx2 = torch.empty(M, C_, **f32)
         gemm(M=M, N=C_, K=R, A=dpre, lda=R, a_kind=0, B=W1, ldb=C_, b_kind=1, C=dx2, ldc=C_, precision=precision)
-        dfx, dg, db = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout)  # + residual branch
+        dfx, _, dg, db = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout)  # + residual branch
         return dfx.view_as(fx), dg, db, dW1, db1, dW2, db2, None, None
 
 
@@ -536,7 +600,7 @@ class LnLinearFn(torch.autograd.Function):
         C_ = fx.shape[-1]
         M = fx.numel() // C_
         Od = W.shape[0]
-        x3, mean, rstd = layernorm_fwd(fx, gamma, beta, eps)
+        x3, _, mean, rstd = layernorm_fwd(fx, gamma, beta, eps)
         out = torch.empty(*fx.shape[:-1], Od, device=fx.device, dtype=torch.float32)
         gemm(M=M, N=Od, K=C_, A=x3, lda=C_, a_kind=0, B=W, ldb=C_, b_kind=0, C=out, ldc=Od, bias=b, precision=precision)
         ctx.save_for_backward(fx, gamma, W, x3, mean, rstd)
@@ -558,5 +622,7 @@ class LnLinearFn(torch.autograd.Function):
              split_k=_split_k(Od, C_, M))
         dx3 = torch.empty(M, C_, **f32)
         gemm(M=M, N=C_, K=Od, A=dout, lda=Od, a_kind=0, B=W, ldb=C_, b_kind=1, C=dx3, ldc=C_, precision=precision)
-        dfx, dg, dbeta = layernorm_bwd(dx3, fx, mean, rstd, gamma)
-        return dfx.view_as(fx), dg, dbeta, dW, db, None, None
+        dfx, dfx16, dg, dbeta = layernorm_bwd(dx3, fx, mean, rstd, gamma, want16=precision == TBNS_PREC_BF16)
+        dfx = dfx.view_as(fx)
+        _stash_grad16(dfx, dfx16)
+        return dfx, dg, dbeta, dW, db, None, None
