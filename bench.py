@@ -257,6 +257,9 @@ def run_ours(args):
                 if prof.get(tag):
                     d2 = [a.elapsed_time(b) for a, b in prof[tag]]
                     roof[tag + "_share_of_step"] = sum(d2) / prof_ms
+            # warm per-kernel-family device time per step (CUDA events around every tagged libtbns launch, eager replays)
+            nprof = 3 if graphed else args.steps
+            roof["kernel_ms_per_step"] = {t: round(sum(a.elapsed_time(b) for a, b in v) / nprof, 3) for t, v in sorted(prof.items())}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, t_call, cores = cpu_reference_run(3, 1)

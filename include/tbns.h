@@ -124,6 +124,7 @@ int tbns_layernorm_fwd(const float* x, const float* gamma, const float* beta, fl
 size_t tbns_layernorm_bwd_ws_floats(int C);
 int tbns_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                        const float* dres, float* dx, void* dx16 /* optional bf16 copy of dx */, float* dgamma, float* dbeta,
+                       float* dsum /* optional [C]: column sums of dx = bias gradient of the layer that produced this stream */,
                        float* ws, int rows, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

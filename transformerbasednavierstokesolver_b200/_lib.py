@@ -81,7 +81,7 @@ _SIGS = {
     "tbns_cast_bf16": (_i, [_fp, _fp, _ll, _fp]),
     "tbns_layernorm_fwd": (_i, [_fp] * 7 + [_i, _i, C.c_float, _fp]),
     "tbns_layernorm_bwd_ws_floats": (C.c_size_t, [_i]),
-    "tbns_layernorm_bwd": (_i, [_fp] * 11 + [_i, _i, _fp]),
+    "tbns_layernorm_bwd": (_i, [_fp] * 12 + [_i, _i, _fp]),
     "tbns_pack_proj_weights": (_i, [_fp] * 7 + [_i, _i, _i, _fp]),
     "tbns_slice_groups": (_i, [_i, _i, _i]),
     "tbns_pa_slice_fwd": (_i, [_fp] * 7 + [_i] * 6 + [_fp]),

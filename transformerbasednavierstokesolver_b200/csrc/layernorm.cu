@@ -7,6 +7,8 @@ namespace tbns {
 
 constexpr int LN_WARPS = 8;
 constexpr int LN_MAX_CTAS = 296;  // 2 x 148 SMs
+constexpr int LN_BWD_CTAS = 592;  // 4 x 148 SMs
+constexpr int COLSUM_ROWS = 592;  // max row chunks of the column-sum kernel (4 x 148)
 
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, float* __restrict__ y,
@@ -159,6 +161,79 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
   }
 }
 
+// Register-resident variant for C = 128*NV (NV float4 per lane): the row's dy / x values are read ONCE and kept in registers
+// between the two passes, dgamma / dbeta / column-sum accumulators live in registers, one combine through shared memory at
+// the end.  part: [cta][3][C] = dgamma | dbeta | column sums of the OUTPUT dx (= bias gradient of whatever produced the
+// tensor this gradient belongs to; see ops.py).
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                        const float* __restrict__ gamma, const float* __restrict__ dres,
+                                                                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
+                                                                        float* __restrict__ part, int rows) {
+  constexpr int C = NV * 128;
+  __shared__ __align__(16) float sm[LN_WARPS][3][C];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 g4[NV], ag[NV], ab[NV], as[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    g4[k] = *reinterpret_cast<const float4*>(gamma + lane * 4 + k * 128);
+    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[k] = ag[k];
+    as[k] = ag[k];
+  }
+  const float invC = 1.f / (float)C;
+  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+    const long long off = (long long)row * C + lane * 4;
+    const float mu = mean[row], rs = rstd[row];
+    float4 d4[NV], xh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      d4[k] = *reinterpret_cast<const float4*>(dy + off + k * 128);
+      const float4 xv = *reinterpret_cast<const float4*>(x + off + k * 128);
+      xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      const float gx = d4[k].x * g4[k].x, gy = d4[k].y * g4[k].y, gz = d4[k].z * g4[k].z, gw = d4[k].w * g4[k].w;
+      s1 += (gx + gy) + (gz + gw);
+      s2 += gx * xh[k].x + gy * xh[k].y + gz * xh[k].z + gw * xh[k].w;
+    }
+    const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float4 o;
+      o.x = (d4[k].x * g4[k].x - c1 - xh[k].x * c2) * rs;
+      o.y = (d4[k].y * g4[k].y - c1 - xh[k].y * c2) * rs;
+      o.z = (d4[k].z * g4[k].z - c1 - xh[k].z * c2) * rs;
+      o.w = (d4[k].w * g4[k].w - c1 - xh[k].w * c2) * rs;
+      if (dres) {
+        const float4 r4 = *reinterpret_cast<const float4*>(dres + off + k * 128);
+        o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+      }
+      *reinterpret_cast<float4*>(dx + off + k * 128) = o;
+      if (dx16) {
+        __nv_bfloat162 h2[2] = {__floats2bfloat162_rn(o.x, o.y), __floats2bfloat162_rn(o.z, o.w)};
+        *reinterpret_cast<uint2*>(dx16 + off + k * 128) = *reinterpret_cast<uint2*>(h2);
+      }
+      ag[k].x += d4[k].x * xh[k].x; ag[k].y += d4[k].y * xh[k].y; ag[k].z += d4[k].z * xh[k].z; ag[k].w += d4[k].w * xh[k].w;
+      ab[k].x += d4[k].x; ab[k].y += d4[k].y; ab[k].z += d4[k].z; ab[k].w += d4[k].w;
+      as[k].x += o.x; as[k].y += o.y; as[k].z += o.z; as[k].w += o.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    *reinterpret_cast<float4*>(&sm[warp][0][lane * 4 + k * 128]) = ag[k];
+    *reinterpret_cast<float4*>(&sm[warp][1][lane * 4 + k * 128]) = ab[k];
+    *reinterpret_cast<float4*>(&sm[warp][2][lane * 4 + k * 128]) = as[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) s += (&sm[w][0][0])[c];
+    part[(long long)blockIdx.x * 3 * C + c] = s;
+  }
+}
+
 __global__ void colsum_partial_kernel(const float* __restrict__ in, long long ld, float* __restrict__ ws, int rows, int cols,
                                       int rows_per_chunk);
 
@@ -172,7 +247,6 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restri
 
 // Column sums (bias gradients): HBM-bound streaming reduction.  Each CTA owns a 128-column panel and a contiguous chunk of
 // rows; 32 float4-lanes x 8 row-lanes, fixed-order combine in shared memory, then a deterministic second stage.
-constexpr int COLSUM_ROWS = 592;  // max row chunks (4 x 148)
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ in, long long ld, float* __restrict__ ws, int rows,
                                                             int cols, int rows_per_chunk) {
   __shared__ float4 red[8][32];
@@ -222,7 +296,7 @@ extern "C" int tbns_layernorm_fwd(const float* x, const float* gamma, const floa
   return TBNS_OK;
 }
 
-extern "C" size_t tbns_layernorm_bwd_ws_floats(int C) { return (size_t)LN_MAX_CTAS * 2 * (size_t)C; }
+extern "C" size_t tbns_layernorm_bwd_ws_floats(int C) { return (size_t)LN_BWD_CTAS * 3 * (size_t)C; }
 
 extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long cols, void* stream) {
   TBNS_REQUIRE(in && out && rows >= 0 && cols >= 0, "tbns_reduce_rows: bad args");
@@ -240,34 +314,56 @@ extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long
 }
 
 extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                                  const float* dres, float* dx, void* dx16, float* dgamma, float* dbeta, float* ws, int rows,
-                                  int C, void* stream) {
+                                  const float* dres, float* dx, void* dx16, float* dgamma, float* dbeta, float* dsum, float* ws,
+                                  int rows, int C, void* stream) {
   TBNS_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws, "tbns_layernorm_bwd: null pointer");
   TBNS_REQUIRE(rows > 0 && C > 0, "tbns_layernorm_bwd: bad dims");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(dx16);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+                         reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(dx16)) & 15) == 0;
+  if (aligned && (C == 128 || C == 256 || C == 512)) {
+    int ctas = cdiv(rows, LN_WARPS * 2);
+    if (ctas > LN_BWD_CTAS) ctas = LN_BWD_CTAS;
+    if (C == 128) layernorm_bwd_reg_kernel<1><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows);
+    else if (C == 256) layernorm_bwd_reg_kernel<2><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows);
+    else layernorm_bwd_reg_kernel<4><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows);
+    TBNS_LAUNCH_CHECK();
+    // ws rows are [dgamma | dbeta | colsum(dx)], width 3C: one fixed-order reduction for all three
+    colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws, 3LL * C, dgamma, ctas, C, ctas);
+    TBNS_LAUNCH_CHECK();
+    colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws + C, 3LL * C, dbeta, ctas, C, ctas);
+    TBNS_LAUNCH_CHECK();
+    if (dsum) {
+      colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws + 2 * C, 3LL * C, dsum, ctas, C, ctas);
+      TBNS_LAUNCH_CHECK();
+    }
+    return TBNS_OK;
+  }
+  // generic path (any C): per-warp shared-memory accumulators
   const size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
   TBNS_REQUIRE(smem <= 200 * 1024, "tbns_layernorm_bwd: C=%d too large", C);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TBNS_SMEM_OPT_IN((layernorm_bwd_kernel), 200 * 1024);
-    attr_set = true;
-  }
+  TBNS_SMEM_OPT_IN((layernorm_bwd_kernel), 200 * 1024);
   int ctas = cdiv(rows, LN_WARPS * 4);
   if (ctas > LN_MAX_CTAS) ctas = LN_MAX_CTAS;
   if (ctas < 1) ctas = 1;
-  cudaStream_t st = (cudaStream_t)stream;
-  layernorm_bwd_kernel<<<ctas, LN_WARPS * 32, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx16), ws, rows, C);
+  layernorm_bwd_kernel<<<ctas, LN_WARPS * 32, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, C);
   TBNS_LAUNCH_CHECK();
-  // ws rows are [dgamma | dbeta], width 2C
-  if ((C & 3) == 0) {
-    colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws, 2LL * C, dgamma, ctas, C, ctas);
+  reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, dgamma, ctas, C, 2LL * C);
+  TBNS_LAUNCH_CHECK();
+  reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws + C, dbeta, ctas, C, 2LL * C);
+  TBNS_LAUNCH_CHECK();
+  if (dsum) {   // column sums of dx through the generic reduction
+    float* tmp = ws;  // ws is free again: reuse it as the colsum workspace (needs COLSUM_ROWS*C <= LN_BWD_CTAS*3*C floats)
+    int chunks = cdiv(rows, 64);
+    if (chunks > COLSUM_ROWS) chunks = COLSUM_ROWS;
+    const int rpc = cdiv(rows, chunks);
+    chunks = cdiv(rows, rpc);
+    colsum_partial_kernel<<<dim3(cdiv(C, 128), chunks), 256, 0, st>>>(dx, C, tmp, rows, C, rpc);
     TBNS_LAUNCH_CHECK();
-    colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws + C, 2LL * C, dbeta, ctas, C, ctas);
-  } else {
-    reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, dgamma, ctas, C, 2LL * C);
+    reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(tmp, dsum, chunks, C, C);
     TBNS_LAUNCH_CHECK();
-    reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws + C, dbeta, ctas, C, 2LL * C);
   }
-  TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
 

@@ -190,8 +190,9 @@ __global__ void __launch_bounds__(256) token_attn_bwd_kernel(const float* __rest
   float* Wks = Wqs + D * DS;
   float* Wvs = Wks + D * DS;
   float* dPs = Wvs + D * DS;  // [G][Cout]  (stage != 0) this (b,h)'s rows of dP
-  float* Wos = dPs + G * Cout;  // [Cout][D]  (stage != 0) this head's slice of to_out.weight
-  float* Os = Wos + Cout * D;   // [G][D]     (stage != 0)
+  float* Os = dPs + G * Cout; // [G][D]     (stage != 0)
+  // (to_out.weight is read straight from L2: staging it too would cost 32 KB and drop the kernel to one CTA per SM,
+  //  i.e. two waves for the B*H = 160 CTAs of the benchmark shape)
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
   const long long bh = (long long)b * H + h;
   const int I = H * D;
@@ -215,10 +216,6 @@ __global__ void __launch_bounds__(256) token_attn_bwd_kernel(const float* __rest
   const float* Oh = O_in + bh * GD;
   if (stage) {
     for (int o = tid; o < G * Cout; o += nt) dPs[o] = dPh[o];
-    for (int o = tid; o < Cout * D; o += nt) {
-      const int c = o / D, dd = o - c * D;
-      Wos[o] = Wo[(long long)c * I + h * D + dd];
-    }
     for (int o = tid; o < GD; o += nt) Os[o] = Oh[o];
     __syncthreads();
     // dO[g,d] = sum_c dP[g,c] Wo[c,h*D+d]
@@ -226,7 +223,7 @@ __global__ void __launch_bounds__(256) token_attn_bwd_kernel(const float* __rest
       const int g = o / D, dd = o - g * D;
       float acc = 0.f;
 #pragma unroll 8
-      for (int c = 0; c < Cout; ++c) acc = fmaf(dPs[g * Cout + c], Wos[c * D + dd], acc);
+      for (int c = 0; c < Cout; ++c) acc = fmaf(dPs[g * Cout + c], __ldg(Wo + (long long)c * I + h * D + dd), acc);
       dO[g * DS + dd] = acc;
     }
     // dWo_part[b, c, h*D+d] = sum_g dP[g,c] O[g,d]
@@ -448,7 +445,7 @@ extern "C" int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const fl
   size_t smem = token_bwd_smem(D, G);
   TBNS_REQUIRE(smem <= SMEM_LIMIT, "tbns_pa_token_attn_bwd: dim_head=%d slice_num=%d exceed shared memory", D, G);
   int stage = 0;
-  const size_t extra = sizeof(float) * ((size_t)G * Cout + (size_t)Cout * D + (size_t)G * D);
+  const size_t extra = sizeof(float) * ((size_t)G * Cout + (size_t)G * D);
   if (smem + extra <= SMEM_LIMIT) {
     stage = 1;
     smem += extra;

@@ -108,7 +108,8 @@ def gemm(*, M, N, K, A, lda, a_kind, B, ldb, b_kind, C=None, ldc=0, batch=1, sA=
 
 def reduce_rows(inp: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
     out = torch.empty(cols, device=inp.device, dtype=torch.float32)
-    check(_lib.load().tbns_reduce_rows(_p(inp), _p(out), rows, cols, _stream()), "tbns_reduce_rows")
+    with _Timed("reduce_rows"):
+        check(_lib.load().tbns_reduce_rows(_p(inp), _p(out), rows, cols, _stream()), "tbns_reduce_rows")
     _count(1)
     return out
 
@@ -117,7 +118,8 @@ def colsum(inp: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(cols, device=inp.device, dtype=torch.float32)
     ws = torch.empty(lib.tbns_colsum_ws_floats(cols), device=inp.device, dtype=torch.float32)
-    check(lib.tbns_colsum(_p(inp), cols, _p(out), _p(ws), rows, cols, _stream()), "tbns_colsum")
+    with _Timed("colsum"):
+        check(lib.tbns_colsum(_p(inp), cols, _p(out), _p(ws), rows, cols, _stream()), "tbns_colsum")
     _count(2)
     return out
 
@@ -125,7 +127,8 @@ def colsum(inp: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
 def cast_bf16(t: torch.Tensor) -> torch.Tensor:
     """fp32 -> bf16 copy (round to nearest even) through libtbns"""
     out = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
-    check(_lib.load().tbns_cast_bf16(_p(t), _p(out), t.numel(), _stream()), "tbns_cast_bf16")
+    with _Timed("cast_bf16"):
+        check(_lib.load().tbns_cast_bf16(_p(t), _p(out), t.numel(), _stream()), "tbns_cast_bf16")
     _count(1)
     return out
 
@@ -188,14 +191,15 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5, want32: bool 
     y16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want16 else None
     mean = torch.empty(rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
-    check(_lib.load().tbns_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(y16), _p(mean), _p(rstd), rows, C_, eps, _stream()),
-          "tbns_layernorm_fwd")
+    with _Timed("layernorm_fwd"):
+        check(_lib.load().tbns_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(y16), _p(mean), _p(rstd), rows, C_, eps, _stream()),
+              "tbns_layernorm_fwd")
     _count(1)
     return y, y16, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, want16: bool = False):
-    """returns (dx, dx16 | None, dgamma, dbeta); dx = LN'(dy) + dres"""
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, want16: bool = False, want_sum: bool = False):
+    """returns (dx, dx16 | None, dgamma, dbeta[, colsum(dx)]); dx = LN'(dy) + dres"""
     _chk(dy, x, mean, rstd, gamma, dres)
     lib = _lib.load()
     C_ = x.shape[-1]
@@ -204,10 +208,14 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, want16: bool = False):
     dx16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want16 else None
     dg = torch.empty(C_, device=x.device, dtype=torch.float32)
     db = torch.empty(C_, device=x.device, dtype=torch.float32)
+    dsum = torch.empty(C_, device=x.device, dtype=torch.float32) if want_sum else None
     ws = torch.empty(lib.tbns_layernorm_bwd_ws_floats(C_), device=x.device, dtype=torch.float32)
-    check(lib.tbns_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), _p(dg), _p(db), _p(ws),
-                                 rows, C_, _stream()), "tbns_layernorm_bwd")
-    _count(3)
+    with _Timed("layernorm_bwd"):
+        check(lib.tbns_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), _p(dg), _p(db),
+                                     _p(dsum), _p(ws), rows, C_, _stream()), "tbns_layernorm_bwd")
+    _count(4 if want_sum else 3)
+    if want_sum:
+        return dx, dx16, dg, db, dsum
     return dx, dx16, dg, db
 
 
@@ -216,18 +224,19 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, want16: bool = False):
 _GRAD16 = {}
 
 
-def _stash_grad16(t: torch.Tensor, t16: Optional[torch.Tensor]):
-    if t16 is not None:
+def _stash_grad16(t: torch.Tensor, t16: Optional[torch.Tensor], colsum_: Optional[torch.Tensor] = None):
+    if t16 is not None or colsum_ is not None:
         if len(_GRAD16) > 64:
             _GRAD16.clear()
-        _GRAD16[t.data_ptr()] = (t16, tuple(t.shape), t._version)
+        _GRAD16[t.data_ptr()] = (t16, tuple(t.shape), t._version, colsum_)
 
 
-def _take_grad16(t: torch.Tensor) -> Optional[torch.Tensor]:
+def _take_grad16(t: torch.Tensor):
+    """-> (bf16 copy | None, column sums | None) left by the producer of gradient tensor `t`"""
     e = _GRAD16.pop(t.data_ptr(), None)
     if e is not None and e[1] == tuple(t.shape) and e[2] == t._version:
-        return e[0]
-    return None
+        return e[0], e[3]
+    return None, None
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -334,8 +343,9 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
     P = torch.empty(B, HG, Cout, **f32)
     P16 = torch.empty(B, HG, Cout, **bf) if tc else None    # K-major operand of dw = dOut.P^T
     PT16 = torch.empty(B, Cout, HG, **bf) if tc else None   # K-major operand of out = w.P
-    check(lib.tbns_pa_token_attn_fwd(_p(part), groups, _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(Tt), _p(tok), _p(q), _p(k), _p(v),
-                                     _p(A), _p(O), _p(P), _p(P16), _p(PT16), B, H, D, G, Cout, st), "tbns_pa_token_attn_fwd")
+    with _Timed("token_attn_fwd"):
+      check(lib.tbns_pa_token_attn_fwd(_p(part), groups, _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(Tt), _p(tok), _p(q), _p(k), _p(v),
+                                     _p(A), _p(O), _p(P), _p(P16), _p(PT16), B, H, D, G, Cout, st), "tbns_pa_token_attn_fwd")  # noqa: E111
     # (3) deslice (+) to_out (+ bias, + residual)   :116-119 / :55-57
     out = torch.empty(B, N, Cout, **f32)
     if tc:
@@ -347,7 +357,7 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
 
 
 def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, saved, heads: int,
-                grid: Optional[Tuple[int, int]], precision: int, Wd16=None, dout16=None):
+                grid: Optional[Tuple[int, int]], precision: int, Wd16=None, dout16=None, dbo=None):
     """returns dx and the parameter gradients in reference (state_dict) layouts.  `saved` is pa_forward's tuple; its last
     entry is the module input (fp32 in SIMT mode, its bf16 copy in tensor-core mode)."""
     lib = _lib.load()
@@ -371,7 +381,8 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
     tc = w.dtype == torch.bfloat16   # forward ran the tensor-core path and kept bf16 copies
 
     # (3') deslice (+) to_out backward
-    dbo = colsum(dout, B * N, Cout)
+    if dbo is None:
+        dbo = colsum(dout, B * N, Cout)
     dP = torch.empty(B, HG, Cout, **f32)
     dw = torch.empty(B, N, HG, **f32)
     if tc:
@@ -389,7 +400,8 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
     ds = torch.empty(B, H, G, **f32)
     dWqkv_part = torch.empty(B * H, 3 * D * D, **f32)
     dWo_part = torch.empty(B, Cout * I, **f32)
-    check(lib.tbns_pa_token_attn_bwd(_p(dP), _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(tok), _p(q), _p(k), _p(v), _p(A), _p(O),
+    with _Timed("token_attn_bwd"):
+      check(lib.tbns_pa_token_attn_bwd(_p(dP), _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(tok), _p(q), _p(k), _p(v), _p(A), _p(O),
                                      _p(dTt), _p(ds), _p(dWqkv_part), _p(dWo_part), B, H, D, G, Cout, st), "tbns_pa_token_attn_bwd")
     _count(3)  # token_attn_bwd, slice_bwd, dtau_finish
     dWqkv = reduce_rows(dWqkv_part, B * H, 3 * D * D).view(3, D, D)
@@ -499,11 +511,13 @@ class AttnBlockFn(torch.autograd.Function):
         heads, grid, precision, wshape, xshape = ctx.cfg
         fx, ln_w, mean, rstd, temperature, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved = ctx.saved_tensors
         dout = dout.contiguous()
-        dout16 = _take_grad16(dout)
+        dout16, dsum = _take_grad16(dout)
         dx1, g = pa_backward(dout, xshape, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
-                             Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16, dout16=dout16)
-        dfx, dfx16, dlw, dlb = layernorm_bwd(dx1, fx, mean, rstd, ln_w, dres=dout, want16=precision == TBNS_PREC_BF16)
-        _stash_grad16(dfx, dfx16)
+                             Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16, dout16=dout16,
+                             dbo=dsum)
+        dfx, dfx16, dlw, dlb, dfsum = layernorm_bwd(dx1, fx, mean, rstd, ln_w, dres=dout, want16=precision == TBNS_PREC_BF16,
+                                                    want_sum=True)
+        _stash_grad16(dfx, dfx16, dfsum)   # column sums of dfx = to-be bias gradient of the previous block's mlp.linear_post
         return (dfx, dlw, dlb, None, g["temperature"], g["Wx"], g["bx"], g["Wfx"], g["bfx"], g["Ws"], g["bs"], g["Wq"], g["Wk"],
                 g["Wv"], g["Wo"], g["bo"], None, None, None, None)
 
@@ -555,10 +569,11 @@ class LnMlpFn(torch.autograd.Function):
         R = W1.shape[0]
         Cout = W2.shape[0]
         f32 = dict(device=fx.device, dtype=torch.float32)
-        db2 = colsum(dout, M, Cout)
+        dout16, db2 = _take_grad16(dout)
+        if db2 is None:
+            db2 = colsum(dout, M, Cout)
         dW2 = torch.empty(Cout, R, **f32)
         if hid.dtype == torch.bfloat16:   # tensor-core mode
-            dout16 = _take_grad16(dout)
             if dout16 is None:
                 dout16 = cast_bf16(dout)
             gemm_tc_wgrad(dout16, hid, 1, 1, M, Cout, R, C=dW2, tag="mlp_dW2")
@@ -570,9 +585,9 @@ class LnMlpFn(torch.autograd.Function):
             gemm_tc_wgrad(dpre16, x2, 1, 1, M, R, C_, C=dW1, tag="mlp_dW1")
             dx2 = torch.empty(M, C_, **f32)
             gemm_tc(dpre16, cast_bf16(W1.t().contiguous()), dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
-            dfx, dfx16, dg, db = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout, want16=True)
+            dfx, dfx16, dg, db, dfsum = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout, want16=True, want_sum=True)
             dfx = dfx.view_as(fx)
-            _stash_grad16(dfx, dfx16)     # the attention stage's backward consumes dfx next: hand it the bf16 copy
+            _stash_grad16(dfx, dfx16, dfsum)   # the attention stage's backward consumes dfx next: bf16 copy + to_out bias gradient
             return dfx, dg, db, dW1, db1, dW2, db2, None, None
         gemm(M=Cout, N=R, K=M, A=dout, lda=Cout, a_kind=1, B=hid, ldb=R, b_kind=1, C=dW2, ldc=R, precision=precision,
              split_k=_split_k(Cout, R, M))
@@ -622,7 +637,7 @@ class LnLinearFn(torch.autograd.Function):
              split_k=_split_k(Od, C_, M))
         dx3 = torch.empty(M, C_, **f32)
         gemm(M=M, N=C_, K=Od, A=dout, lda=Od, a_kind=0, B=W, ldb=C_, b_kind=1, C=dx3, ldc=C_, precision=precision)
-        dfx, dfx16, dg, dbeta = layernorm_bwd(dx3, fx, mean, rstd, gamma, want16=precision == TBNS_PREC_BF16)
+        dfx, dfx16, dg, dbeta, dfsum = layernorm_bwd(dx3, fx, mean, rstd, gamma, want16=precision == TBNS_PREC_BF16, want_sum=True)
         dfx = dfx.view_as(fx)
-        _stash_grad16(dfx, dfx16)
+        _stash_grad16(dfx, dfx16, dfsum)
         return dfx, dg, dbeta, dW, db, None, None
