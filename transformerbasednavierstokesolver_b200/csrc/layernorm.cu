@@ -7,7 +7,7 @@ namespace tbns {
 
 constexpr int LN_WARPS = 8;
 constexpr int LN_MAX_CTAS = 296;  // 2 x 148 SMs
-constexpr int LN_BWD_CTAS = 592;  // 4 x 148 SMs
+constexpr int LN_BWD_CTAS = 444;  // 3 x 148 SMs: one full wave at the register-limited occupancy of the backward kernel
 constexpr int COLSUM_ROWS = 592;  // max row chunks of the column-sum kernel (4 x 148)
 
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,

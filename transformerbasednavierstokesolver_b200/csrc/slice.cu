@@ -13,10 +13,12 @@
 namespace tbns {
 
 constexpr float EPS_NORM = 1e-5f;
+// one CTA per (batch, head) and only B*H of them: latency-bound chains of tiny contractions -> as many warps as a CTA can hold
+constexpr int TOKEN_THREADS = 1024;
 
 // grid (H, B), block 256.  All [rows][D] shared arrays use the padded stride DS = D+1 (bank-conflict free for both
 // row-wise and column-wise thread mappings).
-__global__ void __launch_bounds__(256) token_attn_fwd_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ Wq,
+__global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ Wq,
                                                              const float* __restrict__ Wk, const float* __restrict__ Wv,
                                                              const float* __restrict__ Wo, float* __restrict__ s_out,
                                                              float* __restrict__ Tt_out, float* __restrict__ tok_out,
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(256) token_attn_fwd_kernel(const float* __rest
 }
 
 // grid (H, B), block 256
-__global__ void __launch_bounds__(256) token_attn_bwd_kernel(const float* __restrict__ dP, const float* __restrict__ Wq,
+__global__ void __launch_bounds__(TOKEN_THREADS) token_attn_bwd_kernel(const float* __restrict__ dP, const float* __restrict__ Wq,
                                                              const float* __restrict__ Wk, const float* __restrict__ Wv,
                                                              const float* __restrict__ Wo, const float* __restrict__ s_in,
                                                              const float* __restrict__ tok_in, const float* __restrict__ q_in,
@@ -428,7 +430,7 @@ extern "C" int tbns_pa_token_attn_fwd(const float* part, int nchunk, const float
   }
   TBNS_SMEM_OPT_IN((token_attn_fwd_kernel), (int)SMEM_LIMIT);
   dim3 grid(H, B);
-  token_attn_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(part, nchunk, Wq, Wk, Wv, Wo, s, Tt, tok, q, k, v, A, O, P,
+  token_attn_fwd_kernel<<<grid, TOKEN_THREADS, smem, (cudaStream_t)stream>>>(part, nchunk, Wq, Wk, Wv, Wo, s, Tt, tok, q, k, v, A, O, P,
                                                                    reinterpret_cast<__nv_bfloat16*>(P16),
                                                                    reinterpret_cast<__nv_bfloat16*>(PT16), H, D, G, Cout, stage);
   TBNS_LAUNCH_CHECK();
@@ -452,7 +454,7 @@ extern "C" int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const fl
   }
   TBNS_SMEM_OPT_IN((token_attn_bwd_kernel), (int)SMEM_LIMIT);
   dim3 grid(H, B);
-  token_attn_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part,
+  token_attn_bwd_kernel<<<grid, TOKEN_THREADS, smem, (cudaStream_t)stream>>>(dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part,
                                                                    dWo_part, H, D, G, Cout, stage);
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;

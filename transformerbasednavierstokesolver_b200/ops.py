@@ -154,6 +154,20 @@ def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps=1, flip=0, tag=None, *
     _count(1)
 
 
+def _wgrad_split(tiles: int, kblocks: int) -> int:
+    """split-K factor of the token-contraction kernel: one CTA per SM (197 KB of shared memory each), so pick the smallest
+    split whose CTA count fills whole waves of 148 SMs (>= 95 %), keeping >= 4 k-blocks per CTA."""
+    best, best_eff = 1, 0.0
+    for s in range(1, max(1, min(148, kblocks // 4)) + 1):
+        ctas = tiles * s
+        eff = ctas / (((ctas + _NUM_SMS - 1) // _NUM_SMS) * _NUM_SMS)
+        if eff >= 0.95:
+            return s
+        if eff > best_eff + 1e-9:
+            best, best_eff = s, eff
+    return best
+
+
 def wgrad_supported(Ma: int, Nb: int, taps: int) -> bool:
     return bool(_lib.load().tbns_gemm_tc_wgrad_supported(Ma, Nb, taps))
 
@@ -165,7 +179,7 @@ def gemm_tc_wgrad(A16, B16, Bimg, Hg, Wg, Ma, Nb, taps=1, batched=0, C=None, sca
     batch = Bimg if batched else 1
     tiles = taps * (Ma // 128) * (Nb // BN) * batch
     kblocks = ((Hg * Wg + 63) // 64) * (1 if batched else Bimg)
-    split = max(1, min((2 * _NUM_SMS + tiles - 1) // tiles, max(1, kblocks // 4), 64))
+    split = _wgrad_split(tiles, kblocks)
     ws = torch.empty(split * batch * taps * Ma * Nb, device=A16.device, dtype=torch.float32)
     d = _lib.TcWgradDesc()
     d.A16, d.Ma, d.B16, d.Nb = _p(A16), Ma, _p(B16), Nb
