@@ -332,3 +332,33 @@ def test_slice_weights_partition_of_unity_full_size(dev):
     # clamp: heads with tau outside [0.1, 5] behave like tau at the bound
     L = (XF[:, :H * D].view(B, N, H, D).double() @ Ws.double().t() + bs.double()) / tau.double().clamp(0.1, 5.0)[None, None, :, None]
     assert O.rel_l2(w4.cpu(), torch.softmax(L, -1).cpu()) < 1e-5
+
+
+def test_cfg5_rollout_shape_block_forward_bf16(dev):
+    """BASELINE cfg 5 shape (256x256 grid, C=256, 8 heads, slice_num 64): one Transolver block forward in bf16 mode against
+    the fp32 oracle on bf16-representable weights/inputs, plus the closed-loop rollout plumbing of train.rollout."""
+    from transformerbasednavierstokesolver_b200 import train
+    from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Model, Transolver_block
+    torch.manual_seed(11)
+    blk = Transolver_block(num_heads=8, hidden_dim=256, dropout=0.0, mlp_ratio=1, last_layer=False, slice_num=64, H=256, W=256)
+    with torch.no_grad():
+        blk.Attn.in_project_slice.weight.mul_(4.0)
+        for p in blk.parameters():
+            p.copy_(p.bfloat16().float())
+    fx = torch.randn(1, 65536, 256).bfloat16().float()
+    sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    ref, _ = O.block_forward(fx, sd, 8, (256, 256))
+    blk.Attn.precision = "bf16"
+    blk = blk.to(dev)
+    with torch.no_grad():
+        out = blk(fx.to(dev))
+    assert O.rel_l2(out.cpu(), ref) < BF16_OUT_TOL
+    # rollout plumbing on a small model at the same slice_num / head shape: window shift feeds predictions back
+    torch.manual_seed(12)
+    m = Model(space_dim=2, n_layers=2, n_hidden=256, n_head=8, fun_dim=10, out_dim=1, slice_num=64, ref=8, unified_pos=1, H=32, W=32).to(dev)
+    x, f, _ = train.synthetic_ns_batch(2, 32, 10, 10, seed=5, device=dev)
+    roll = train.rollout(m, x, f, T=4, step=1)
+    assert roll.shape == (2, 1024, 4) and bool(torch.isfinite(roll).all())
+    with torch.no_grad():
+        first = m(x, fx=f)
+    assert torch.allclose(first[..., 0], roll[..., 0], atol=1e-5)
