@@ -335,6 +335,84 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// tcgen05.ld 16x256b.x4: 16 TMEM lanes x 32 columns per warp instruction.  Thread t receives, for column group j = 0..3,
+// v[4j+0..1] = (lane t/4,     columns 8j + 2(t%4) + {0,1})  and  v[4j+2..3] = (lane t/4 + 8, same columns)
+// (layout probed on hardware: profiles/probes/tmem_ld_shapes.cu).  Four threads cover one 32-byte sector of a row, so the
+// epilogue's global accesses touch 8 full sectors per warp request instead of 32 half-used ones (thread-per-row layout).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// fused epilogue on the two 16x256b fragments of a warp's 32-lane quadrant: v[0] = lanes 0..15, v[1] = lanes 16..31 (layout
+// above); grow[k] = global row of tile row (t/4 + 8k) or -1; n = first of the 32 columns; t = lane id.
+// All global loads (GELU' input, residual) are issued before any arithmetic so their latencies overlap.
+__device__ __forceinline__ void tc_epi_frag2(const TcParams& p, float (&v)[2][16], const long long (&grow)[4], int n, int t) {
+  const int cb = n + 2 * (t & 3);
+  float2 ld[4][4];   // [row k][column group j]
+  const float* src = p.act == 2 ? p.aux_in : p.residual;
+  const long long lds = p.act == 2 ? p.ldaux : p.ldr;
+  if (src) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        ld[k][j] = grow[k] >= 0 ? *reinterpret_cast<const float2*>(src + grow[k] * lds + cb + 8 * j) : make_float2(0.f, 0.f);
+  }
+  float2 bias[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bias[j] = p.bias ? *reinterpret_cast<const float2*>(p.bias + cb + 8 * j) : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long gr = grow[k];
+    if (gr < 0) continue;   // uniform over the four threads that share a row (and exchange with each other below)
+    uint32_t mine[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = cb + 8 * j;
+      float x0 = v[k >> 1][4 * j + 2 * (k & 1)] + bias[j].x, x1 = v[k >> 1][4 * j + 2 * (k & 1) + 1] + bias[j].y;
+      if (p.act == 1) {
+        if (p.aux_out) *reinterpret_cast<float2*>(p.aux_out + gr * p.ldaux + c) = make_float2(x0, x1);
+        x0 = gelu_fast(x0);
+        x1 = gelu_fast(x1);
+      } else if (p.act == 2) {
+        x0 *= gelu_grad_fast(ld[k][j].x);
+        x1 *= gelu_grad_fast(ld[k][j].y);
+      } else if (p.residual) {
+        x0 += ld[k][j].x;
+        x1 += ld[k][j].y;
+      }
+      if (p.round_tf32) {
+        uint32_t u0, u1;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u0) : "f"(x0));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u1) : "f"(x1));
+        x0 = __uint_as_float(u0);
+        x1 = __uint_as_float(u1);
+      }
+      if (p.C) *reinterpret_cast<float2*>(p.C + gr * p.ldc + c) = make_float2(x0, x1);
+      if (p.C16) {
+        // bf16 pairs are only 4 bytes: trade pairs with the neighbouring lane so that every thread owns 4 consecutive columns
+        // (8 bytes) of column group j or j+1 and four threads fill one 32-byte sector of the row
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+        mine[j & 1] = *reinterpret_cast<uint32_t*>(&h2);
+        if (j & 1) {
+          const bool even = (t & 1) == 0;
+          const uint32_t got = __shfl_xor_sync(0xffffffffu, even ? mine[1] : mine[0], 1);
+          uint2 o;
+          o.x = even ? mine[0] : got;
+          o.y = even ? got : mine[1];
+          const int cc = even ? (c - 8) : (c - 2);   // even: group j-1 columns 2a..2a+3 ; odd: group j columns 2a-2..2a+1
+          *reinterpret_cast<uint2*>(p.C16 + gr * p.ldc16 + cc) = o;
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 struct TcpSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
@@ -450,29 +528,36 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // ===== epilogue: warps 2..9 =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int r = q * 32 + lane;
-    const int hh = r / p.BW, ww = r - hh * p.BW;
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const int nt = tile % n_tiles, mt = tile / n_tiles;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, bimg = mt / (p.tiles_w * p.tiles_h);
-      const int h = th * p.BH + hh, w = tw * p.BW + ww;
-      const bool valid = (h < p.Hg) && (w < p.Wg);
-      const long long grow = ((long long)bimg * p.Hg + h) * p.Wg + w;
       const int n0 = nt * BN;
+      // the four tile rows this thread touches: q*32 + lane/4 + 8k
+      long long grow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = q * 32 + (lane >> 2) + 8 * k;
+        const int hh = r / p.BW, ww = r - hh * p.BW;
+        const int h = th * p.BH + hh, w = tw * p.BW + ww;
+        grow[k] = (h < p.Hg && w < p.Wg) ? ((long long)bimg * p.Hg + h) * p.Wg + w : -1;
+      }
       const uint32_t as = j & 1;
       mbar_wait(bar_accf + as * 8, (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += 64) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        float v[2][16];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0);
+        tmem_ld_16x256b_x4(ta, v[0]);                    // lanes q*32 + 0..15
+        tmem_ld_16x256b_x4(ta + (16u << 16), v[1]);      // lanes q*32 + 16..31
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (c0 + 64 >= BN) {
           // last TMEM read of this tile by this thread: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           mbar_arrive(bar_acce + as * 8);
         }
-        if (valid) tc_epi_store(p, v, grow, n0 + c0);
+        tc_epi_frag2(p, v, grow, n0 + c0, lane);
       }
     }
   }
