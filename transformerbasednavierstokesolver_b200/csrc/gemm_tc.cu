@@ -245,9 +245,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Persistent TN kernel: one CTA per SM loops over output tiles; the fp32 accumulator is double-buffered in TMEM
 // (2 x BN columns) so the fused epilogue of tile i (8 warps: tcgen05.ld -> bias / GELU / GELU' / residual -> fp32 / bf16
 // stores) overlaps the TMA + tcgen05.mma main loop of tile i+1.  Roles: warp 0 TMA producer, warp 1 TMEM allocator +
-// MMA issuer, warps 2-9 epilogue (warp%4 = TMEM lane quadrant, (warp-2)/4 = which half of the 32-column chunks).
+// MMA issuer, warps 2-17 epilogue (warp%4 = TMEM lane quadrant, (warp-2)/4 = which quarter of the 32-column chunks): the
+// fused epilogue is instruction-bound (GELU, conversions, 2-3 output streams), so it gets as many warps as registers allow.
 // ------------------------------------------------------------------------------------------------
-constexpr int TCP_THREADS = 320;
+constexpr int TCP_EPI_WARPS = 16;                     // 4 TMEM lane quadrants x 4 column slots
+constexpr int TCP_THREADS = 64 + 32 * TCP_EPI_WARPS;
 
 // GELU / GELU' for the tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16
 // rounding applied to the result), one exp shared between erf and the Gaussian density.
@@ -525,9 +527,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
     }
   } else {
-    // ===== epilogue: warps 2..9 =====
+    // ===== epilogue: warps 2..17 =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int slot = (warp - 2) >> 2;
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const int nt = tile % n_tiles, mt = tile / n_tiles;
@@ -545,20 +547,23 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const uint32_t as = j & 1;
       mbar_wait(bar_accf + as * 8, (j >> 1) & 1);
       tc_fence_after();
+      bool handed_back = false;
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      for (int c0 = slot * 32; c0 < BN; c0 += 32 * (TCP_EPI_WARPS / 4)) {
         float v[2][16];
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0);
         tmem_ld_16x256b_x4(ta, v[0]);                    // lanes q*32 + 0..15
         tmem_ld_16x256b_x4(ta + (16u << 16), v[1]);      // lanes q*32 + 16..31
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 64 >= BN) {
+        if (c0 + 32 * (TCP_EPI_WARPS / 4) >= BN) {
           // last TMEM read of this tile by this thread: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           mbar_arrive(bar_acce + as * 8);
+          handed_back = true;
         }
         tc_epi_frag2(p, v, grow, n0 + c0, lane);
       }
+      if (!handed_back) mbar_arrive(bar_acce + as * 8);   // narrow tiles: this warp's column slot does not exist
     }
   }
   tc_fence_before();
