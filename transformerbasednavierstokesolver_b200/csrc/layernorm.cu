@@ -329,7 +329,13 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
     else if (C == 256) layernorm_bwd_reg_kernel<2><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows);
     else layernorm_bwd_reg_kernel<4><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows);
     TBNS_LAUNCH_CHECK();
-    // ws rows are [dgamma | dbeta | colsum(dx)], width 3C: one fixed-order reduction for all three
+    // ws rows are [dgamma | dbeta | colsum(dx)], width 3C: fixed-order reduction; a single launch when the caller's three
+    // outputs are one contiguous [3][C] array
+    if (dsum && dbeta == dgamma + C && dsum == dgamma + 2 * C) {
+      colsum_partial_kernel<<<dim3(cdiv(3 * C, 128), 1), 256, 0, st>>>(ws, 3LL * C, dgamma, ctas, 3 * C, ctas);
+      TBNS_LAUNCH_CHECK();
+      return TBNS_OK;
+    }
     colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws, 3LL * C, dgamma, ctas, C, ctas);
     TBNS_LAUNCH_CHECK();
     colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws + C, 3LL * C, dbeta, ctas, C, ctas);

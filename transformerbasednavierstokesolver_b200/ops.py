@@ -220,14 +220,14 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, want16: bool = False, wan
     rows = x.numel() // C_
     dx = torch.empty_like(x)
     dx16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want16 else None
-    dg = torch.empty(C_, device=x.device, dtype=torch.float32)
-    db = torch.empty(C_, device=x.device, dtype=torch.float32)
-    dsum = torch.empty(C_, device=x.device, dtype=torch.float32) if want_sum else None
+    out3 = torch.empty(3 if want_sum else 2, C_, device=x.device, dtype=torch.float32)   # contiguous: one reduction launch
+    dg, db = out3[0], out3[1]
+    dsum = out3[2] if want_sum else None
     ws = torch.empty(lib.tbns_layernorm_bwd_ws_floats(C_), device=x.device, dtype=torch.float32)
     with _Timed("layernorm_bwd"):
         check(lib.tbns_layernorm_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), _p(dg), _p(db),
                                      _p(dsum), _p(ws), rows, C_, _stream()), "tbns_layernorm_bwd")
-    _count(4 if want_sum else 3)
+    _count(2 if want_sum else 3)
     if want_sum:
         return dx, dx16, dg, db, dsum
     return dx, dx16, dg, db
