@@ -249,7 +249,10 @@ def run_ours(args):
             avg_ms = sum(durs) / len(durs)
             ach = conv_fprop_flops(tokens_per_launch) / (avg_ms / 1e3) / 1e12
             roof = {"kernel": "projection conv3x3 fprop (implicit GEMM, x|fx fused)", "bound": "tensor", "achieved": ach,
-                    "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
+                    "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
+                    # (profiles/ncu_r01_conv_fprop_persistent.md); algorithmic minimum 2*M*C + 4*M*2I + 2*9C*2I = 212 MB
+                    "traffic": 163.44e6 if batched else None, "traffic_unit": "bytes/launch (ncu)",
                     "peak_source": pk["source"] + " (sustained bf16 cuBLAS)", "avg_launch_ms": avg_ms, "launches_timed": len(durs),
                     "share_of_step": sum(durs) / prof_ms,
                     "timed": "eager replays after the graph-timed region" if graphed else "inside the timed region"}

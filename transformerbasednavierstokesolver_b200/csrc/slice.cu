@@ -393,11 +393,22 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 using namespace tbns;
 
 extern "C" int tbns_slice_groups(int B, int N, int H) {
+  // CTAs per (batch, head): each CTA walks ceil(nchunk / groups) 128-token chunks.  Pick the count that minimises the number
+  // of chunk-times on the critical path, rounds(B*H*groups over the resident-CTA slots) x chunks per CTA, for the backward
+  // kernel (2 CTAs / SM, weighted double) and the forward kernel (4 CTAs / SM); ties go to fewer partials.
   const int nchunk = cdiv(N, TOK);
-  const int bh = B * H > 0 ? B * H : 1;
-  int target = cdiv(4 * 148, bh);
-  if (target < 1) target = 1;
-  return nchunk < target ? nchunk : target;
+  const long long bh = (long long)(B > 0 ? B : 1) * (H > 0 ? H : 1);
+  long long best_cost = -1;
+  int best = 1;
+  for (int g = 1; g <= nchunk; ++g) {
+    const long long per = cdiv(nchunk, g);
+    const long long cost = 2 * ((bh * g + 295) / 296) * per + ((bh * g + 591) / 592) * per;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = g;
+    }
+  }
+  return best;
 }
 
 extern "C" int tbns_pa_slice_fwd(const float* XF, const float* Ws, const float* bs, const float* temperature, float* w, void* w16,
