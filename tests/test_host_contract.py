@@ -1,0 +1,67 @@
+"""CPU tests of the host-side mirror of the reference interface: registry keys, constructor / attribute contract,
+state_dict key compatibility with the reference's trained checkpoint layout, and the loud failures (no CPU path,
+unsupported options) that replace silent divergence."""
+import types
+
+import pytest
+import torch
+
+from transformerbasednavierstokesolver_b200 import model_dict, set_default_precision, get_default_precision
+from transformerbasednavierstokesolver_b200.model import Physics_Attention as PA
+from transformerbasednavierstokesolver_b200.model import Transolver_Irregular_Mesh, Transolver_Structured_Mesh_2D
+from transformerbasednavierstokesolver_b200.model.SOL_Transolver_Structured_Mesh_2D import SOL_Transolver_Structured_Mesh_2D
+
+
+def test_registry_keys_match_reference():
+    for name, mod in (("Transolver_Irregular_Mesh", Transolver_Irregular_Mesh), ("Transolver_Structured_Mesh_2D", Transolver_Structured_Mesh_2D)):
+        assert model_dict.get_model(types.SimpleNamespace(model=name)) is mod
+        assert hasattr(mod, "Model")
+    for name in ("Transolver_Structured_Mesh_3D", "Transolver_Structured_Mesh2D_Encoder"):   # registered by the reference, out of scope here
+        with pytest.raises(NotImplementedError):
+            model_dict.get_model(types.SimpleNamespace(model=name))
+    with pytest.raises(KeyError):
+        model_dict.get_model(types.SimpleNamespace(model="Transolver_2D"))   # exp_ns.py's default is not a key in the reference either
+
+
+def test_attention_module_contract(golden):
+    fx = golden("pa_structured_small.pt")
+    m = PA.Physics_Attention_Structured_Mesh_2D(**fx["kwargs"])
+    assert set(m.state_dict().keys()) == set(fx["state"].keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(fx["state"][k].shape), k
+    assert (m.heads, m.dim_head, m.H, m.W) == (4, 8, 6, 5)
+    assert float(m.temperature.flatten()[0]) == 0.5 and tuple(m.temperature.shape) == (1, 4, 1, 1)
+    fi = golden("pa_irregular_small.pt")
+    mi = PA.Physics_Attention_Irregular_Mesh(**fi["kwargs"])
+    assert set(mi.state_dict().keys()) == set(fi["state"].keys())
+    assert isinstance(mi.in_project_x, torch.nn.Linear) and isinstance(m.in_project_x, torch.nn.Conv2d)
+
+
+def test_trained_checkpoint_layout_loads_strict():
+    """shape of checkpoints/ep400_sim100.pt: 8 layers, n_hidden 64, 8 heads, slice_num 32, fun_dim 10, unified_pos 1, ref 8"""
+    m = Transolver_Structured_Mesh_2D.Model(space_dim=2, n_layers=8, n_hidden=64, n_head=8, fun_dim=10, out_dim=1, slice_num=32, ref=8,
+                                            unified_pos=1, H=64, W=64, mlp_ratio=1)
+    sd = m.state_dict()
+    assert sum(v.numel() for v in sd.values()) == 714753
+    assert "blocks.7.mlp2.weight" in sd and "blocks.0.Attn.to_out.0.bias" in sd and "preprocess.linear_pre.0.weight" in sd
+    assert tuple(sd["preprocess.linear_pre.0.weight"].shape) == (128, 74) and "placeholder" in sd
+    assert not hasattr(m, "pos") or "pos" not in sd          # the position table is a plain attribute, not a buffer
+
+
+def test_loud_failures():
+    with pytest.raises(NotImplementedError):
+        Transolver_Structured_Mesh_2D.Model(Time_Input=True)
+    with pytest.raises(NotImplementedError):
+        PA.Physics_Attention_Structured_Mesh_2D(16, heads=2, dim_head=8, kernel=5)
+    m = PA.Physics_Attention_Irregular_Mesh(16, heads=2, dim_head=8, dropout=0.1, slice_num=4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.randn(1, 7, 16))
+    with pytest.raises(ValueError):
+        set_default_precision("fp16")
+    assert get_default_precision() in ("bf16", "fp32")
+
+
+def test_sol_wrapper_attributes():
+    s = SOL_Transolver_Structured_Mesh_2D(space_dim=2, n_layers=1, n_hidden=16, n_head=2, fun_dim=3, slice_num=4, H=4, W=4, step=1, look_ahead=3)
+    assert s.n == 3 and s.step == 1 and hasattr(s, "transolver_model")
+    assert all(k.startswith("transolver_model.") for k in s.state_dict().keys())
