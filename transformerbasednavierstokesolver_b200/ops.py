@@ -133,6 +133,25 @@ def cast_bf16(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_W16_CACHE = {}
+
+
+def weight_bf16(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """bf16 (optionally transposed) copy of a weight matrix as a K-major tensor-core operand, cached until the fp32 master
+    changes (optimizer step / load_state_dict bump `_version`)."""
+    key = (W.data_ptr(), transpose)
+    hit = _W16_CACHE.get(key)
+    if hit is not None and hit[0] == W._version and hit[1].shape == ((W.shape[1], W.shape[0]) if transpose else W.shape):
+        return hit[1]
+    with torch.no_grad():
+        src = W.detach().t().contiguous() if transpose else W.detach().contiguous()
+        w16 = cast_bf16(src)
+    if len(_W16_CACHE) > 4096:
+        _W16_CACHE.clear()
+    _W16_CACHE[key] = (W._version, w16)
+    return w16
+
+
 def tc_supported(Cin: int, N: int, taps: int) -> bool:
     return bool(_lib.load().tbns_gemm_tc_supported(Cin, N, taps))
 
@@ -557,9 +576,9 @@ class LnMlpFn(torch.autograd.Function):
             # tensor-core MLP: bf16 operands; LN output and hidden activation only ever exist in bf16 (+ fp32 pre-activation
             # for GELU')
             hid16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
-            gemm_tc(x2_16, cast_bf16(W1), None, b1, 1, 1, M, C_, R, act=1, aux_out=pre, C16=hid16, tag="mlp_fc1")
+            gemm_tc(x2_16, weight_bf16(W1), None, b1, 1, 1, M, C_, R, act=1, aux_out=pre, C16=hid16, tag="mlp_fc1")
             out = torch.empty(*fx.shape[:-1], Cout, device=fx.device, dtype=torch.float32)
-            gemm_tc(hid16, cast_bf16(W2), out, b2, 1, 1, M, R, Cout, residual=fx, tag="mlp_fc2")
+            gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, residual=fx, tag="mlp_fc2")
             ctx.save_for_backward(fx, gamma, W1, W2, x2_16, mean, rstd, pre, hid16)
             ctx.precision = precision
             return out
@@ -593,12 +612,12 @@ class LnMlpFn(torch.autograd.Function):
             gemm_tc_wgrad(dout16, hid, 1, 1, M, Cout, R, C=dW2, tag="mlp_dW2")
             dpre = torch.empty(M, R, **f32)
             dpre16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
-            gemm_tc(dout16, cast_bf16(W2.t().contiguous()), dpre, None, 1, 1, M, Cout, R, act=2, aux_in=pre, C16=dpre16, tag="mlp_dpre")
+            gemm_tc(dout16, weight_bf16(W2, transpose=True), dpre, None, 1, 1, M, Cout, R, act=2, aux_in=pre, C16=dpre16, tag="mlp_dpre")
             db1 = colsum(dpre, M, R)
             dW1 = torch.empty(R, C_, **f32)
             gemm_tc_wgrad(dpre16, x2, 1, 1, M, R, C_, C=dW1, tag="mlp_dW1")
             dx2 = torch.empty(M, C_, **f32)
-            gemm_tc(dpre16, cast_bf16(W1.t().contiguous()), dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
+            gemm_tc(dpre16, weight_bf16(W1, transpose=True), dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
             dfx, dfx16, dg, db, dfsum = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout, want16=True, want_sum=True)
             dfx = dfx.view_as(fx)
             _stash_grad16(dfx, dfx16, dfsum)   # the attention stage's backward consumes dfx next: bf16 copy + to_out bias gradient
