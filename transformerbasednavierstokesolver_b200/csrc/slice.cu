@@ -18,6 +18,7 @@ constexpr int TOKEN_THREADS = 1024;
 
 // grid (H, B), block 256.  All [rows][D] shared arrays use the padded stride DS = D+1 (bank-conflict free for both
 // row-wise and column-wise thread mappings).
+template <int DT, int GT>
 __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ Wq,
                                                              const float* __restrict__ Wk, const float* __restrict__ Wv,
                                                              const float* __restrict__ Wo, float* __restrict__ s_out,
@@ -26,7 +27,8 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
                                                              float* __restrict__ v_out, float* __restrict__ A_out,
                                                              float* __restrict__ O_out, float* __restrict__ P,
                                                              __nv_bfloat16* __restrict__ P16, __nv_bfloat16* __restrict__ PT16, int H,
-                                                             int D, int G, int Cout, int stage) {
+                                                             int D_rt, int G_rt, int Cout, int stage) {
+  const int D = DT > 0 ? DT : D_rt, G = GT > 0 ? GT : G_rt;   // compile-time for the common head shapes: loops unroll, index math folds
   extern __shared__ float sm[];
   const int DS = D + 1, GD = G * D, GS = G * DS, AS = G + 1;
   float* tok = sm;            // [G][DS]
@@ -150,8 +152,11 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
   }
   for (int o = tid; o < G * Cout; o += nt) {
     const int g = o / Cout, c = o - g * Cout;
+    const float* ov = O + g * DS;
+    const float* wv = Wos + c * DS;
     float acc = 0.f;
-    for (int dd = 0; dd < D; ++dd) acc = fmaf(O[g * DS + dd], Wos[c * DS + dd], acc);
+#pragma unroll 8
+    for (int dd = 0; dd < D; ++dd) acc = fmaf(ov[dd], wv[dd], acc);
     Pout[(long long)g * Cout + c] = acc;
     if (P16) P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(acc);
     Ps[g * (Cout + 1) + c] = acc;
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
 }
 
 // grid (H, B), block 256
+template <int DT, int GT>
 __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_bwd_kernel(const float* __restrict__ dP, const float* __restrict__ Wq,
                                                              const float* __restrict__ Wk, const float* __restrict__ Wv,
                                                              const float* __restrict__ Wo, const float* __restrict__ s_in,
@@ -173,8 +179,9 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_bwd_kernel(const flo
                                                              const float* __restrict__ k_in, const float* __restrict__ v_in,
                                                              const float* __restrict__ A_in, const float* __restrict__ O_in,
                                                              float* __restrict__ dTt, float* __restrict__ ds,
-                                                             float* __restrict__ dWqkv_part, float* __restrict__ dWo_part, int H, int D,
-                                                             int G, int Cout, int stage) {
+                                                             float* __restrict__ dWqkv_part, float* __restrict__ dWo_part, int H,
+                                                             int D_rt, int G_rt, int Cout, int stage) {
+  const int D = DT > 0 ? DT : D_rt, G = GT > 0 ? GT : G_rt;
   extern __shared__ float sm[];
   const int DS = D + 1, GD = G * D, GS = G * DS, AS = G + 1;
   float* tok = sm;
@@ -223,18 +230,44 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_bwd_kernel(const flo
     // dO[g,d] = sum_c dP[g,c] Wo[c,h*D+d]
     for (int o = tid; o < GD; o += nt) {
       const int g = o / D, dd = o - g * D;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int c = 0; c < Cout; ++c) acc = fmaf(dPs[g * Cout + c], __ldg(Wo + (long long)c * I + h * D + dd), acc);
-      dO[g * DS + dd] = acc;
+      const float* a = dPs + g * Cout;
+      const float* w = Wo + h * D + dd;          // stride I per output channel c
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int c = 0;
+      for (; c + 3 < Cout; c += 4, w += 4 * (long long)I) {
+        const float4 av = *reinterpret_cast<const float4*>(a + c);
+        a0 = fmaf(av.x, __ldg(w), a0);
+        a1 = fmaf(av.y, __ldg(w + I), a1);
+        a2 = fmaf(av.z, __ldg(w + 2 * (long long)I), a2);
+        a3 = fmaf(av.w, __ldg(w + 3 * (long long)I), a3);
+      }
+      for (; c < Cout; ++c, w += I) a0 = fmaf(a[c], __ldg(w), a0);
+      dO[g * DS + dd] = (a0 + a1) + (a2 + a3);
     }
     // dWo_part[b, c, h*D+d] = sum_g dP[g,c] O[g,d]
-    for (int o = tid; o < Cout * D; o += nt) {
-      const int c = o / D, dd = o - c * D;
-      float acc = 0.f;
+    if ((D & 3) == 0) {
+      // 4 consecutive dim_head columns per thread: one LDS + one LDS.128 per 4 FMAs, 16-byte stores
+      const int D4 = D >> 2;
+      for (int o = tid; o < Cout * D4; o += nt) {
+        const int c = o / D4, d4 = (o - c * D4) * 4;
+        const float* a = dPs + c;
+        const float* ov = Os + d4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-      for (int g = 0; g < G; ++g) acc = fmaf(dPs[g * Cout + c], Os[g * D + dd], acc);
-      dWo_part[((long long)b * Cout + c) * I + h * D + dd] = acc;
+        for (int g = 0; g < G; ++g, a += Cout, ov += D) {
+          const float av = *a;
+          const float4 o4 = *reinterpret_cast<const float4*>(ov);
+          acc.x = fmaf(av, o4.x, acc.x); acc.y = fmaf(av, o4.y, acc.y); acc.z = fmaf(av, o4.z, acc.z); acc.w = fmaf(av, o4.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(dWo_part + ((long long)b * Cout + c) * I + h * D + d4) = acc;
+      }
+    } else {
+      for (int o = tid; o < Cout * D; o += nt) {
+        const int c = o / D, dd = o - c * D;
+        float acc = 0.f;
+        for (int g = 0; g < G; ++g) acc = fmaf(dPs[g * Cout + c], Os[g * D + dd], acc);
+        dWo_part[((long long)b * Cout + c) * I + h * D + dd] = acc;
+      }
     }
   } else {
     // dO[g,d] = sum_c dP[g,c] Wo[c,h*D+d]
@@ -439,11 +472,22 @@ extern "C" int tbns_pa_token_attn_fwd(const float* part, int nchunk, const float
     stage = 1;
     smem += token_fwd_stage_smem(D, G, Cout);
   }
-  TBNS_SMEM_OPT_IN((token_attn_fwd_kernel), (int)SMEM_LIMIT);
   dim3 grid(H, B);
-  token_attn_fwd_kernel<<<grid, TOKEN_THREADS, smem, (cudaStream_t)stream>>>(part, nchunk, Wq, Wk, Wv, Wo, s, Tt, tok, q, k, v, A, O, P,
-                                                                   reinterpret_cast<__nv_bfloat16*>(P16),
-                                                                   reinterpret_cast<__nv_bfloat16*>(PT16), H, D, G, Cout, stage);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(P16);
+  __nv_bfloat16* pt16 = reinterpret_cast<__nv_bfloat16*>(PT16);
+#define TBNS_TOKEN_FWD(DT_, GT_)                                                                                                     \
+  do {                                                                                                                               \
+    TBNS_SMEM_OPT_IN((token_attn_fwd_kernel<DT_, GT_>), (int)SMEM_LIMIT);                                                            \
+    token_attn_fwd_kernel<DT_, GT_><<<grid, TOKEN_THREADS, smem, st>>>(part, nchunk, Wq, Wk, Wv, Wo, s, Tt, tok, q, k, v, A, O, P, p16, \
+                                                                       pt16, H, D, G, Cout, stage);                                  \
+  } while (0)
+  if (D == 32 && G == 32) TBNS_TOKEN_FWD(32, 32);
+  else if (D == 32 && G == 64) TBNS_TOKEN_FWD(32, 64);
+  else if (D == 16 && G == 64) TBNS_TOKEN_FWD(16, 64);
+  else if (D == 8 && G == 32) TBNS_TOKEN_FWD(8, 32);
+  else TBNS_TOKEN_FWD(0, 0);
+#undef TBNS_TOKEN_FWD
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
@@ -463,10 +507,20 @@ extern "C" int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const fl
     stage = 1;
     smem += extra;
   }
-  TBNS_SMEM_OPT_IN((token_attn_bwd_kernel), (int)SMEM_LIMIT);
   dim3 grid(H, B);
-  token_attn_bwd_kernel<<<grid, TOKEN_THREADS, smem, (cudaStream_t)stream>>>(dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part,
-                                                                   dWo_part, H, D, G, Cout, stage);
+  cudaStream_t st = (cudaStream_t)stream;
+#define TBNS_TOKEN_BWD(DT_, GT_)                                                                                                       \
+  do {                                                                                                                                 \
+    TBNS_SMEM_OPT_IN((token_attn_bwd_kernel<DT_, GT_>), (int)SMEM_LIMIT);                                                              \
+    token_attn_bwd_kernel<DT_, GT_><<<grid, TOKEN_THREADS, smem, st>>>(dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part,  \
+                                                                       dWo_part, H, D, G, Cout, stage);                                \
+  } while (0)
+  if (D == 32 && G == 32) TBNS_TOKEN_BWD(32, 32);
+  else if (D == 32 && G == 64) TBNS_TOKEN_BWD(32, 64);
+  else if (D == 16 && G == 64) TBNS_TOKEN_BWD(16, 64);
+  else if (D == 8 && G == 32) TBNS_TOKEN_BWD(8, 32);
+  else TBNS_TOKEN_BWD(0, 0);
+#undef TBNS_TOKEN_BWD
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
