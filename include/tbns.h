@@ -88,6 +88,7 @@ typedef struct tbns_tc_desc {
   float* C; long long ldc;      /* fp32 output or NULL                                                  */
   void* C16; long long ldc16;   /* bf16 output or NULL (operand of the next tensor-core contraction)    */
   int round_tf32;               /* 1: round the fp32 output to TF32 (RNA): it feeds kind::tf32 MMAs downstream */
+  int aux_bf16;                 /* 1: aux_out / aux_in point to bf16 buffers (halves the GELU side-stream traffic)   */
 } tbns_tc_desc;
 int tbns_gemm_tc_supported(int Cin, int N, int taps);
 int tbns_gemm_tc(const tbns_tc_desc* d, void* stream);
@@ -156,7 +157,8 @@ int tbns_pa_slice_fwd_tc(const float* XF, const float* Ws, const float* bs, cons
                          int B, int N, int H, int D, int G, int clamp, void* stream);
 /* backward twin: dXF16 (bf16) only; the projection-bias gradients follow from dbs and s on the host side
  * (db_x = dbs.Ws, db_fx = s.dTt), so no dbcat_part is produced. */
-int tbns_pa_slice_bwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, const float* dw,
+/* dw16: the deslice gradient [B,N,H*G] in bf16 (written by the dw GEMM's bf16 output) */
+int tbns_pa_slice_bwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, const void* dw16,
                          const float* dTt, const float* ds, void* dXF16, float* dWs_part, float* dtau_part, int B, int N,
                          int H, int D, int G, int clamp, void* stream);
 
@@ -190,6 +192,7 @@ int tbns_pa_dtau_finish(const float* dtau_part, const float* temperature, float*
 int tbns_reduce_rows(const float* in, float* out, int rows, long long cols, void* stream);
 /* column sums of a [rows, cols] matrix (bias gradients); ws: tbns_colsum_ws_floats(cols) floats */
 size_t tbns_colsum_ws_floats(long long cols);
+int tbns_colsum_bf16(const void* in16, long long ld, float* out, float* ws, int rows, int cols, void* stream);
 int tbns_colsum(const float* in, long long ld, float* out, float* ws, int rows, int cols, void* stream);
 
 #ifdef __cplusplus

@@ -59,6 +59,7 @@ w16 = torch.empty(B, N, H * G, device=dev, dtype=torch.bfloat16)
 part = torch.empty(B * H * groups * G * (D + 1), device=dev)
 dw = torch.randn(B, N, H * G, generator=g).to(dev); dTt = torch.randn(B, H, G, D, generator=g).to(dev); ds = torch.randn(B, H, G, generator=g).to(dev)
 dXF16o = torch.empty(M, I2, device=dev, dtype=torch.bfloat16)
+dw16 = dw.bfloat16()
 dWs_p = torch.empty(B * H * groups, G * (D + 1), device=dev); dtau_p = torch.empty(B * H * groups, device=dev); dbc = torch.empty(B * groups, H * 2 * D, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 P = lambda t: t.data_ptr()
@@ -66,7 +67,7 @@ cases2 = {
     "slice_fwd SIMT": lambda: lib.tbns_pa_slice_fwd(P(XFs), P(Ws), P(bs), P(tau), None, P(w16), P(part), B, N, H, D, G, 1, st),
     "slice_fwd tcgen05": lambda: lib.tbns_pa_slice_fwd_tc(P(XFs), P(Ws), P(bs), P(tau), P(w16), P(part), B, N, H, D, G, 1, st),
     "slice_bwd SIMT": lambda: lib.tbns_pa_slice_bwd(P(XFs), P(Ws), P(bs), P(tau), P(dw), P(dTt), P(ds), None, P(dXF16o), P(dWs_p), P(dtau_p), P(dbc), B, N, H, D, G, 1, st),
-    "slice_bwd tcgen05": lambda: lib.tbns_pa_slice_bwd_tc(P(XFs), P(Ws), P(bs), P(tau), P(dw), P(dTt), P(ds), P(dXF16o), P(dWs_p), P(dtau_p), B, N, H, D, G, 1, st),
+    "slice_bwd tcgen05": lambda: lib.tbns_pa_slice_bwd_tc(P(XFs), P(Ws), P(bs), P(tau), P(dw16), P(dTt), P(ds), P(dXF16o), P(dWs_p), P(dtau_p), B, N, H, D, G, 1, st),
 }
 for name, fn in cases2.items():
     for _ in range(3):

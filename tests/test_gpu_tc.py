@@ -209,7 +209,12 @@ def test_tc_slice_bwd_matches_simt(B, N, H, G):
     dXF16 = torch.full((B * N, 2 * I), float("nan"), device=dev, dtype=torch.bfloat16)
     dWs_p = torch.full((B * H * groups, G * (D + 1)), float("nan"), device=dev)
     dtau_p = torch.full((B * H * groups,), float("nan"), device=dev)
-    _lib.check(lib.tbns_pa_slice_bwd_tc(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), dw.data_ptr(), dTt.data_ptr(),
+    dw = dw.bfloat16().float()           # the tensor-core kernel takes the deslice gradient in bf16
+    _lib.check(lib.tbns_pa_slice_bwd(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), dw.data_ptr(), dTt.data_ptr(),
+                                     ds.data_ptr(), dXF_ref.data_ptr(), None, dWs_ref.data_ptr(), dtau_ref.data_ptr(), dbc_ref.data_ptr(),
+                                     B, N, H, D, G, 1, st), "slice_bwd")
+    dw16 = dw.bfloat16()
+    _lib.check(lib.tbns_pa_slice_bwd_tc(XF.data_ptr(), Ws.data_ptr(), bs.data_ptr(), tau.data_ptr(), dw16.data_ptr(), dTt.data_ptr(),
                                         ds.data_ptr(), dXF16.data_ptr(), dWs_p.data_ptr(), dtau_p.data_ptr(), B, N, H, D, G, 1, st),
                "slice_bwd_tc")
     torch.cuda.synchronize()

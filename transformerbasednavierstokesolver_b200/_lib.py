@@ -49,7 +49,7 @@ class TcDesc(C.Structure):
         ("residual", _fp), ("ldr", _ll),
         ("C", _fp), ("ldc", _ll),
         ("C16", _fp), ("ldc16", _ll),
-        ("round_tf32", _i),
+        ("round_tf32", _i), ("aux_bf16", _i),
     ]
 
 
@@ -95,6 +95,7 @@ _SIGS = {
     "tbns_reduce_rows": (_i, [_fp, _fp, _i, _ll, _fp]),
     "tbns_colsum_ws_floats": (C.c_size_t, [_ll]),
     "tbns_colsum": (_i, [_fp, _ll, _fp, _fp, _i, _i, _fp]),
+    "tbns_colsum_bf16": (_i, [_fp, _ll, _fp, _fp, _i, _i, _fp]),
 }
 
 EXPORTS = tuple(_SIGS.keys())

@@ -34,6 +34,7 @@ struct TcParams {
   float* aux_out;
   const float* aux_in;
   long long ldaux;
+  int aux_bf16;             // aux_out / aux_in hold bf16 instead of fp32 (persistent kernel only)
   int Bimg, Hg, Wg, Cin, taps, flip;
   int BW, BH;               // the 128-token M tile is a BH x BW patch of the grid (BW*BH == 128)
   int tiles_w, tiles_h;
@@ -359,11 +360,19 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& p, float (&v)[2][16
   const float* src = p.act == 2 ? p.aux_in : p.residual;
   const long long lds = p.act == 2 ? p.ldaux : p.ldr;
   if (src) {
+    const bool h16 = p.act == 2 && p.aux_bf16;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        ld[k][j] = grow[k] >= 0 ? *reinterpret_cast<const float2*>(src + grow[k] * lds + cb + 8 * j) : make_float2(0.f, 0.f);
+      for (int j = 0; j < 4; ++j) {
+        if (grow[k] < 0) {
+          ld[k][j] = make_float2(0.f, 0.f);
+        } else if (h16) {
+          ld[k][j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(src) + grow[k] * lds + cb + 8 * j));
+        } else {
+          ld[k][j] = *reinterpret_cast<const float2*>(src + grow[k] * lds + cb + 8 * j);
+        }
+      }
   }
   float2 bias[4];
 #pragma unroll
@@ -378,7 +387,10 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& p, float (&v)[2][16
       const int c = cb + 8 * j;
       float x0 = v[k >> 1][4 * j + 2 * (k & 1)] + bias[j].x, x1 = v[k >> 1][4 * j + 2 * (k & 1) + 1] + bias[j].y;
       if (p.act == 1) {
-        if (p.aux_out) *reinterpret_cast<float2*>(p.aux_out + gr * p.ldaux + c) = make_float2(x0, x1);
+        if (p.aux_out) {
+          if (p.aux_bf16) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + gr * p.ldaux + c) = __floats2bfloat162_rn(x0, x1);
+          else *reinterpret_cast<float2*>(p.aux_out + gr * p.ldaux + c) = make_float2(x0, x1);
+        }
         x0 = gelu_fast(x0);
         x1 = gelu_fast(x1);
       } else if (p.act == 2) {
@@ -797,7 +809,7 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
   TcParams p;
   p.C = d.C; p.ldc = d.ldc; p.C16 = reinterpret_cast<__nv_bfloat16*>(d.C16); p.ldc16 = d.ldc16;
   p.bias = d.bias; p.residual = d.residual; p.ldr = d.ldr;
-  p.act = d.act; p.aux_out = d.aux_out; p.aux_in = d.aux_in; p.ldaux = d.ldaux;
+  p.act = d.act; p.aux_out = d.aux_out; p.aux_in = d.aux_in; p.ldaux = d.ldaux; p.aux_bf16 = d.aux_bf16;
   p.Bimg = d.Bimg; p.Hg = d.Hg; p.Wg = d.Wg; p.Cin = d.Cin; p.taps = d.taps; p.flip = d.flip;
   p.BW = pick_bw(d.Hg, d.Wg, TC_BM); p.BH = TC_BM / p.BW;
   p.tiles_w = cdiv(d.Wg, p.BW); p.tiles_h = cdiv(d.Hg, p.BH);
@@ -845,6 +857,7 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
     if (BNp == 128) return launch_tcp<128, 6>(tmA, tmB, p, (int)m_tiles, st);
     return launch_tcp<64, 8>(tmA, tmB, p, (int)m_tiles, st);
   }
+  TBNS_REQUIRE(!d.aux_bf16, "tbns_gemm_tc: bf16 aux buffers need the persistent kernel");
   if (BN == 256) return launch_tc<256, 4>(tmA, tmB, p, (int)m_tiles, st);
   if (BN == 128) return short_k ? launch_tc<128, 3>(tmA, tmB, p, (int)m_tiles, st) : launch_tc<128, 6>(tmA, tmB, p, (int)m_tiles, st);
   return launch_tc<64, 8>(tmA, tmB, p, (int)m_tiles, st);

@@ -373,6 +373,43 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
   return TBNS_OK;
 }
 
+// bf16 input variant: 16 column-lanes x 8 columns (one uint4) per row-lane
+__global__ void __launch_bounds__(256) colsum16_partial_kernel(const __nv_bfloat16* __restrict__ in, long long ld, float* __restrict__ ws,
+                                                              int rows, int cols, int rows_per_chunk) {
+  __shared__ float red[16][16][8];
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c = blockIdx.x * 128 + cl * 8;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(rows, r0 + rows_per_chunk);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c + 7 < cols) {
+    for (int r = r0 + rl; r < r1; r += 16) {
+      const uint4 u = *reinterpret_cast<const uint4*>(in + (long long)r * ld + c);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cl][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && c + 7 < cols) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s += red[i][cl][j];
+      ws[(long long)blockIdx.y * cols + c + j] = s;
+    }
+  }
+}
+
 extern "C" size_t tbns_colsum_ws_floats(long long cols) { return (size_t)COLSUM_ROWS * (size_t)cols; }
 
 extern "C" int tbns_colsum(const float* in, long long ld, float* out, float* ws, int rows, int cols, void* stream) {
@@ -385,6 +422,20 @@ extern "C" int tbns_colsum(const float* in, long long ld, float* out, float* ws,
   chunks = cdiv(rows, rows_per_chunk);
   dim3 grid(cdiv(cols, 128), chunks);
   colsum_partial_kernel<<<grid, 256, 0, st>>>(in, ld, ws, rows, cols, rows_per_chunk);
+  TBNS_LAUNCH_CHECK();
+  return tbns_reduce_rows(ws, out, chunks, cols, stream);
+}
+
+extern "C" int tbns_colsum_bf16(const void* in16, long long ld, float* out, float* ws, int rows, int cols, void* stream) {
+  TBNS_REQUIRE(in16 && out && ws && rows > 0 && cols > 0, "tbns_colsum_bf16: bad args");
+  TBNS_REQUIRE((reinterpret_cast<uintptr_t>(in16) & 15) == 0 && cols % 8 == 0 && ld % 8 == 0, "tbns_colsum_bf16: needs 16-byte aligned rows, cols %% 8 == 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  int chunks = cdiv(rows, 128);
+  if (chunks > COLSUM_ROWS) chunks = COLSUM_ROWS;
+  const int rows_per_chunk = cdiv(rows, chunks);
+  chunks = cdiv(rows, rows_per_chunk);
+  dim3 grid(cdiv(cols, 128), chunks);
+  colsum16_partial_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in16), ld, ws, rows, cols, rows_per_chunk);
   TBNS_LAUNCH_CHECK();
   return tbns_reduce_rows(ws, out, chunks, cols, stream);
 }

@@ -249,7 +249,7 @@ struct StBwdSmem {
 template <int G>
 __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmXF, const float* __restrict__ Ws,
                                                               const float* __restrict__ bs, const float* __restrict__ temperature,
-                                                              const float* __restrict__ dw, const float* __restrict__ dTt,
+                                                              const __nv_bfloat16* __restrict__ dw, const float* __restrict__ dTt,
                                                               const float* __restrict__ ds, __nv_bfloat16* __restrict__ dXF16,
                                                               float* __restrict__ dWs_part, float* __restrict__ dtau_part, int N, int H,
                                                               int nchunk, int clamp) {
@@ -329,11 +329,17 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
     // this token's deslice gradient row (issued early: overlaps the TMA / MMA latency)
     float dwv[G];
     if (valid) {
-      const float* dr = dw + row * HG + h * G;
+      const __nv_bfloat16* dr = dw + row * HG + h * G;
 #pragma unroll
-      for (int c = 0; c < G / 4; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(dr + 4 * c);
-        dwv[4 * c] = v.x; dwv[4 * c + 1] = v.y; dwv[4 * c + 2] = v.z; dwv[4 * c + 3] = v.w;
+      for (int c = 0; c < G / 8; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(dr + 8 * c);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          dwv[8 * c + 2 * j] = f.x;
+          dwv[8 * c + 2 * j + 1] = f.y;
+        }
       }
     } else {
 #pragma unroll
@@ -488,7 +494,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
 }
 
 template <int G>
-static int launch_slice_bwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, const float* dw,
+static int launch_slice_bwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, const __nv_bfloat16* dw,
                                const float* dTt, const float* ds, __nv_bfloat16* dXF16, float* dWs_part, float* dtau_part, int B, int N,
                                int H, int groups, int clamp, cudaStream_t st) {
   CUtensorMap tm;
@@ -524,10 +530,11 @@ extern "C" int tbns_pa_slice_fwd_tc(const float* XF, const float* Ws, const floa
   return launch_slice_fwd_tc<64>(XF, Ws, bs, temperature, reinterpret_cast<__nv_bfloat16*>(w16), part, B, N, H, groups, clamp, st);
 }
 
-extern "C" int tbns_pa_slice_bwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, const float* dw,
+extern "C" int tbns_pa_slice_bwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, const void* dw16,
                                     const float* dTt, const float* ds, void* dXF16, float* dWs_part, float* dtau_part, int B, int N,
                                     int H, int D, int G, int clamp, void* stream) {
-  TBNS_REQUIRE(XF && Ws && bs && temperature && dw && dTt && ds && dXF16 && dWs_part && dtau_part, "tbns_pa_slice_bwd_tc: null pointer");
+  TBNS_REQUIRE(XF && Ws && bs && temperature && dw16 && dTt && ds && dXF16 && dWs_part && dtau_part, "tbns_pa_slice_bwd_tc: null pointer");
+  const __nv_bfloat16* dw = reinterpret_cast<const __nv_bfloat16*>(dw16);
   TBNS_REQUIRE(tbns_pa_slice_tc_supported(D, G), "tbns_pa_slice_bwd_tc: needs dim_head 32 and slice_num 32 or 64 (got %d, %d)", D, G);
   TBNS_REQUIRE(B > 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "tbns_pa_slice_bwd_tc: bad dims");
   TBNS_REQUIRE((reinterpret_cast<uintptr_t>(XF) & 15) == 0 && (reinterpret_cast<uintptr_t>(dXF16) & 15) == 0 &&

@@ -124,6 +124,16 @@ def colsum(inp: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
     return out
 
 
+def colsum_bf16(inp16: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(cols, device=inp16.device, dtype=torch.float32)
+    ws = torch.empty(lib.tbns_colsum_ws_floats(cols), device=inp16.device, dtype=torch.float32)
+    with _Timed("colsum"):
+        check(lib.tbns_colsum_bf16(_p(inp16), cols, _p(out), _p(ws), rows, cols, _stream()), "tbns_colsum_bf16")
+    _count(2)
+    return out
+
+
 def cast_bf16(t: torch.Tensor) -> torch.Tensor:
     """fp32 -> bf16 copy (round to nearest even) through libtbns"""
     out = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
@@ -157,7 +167,7 @@ def tc_supported(Cin: int, N: int, taps: int) -> bool:
 
 
 def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps=1, flip=0, tag=None, *, C16=None, w_batched=0, act=0, aux_out=None,
-            aux_in=None, residual=None, round_tf32=0):
+            aux_in=None, residual=None, round_tf32=0, aux_bf16=0):
     """tcgen05 implicit GEMM, K-major operands (include/tbns.h: tbns_gemm_tc).  C fp32 and/or C16 bf16 outputs [.., N]."""
     d = _lib.TcDesc()
     d.A16, d.Bimg, d.Hg, d.Wg, d.Cin, d.taps, d.flip = _p(A16), Bimg, Hg, Wg, Cin, taps, flip
@@ -168,6 +178,7 @@ def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps=1, flip=0, tag=None, *
     d.C, d.ldc = _p(C), N
     d.C16, d.ldc16 = _p(C16), N
     d.round_tf32 = round_tf32
+    d.aux_bf16 = aux_bf16
     with _Timed(tag):
         check(_lib.load().tbns_gemm_tc(ct.byref(d), _stream()), "tbns_gemm_tc")
     _count(1)
@@ -417,12 +428,14 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
     if dbo is None:
         dbo = colsum(dout, B * N, Cout)
     dP = torch.empty(B, HG, Cout, **f32)
-    dw = torch.empty(B, N, HG, **f32)
+    slice_tc = tc and bool(lib.tbns_pa_slice_tc_supported(D, G))
+    dw = None if slice_tc else torch.empty(B, N, HG, **f32)
+    dw16 = torch.empty(B, N, HG, device=dev, dtype=torch.bfloat16) if slice_tc else None   # the tf32 slice kernel reads bf16
     if tc:
         if dout16 is None:
             dout16 = cast_bf16(dout)
         gemm_tc_wgrad(w, dout16, B, 1, N, HG, Cout, batched=1, C=dP, tag="deslice_dP")
-        gemm_tc(dout16, P, dw, None, B, 1, N, Cout, HG, w_batched=1, tag="deslice_dw")
+        gemm_tc(dout16, P, dw, None, B, 1, N, Cout, HG, w_batched=1, C16=dw16, tag="deslice_dw")
     else:
         gemm(M=HG, N=Cout, K=N, A=w, lda=HG, a_kind=1, B=dout, ldb=Cout, b_kind=1, C=dP, ldc=Cout, batch=B, sA=N * HG, sB=N * Cout,
              sC=HG * Cout, precision=precision, split_k=_split_k(HG, Cout, N, B), tag="deslice_dP")
@@ -444,10 +457,9 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
     dXF16 = torch.empty(B * N, I2, device=dev, dtype=torch.bfloat16) if tc else None
     dWs_part = torch.empty(B * H * groups, G * (D + 1), **f32)
     dtau_part = torch.empty(B * H * groups, **f32)
-    slice_tc = tc and bool(lib.tbns_pa_slice_tc_supported(D, G))
     if slice_tc:
         with _Timed("slice_bwd"):
-            check(lib.tbns_pa_slice_bwd_tc(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw), _p(dTt), _p(ds), _p(dXF16), _p(dWs_part),
+            check(lib.tbns_pa_slice_bwd_tc(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw16), _p(dTt), _p(ds), _p(dXF16), _p(dWs_part),
                                            _p(dtau_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd_tc")
         # projection-bias gradients from token-reduced quantities: db_x = (sum_t dL).Ws, db_fx = (sum_t w).dTt
         dbs_bh = dWs_part.view(B, H, groups, G, D + 1)[..., D].sum(2)
@@ -576,7 +588,8 @@ class LnMlpFn(torch.autograd.Function):
             # tensor-core MLP: bf16 operands; LN output and hidden activation only ever exist in bf16 (+ fp32 pre-activation
             # for GELU')
             hid16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
-            gemm_tc(x2_16, weight_bf16(W1), None, b1, 1, 1, M, C_, R, act=1, aux_out=pre, C16=hid16, tag="mlp_fc1")
+            pre = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)   # GELU' input for backward: bf16 is plenty
+            gemm_tc(x2_16, weight_bf16(W1), None, b1, 1, 1, M, C_, R, act=1, aux_out=pre, aux_bf16=1, C16=hid16, tag="mlp_fc1")
             out = torch.empty(*fx.shape[:-1], Cout, device=fx.device, dtype=torch.float32)
             gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, residual=fx, tag="mlp_fc2")
             ctx.save_for_backward(fx, gamma, W1, W2, x2_16, mean, rstd, pre, hid16)
@@ -610,10 +623,10 @@ class LnMlpFn(torch.autograd.Function):
             if dout16 is None:
                 dout16 = cast_bf16(dout)
             gemm_tc_wgrad(dout16, hid, 1, 1, M, Cout, R, C=dW2, tag="mlp_dW2")
-            dpre = torch.empty(M, R, **f32)
             dpre16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
-            gemm_tc(dout16, weight_bf16(W2, transpose=True), dpre, None, 1, 1, M, Cout, R, act=2, aux_in=pre, C16=dpre16, tag="mlp_dpre")
-            db1 = colsum(dpre, M, R)
+            gemm_tc(dout16, weight_bf16(W2, transpose=True), None, None, 1, 1, M, Cout, R, act=2, aux_in=pre, aux_bf16=1, C16=dpre16,
+                    tag="mlp_dpre")
+            db1 = colsum_bf16(dpre16, M, R)
             dW1 = torch.empty(R, C_, **f32)
             gemm_tc_wgrad(dpre16, x2, 1, 1, M, R, C_, C=dW1, tag="mlp_dW1")
             dx2 = torch.empty(M, C_, **f32)
