@@ -236,6 +236,14 @@ def run_ours(args):
         step_e2e(i)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
 
+    replicas_identical = None
+    if world > 1:
+        # data-parallel invariant: every reduction on the path is fixed-order, so replicas must stay BITWISE identical
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        digest = torch.stack([flat.double().sum(), flat.double().abs().sum(), flat[::97].double().sum()])
+        gathered = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(gathered, digest)
+        replicas_identical = all(bool(torch.equal(gathered[0], t)) for t in gathered)
     if rank == 0:
         pk = peaks()
         gb = PER_GPU_BATCH * world
@@ -274,7 +282,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": gb, "parallelism": f"dp{world}",
-                       "teacher_forced_calls_batched": batched, "cuda_graph": graphed,
+                       "teacher_forced_calls_batched": batched, "cuda_graph": graphed, "replicas_identical": replicas_identical,
                        "l2": "activations written per step (>1 GB) exceed the 126 MB L2; fresh input batch every step"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": per_step_in, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
