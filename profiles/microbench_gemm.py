@@ -1,5 +1,6 @@
 """Micro-benchmark of the tcgen05 GEMM kernels at the bench shapes (B=20 images of 64x64, C=256): CUDA-event timing of
 isolated launches with an L2 flush between iterations.  usage: python profiles/microbench_gemm.py [iters]"""
+import os
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -16,7 +17,7 @@ bias = torch.randn(I2, generator=g).to(dev)
 XF = torch.empty(M, I2, device=dev)
 W1 = (torch.randn(C, C, generator=g) / 16).to(dev).bfloat16()
 b1 = torch.randn(C, generator=g).to(dev)
-pre = torch.empty(M, C, device=dev)
+pre16 = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
 hid16 = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
 res = torch.randn(M, C, generator=g).to(dev)
 out = torch.empty(M, C, device=dev)
@@ -27,12 +28,18 @@ flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
 cases = {
     "conv_fprop 81920x2304x512": (lambda: ops.gemm_tc(x16, Wf16, XF, bias, B, Hg, Wg, C, I2, 9, 0), 2.0 * M * 9 * C * I2),
-    "fc1 81920x256x256 +bias+gelu+pre+bf16": (lambda: ops.gemm_tc(x16, W1, None, b1, 1, 1, M, C, C, act=1, aux_out=pre, C16=hid16), 2.0 * M * C * C),
+    "fc1 81920x256x256 +bias+gelu+pre16+bf16": (lambda: ops.gemm_tc(x16, W1, None, b1, 1, 1, M, C, C, act=1, aux_out=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
+    "dpre 81920x256x256 gelu'(pre16)+bf16": (lambda: ops.gemm_tc(x16, W1, None, None, 1, 1, M, C, C, act=2, aux_in=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
+    "dx2 81920x256x256 fp32 out": (lambda: ops.gemm_tc(x16, W1, out, None, 1, 1, M, C, C), 2.0 * M * C * C),
     "fc2 81920x256x256 +bias+res": (lambda: ops.gemm_tc(hid16, W1, out, b1, 1, 1, M, C, C, residual=res), 2.0 * M * C * C),
     "conv_wgrad 2304x512x81920": (lambda: ops.gemm_tc_wgrad(x16, dXF16, B, Hg, Wg, C, I2, taps=9, scatter=(dWx, dWfx), I=C), 2.0 * M * 9 * C * I2),
 }
+only = os.environ.get("MB_ONLY")          # comma-separated name prefixes (for ncu captures)
+warm = int(os.environ.get("MB_WARM", "3"))
+if only:
+    cases = {k: v for k, v in cases.items() if any(k.startswith(o) for o in only.split(","))}
 for name, (fn, flops) in cases.items():
-    for _ in range(3):
+    for _ in range(warm):
         fn()
     ts = []
     for _ in range(iters):
@@ -47,6 +54,8 @@ for name, (fn, flops) in cases.items():
     med = ts[len(ts) // 2]
     print(f"{name:45s} median {med*1e3:8.1f} us   {flops/med/1e9:8.1f} TFLOP/s")
 
+if only:
+    sys.exit(0)
 # slice stage: exact SIMT kernels vs the tcgen05 (tf32) kernels
 from transformerbasednavierstokesolver_b200 import _lib
 lib = _lib.load()

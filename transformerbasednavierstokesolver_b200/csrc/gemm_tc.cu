@@ -354,12 +354,44 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
 // fused epilogue on the two 16x256b fragments of a warp's 32-lane quadrant: v[0] = lanes 0..15, v[1] = lanes 16..31 (layout
 // above); grow[k] = global row of tile row (t/4 + 8k) or -1; n = first of the 32 columns; t = lane id.
 // All global loads (GELU' input, residual) are issued before any arithmetic so their latencies overlap.
-__device__ __forceinline__ void tc_epi_frag2(const TcParams& p, float (&v)[2][16], const long long (&grow)[4], int n, int t) {
+// EPI < 0: every option is a runtime test on TcParams.  EPI >= 0: a bit set of EPI_* flags fixed at compile time, so the
+// short-K contractions (whose time is all epilogue) run straight-line code for exactly the options they use.
+enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_DGELU = 4, EPI_RES = 8, EPI_ROUND = 16, EPI_C = 32, EPI_C16 = 64, EPI_AUX16 = 128,
+             EPI_AUXOUT = 256 };
+static int epi_code(const TcParams& p) {
+  return (p.bias ? EPI_BIAS : 0) | (p.act == 1 ? EPI_GELU : 0) | (p.act == 2 ? EPI_DGELU : 0) | (p.residual ? EPI_RES : 0) |
+         (p.round_tf32 ? EPI_ROUND : 0) | (p.C ? EPI_C : 0) | (p.C16 ? EPI_C16 : 0) | (p.aux_bf16 ? EPI_AUX16 : 0) |
+         (p.act == 1 && p.aux_out ? EPI_AUXOUT : 0);
+}
+
+template <int EPI>
+__device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][16], const long long (&grow)[4], int n, int t) {
+  // compile-time view of the options (constant-folded when EPI >= 0)
+  struct {
+    const float* bias; int act; float* aux_out; const float* aux_in; long long ldaux; const float* residual; long long ldr;
+    float* C; long long ldc; __nv_bfloat16* C16; long long ldc16; int round_tf32; int aux_bf16;
+  } p;
+  constexpr bool GEN = EPI < 0;
+  p.bias = (GEN || (EPI & EPI_BIAS)) ? pp.bias : nullptr;
+  p.act = GEN ? pp.act : ((EPI & EPI_GELU) ? 1 : (EPI & EPI_DGELU) ? 2 : 0);
+  p.aux_out = (GEN || (EPI & EPI_AUXOUT)) ? pp.aux_out : nullptr;
+  p.aux_in = pp.aux_in;
+  p.ldaux = pp.ldaux;
+  p.residual = (GEN || (EPI & EPI_RES)) ? pp.residual : nullptr;
+  p.ldr = pp.ldr;
+  p.C = (GEN || (EPI & EPI_C)) ? pp.C : nullptr;
+  p.ldc = pp.ldc;
+  p.C16 = (GEN || (EPI & EPI_C16)) ? pp.C16 : nullptr;
+  p.ldc16 = pp.ldc16;
+  p.round_tf32 = GEN ? pp.round_tf32 : ((EPI & EPI_ROUND) ? 1 : 0);
+  p.aux_bf16 = GEN ? pp.aux_bf16 : ((EPI & EPI_AUX16) ? 1 : 0);
+  constexpr bool K_BIAS = !GEN && (EPI & EPI_BIAS), K_RES = !GEN && (EPI & EPI_RES), K_C = !GEN && (EPI & EPI_C),
+                 K_C16 = !GEN && (EPI & EPI_C16), K_AUXOUT = !GEN && (EPI & EPI_AUXOUT);
   const int cb = n + 2 * (t & 3);
   float2 ld[4][4];   // [row k][column group j]
   const float* src = p.act == 2 ? p.aux_in : p.residual;
   const long long lds = p.act == 2 ? p.ldaux : p.ldr;
-  if (src) {
+  if (K_RES || p.act == 2 || (GEN && src)) {
     const bool h16 = p.act == 2 && p.aux_bf16;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -376,7 +408,8 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& p, float (&v)[2][16
   }
   float2 bias[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) bias[j] = p.bias ? *reinterpret_cast<const float2*>(p.bias + cb + 8 * j) : make_float2(0.f, 0.f);
+  for (int j = 0; j < 4; ++j)
+    bias[j] = (K_BIAS || (GEN && p.bias)) ? *reinterpret_cast<const float2*>(p.bias + cb + 8 * j) : make_float2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const long long gr = grow[k];
@@ -387,7 +420,7 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& p, float (&v)[2][16
       const int c = cb + 8 * j;
       float x0 = v[k >> 1][4 * j + 2 * (k & 1)] + bias[j].x, x1 = v[k >> 1][4 * j + 2 * (k & 1) + 1] + bias[j].y;
       if (p.act == 1) {
-        if (p.aux_out) {
+        if (K_AUXOUT || (GEN && p.aux_out)) {
           if (p.aux_bf16) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + gr * p.ldaux + c) = __floats2bfloat162_rn(x0, x1);
           else *reinterpret_cast<float2*>(p.aux_out + gr * p.ldaux + c) = make_float2(x0, x1);
         }
@@ -396,7 +429,7 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& p, float (&v)[2][16
       } else if (p.act == 2) {
         x0 *= gelu_grad_fast(ld[k][j].x);
         x1 *= gelu_grad_fast(ld[k][j].y);
-      } else if (p.residual) {
+      } else if (K_RES || (GEN && p.residual)) {
         x0 += ld[k][j].x;
         x1 += ld[k][j].y;
       }
@@ -407,8 +440,8 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& p, float (&v)[2][16
         x0 = __uint_as_float(u0);
         x1 = __uint_as_float(u1);
       }
-      if (p.C) *reinterpret_cast<float2*>(p.C + gr * p.ldc + c) = make_float2(x0, x1);
-      if (p.C16) {
+      if (K_C || (GEN && p.C)) *reinterpret_cast<float2*>(p.C + gr * p.ldc + c) = make_float2(x0, x1);
+      if (K_C16 || (GEN && p.C16)) {
         // bf16 pairs are only 4 bytes: trade pairs with the neighbouring lane so that every thread owns 4 consecutive columns
         // (8 bytes) of column group j or j+1 and four threads fill one 32-byte sector of the row
         __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
@@ -437,7 +470,7 @@ struct TcpSmem {
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                           int total_tiles) {
@@ -573,7 +606,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           mbar_arrive(bar_acce + as * 8);
           handed_back = true;
         }
-        tc_epi_frag2(p, v, grow, n0 + c0, lane);
+        tc_epi_frag2<EPI>(p, v, grow, n0 + c0, lane);
       }
       if (!handed_back) mbar_arrive(bar_acce + as * 8);   // narrow tiles: this warp's column slot does not exist
     }
@@ -747,10 +780,10 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
   return TBNS_OK;
 }
 
-template <int BN, int STAGES>
-static int launch_tcp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
+template <int BN, int STAGES, int EPI>
+static int launch_tcp_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
   using S = TcpSmem<BN, STAGES>;
-  TBNS_SMEM_OPT_IN((gemm_tc_persistent_kernel<BN, STAGES>), S::TOTAL);
+  TBNS_SMEM_OPT_IN((gemm_tc_persistent_kernel<BN, STAGES, EPI>), S::TOTAL);
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -759,9 +792,31 @@ static int launch_tcp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPa
   }
   const int total = m_tiles * (p.N / BN);
   const int grid = total < sms ? total : sms;
-  gemm_tc_persistent_kernel<BN, STAGES><<<grid, TCP_THREADS, S::TOTAL, st>>>(tmA, tmB, p, total);
+  gemm_tc_persistent_kernel<BN, STAGES, EPI><<<grid, TCP_THREADS, S::TOTAL, st>>>(tmA, tmB, p, total);
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
+}
+
+// the option sets of the Transolver block's contractions get straight-line epilogues; anything else takes the generic one
+template <int BN, int STAGES>
+static int launch_tcp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
+  static const bool generic_only = [] { const char* e = getenv("TBNS_TC_EPI_GENERIC"); return e && e[0] == '1'; }();
+  if (!generic_only) {
+    switch (epi_code(p)) {
+#define TBNS_EPI_CASE(code) case (code): return launch_tcp_epi<BN, STAGES, (code)>(tmA, tmB, p, m_tiles, st);
+      TBNS_EPI_CASE(EPI_C)                                                          // dgrad, dx2
+      TBNS_EPI_CASE(EPI_BIAS | EPI_C)                                               // projection fprop
+      TBNS_EPI_CASE(EPI_BIAS | EPI_ROUND | EPI_C)                                   // projection fprop feeding the tf32 slice stage
+      TBNS_EPI_CASE(EPI_BIAS | EPI_RES | EPI_C)                                     // deslice (+) to_out + residual, fc2 + residual
+      TBNS_EPI_CASE(EPI_C | EPI_C16)                                                // dw (fp32 + bf16)
+      TBNS_EPI_CASE(EPI_C16)                                                        // dw (bf16 only)
+      TBNS_EPI_CASE(EPI_BIAS | EPI_GELU | EPI_AUXOUT | EPI_AUX16 | EPI_C16)         // fc1: pre (bf16) + gelu (bf16)
+      TBNS_EPI_CASE(EPI_DGELU | EPI_AUX16 | EPI_C16)                                // dpre = (dy W2) * gelu'(pre)
+#undef TBNS_EPI_CASE
+      default: break;
+    }
+  }
+  return launch_tcp_epi<BN, STAGES, -1>(tmA, tmB, p, m_tiles, st);
 }
 
 template <int BN, int STAGES>
