@@ -128,6 +128,17 @@ int tbns_layernorm_bwd(const float* dy, const float* x, const float* mean, const
                        float* dsum /* optional [C]: column sums of dx = bias gradient of the layer that produced this stream */,
                        float* ws, int rows, int C, void* stream);
 
+/* Last layer with out_dim = 1: out = mlp2(ln_3(x)) = LN(x) . w + b in one pass over x
+ * (model/Transolver_Structured_Mesh_2D.py:66-67,72-73).  C in {128, 256, 512}. */
+int tbns_ln_linear1_supported(int C);
+int tbns_ln_linear1_fwd(const float* x, const float* gamma, const float* beta, const float* w /* [C] */, const float* b /* [1] */,
+                        float* out /* [rows] */, float* mean, float* rstd, int rows, int C, float eps, void* stream);
+/* dx = LN'(dout (x) w) + dres.  sums [3][C]: S_c = sum_r dout[r]*xhat[r][c] | D = sum_r dout[r] (replicated over c) |
+ * column sums of dx; then dgamma = w*S, dbeta = w*D, dw = gamma*S + beta*D, db = D.  ws: tbns_layernorm_bwd_ws_floats(C). */
+int tbns_ln_linear1_bwd(const float* dout /* [rows] */, const float* w, const float* x, const float* mean, const float* rstd,
+                        const float* gamma, const float* dres, float* dx, void* dx16, float* sums, float* ws, int rows, int C,
+                        void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Weight packing for the projections (nn.Conv2d 3x3 / nn.Linear pair in_project_x, in_project_fx:
  * model/Physics_Attention.py:18-19, :74-75).  taps = 9 (structured) or 1 (irregular).

@@ -142,6 +142,28 @@ def test_layernorm(dev, rows, C):
     assert O.rel_l2(db.cpu(), rdb) < 5e-6
 
 
+@pytest.mark.parametrize("rows,C,Od", [(5000, 256, 1), (777, 128, 1), (300, 512, 1), (1000, 256, 3), (50, 96, 1)])
+def test_last_layer_ln_linear(dev, rows, C, Od):
+    """mlp2(ln_3(fx)): the fused out_dim=1 kernels (C in {128,256,512}) and the generic route, against the oracle
+    (model/Transolver_Structured_Mesh_2D.py:72-73)."""
+    ops = _ops()
+    from transformerbasednavierstokesolver_b200._lib import TBNS_PREC_FP32
+    g = torch.Generator().manual_seed(rows + C + Od)
+    fx = (torch.randn(2, rows // 2, C, generator=g) * 1.5 + 0.3)
+    gam, bet = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    W, b = torch.randn(Od, C, generator=g) / C ** 0.5, torch.randn(Od, generator=g)
+    dout = torch.randn(2, rows // 2, Od, generator=g)
+    t = [v.to(dev).requires_grad_(True) for v in (fx, gam, bet, W, b)]
+    out = ops.LnLinearFn.apply(*t, 1e-5, TBNS_PREC_FP32)
+    out.backward(dout.to(dev))
+    rout, sv = O.ln_linear_fwd(fx.double(), gam.double(), bet.double(), W.double(), b.double())
+    rdfx, rg = O.ln_linear_bwd(dout.double(), gam.double(), W.double(), sv)
+    assert O.rel_l2(out.detach().cpu(), rout) < 1e-5
+    for got, want in zip([v.grad for v in t], [rdfx, rg["ln_w"], rg["ln_b"], rg["W"], rg["b"]]):
+        assert got.shape == want.shape
+        assert O.rel_l2(got.cpu(), want) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------
 # attention module / block / model against the golden vectors of the live reference
 # ------------------------------------------------------------------------------------------------

@@ -225,3 +225,32 @@ def test_tc_slice_bwd_matches_simt(B, N, H, G):
     ta = dtau_p.view(B, H, groups).sum((0, 2)).cpu()
     tr = dtau_ref.view(B, H, groups).sum((0, 2)).cpu()
     assert O.rel_l2(ta, tr) < 1e-2     # sum of signed dL'*L terms: cancellation amplifies the tf32 operand rounding
+
+
+@pytest.mark.parametrize("M,K,R,Cout,need_dx", [(8192, 74, 512, 256, False), (972, 2, 256, 128, True), (4096, 65, 256, 128, True)])
+def test_preprocess_mlp_tc(M, K, R, Cout, need_dx):
+    """ops.MlpFn (preprocess on the tensor cores, K zero-padded to 64) against fp64 torch on bf16-representable operands:
+    model/Transolver_Structured_Mesh_2D.py:13-38,206-207.  bf16-mode tolerance 2e-3 on the output (hidden activation is rounded to bf16), 5e-3 on gradients."""
+    from transformerbasednavierstokesolver_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + K)
+    r16 = lambda t: t.bfloat16().float()
+    inp = r16(torch.randn(2, M // 2, K, generator=g)).to(dev).requires_grad_(need_dx)
+    W1 = r16(torch.randn(R, K, generator=g) / K ** 0.5).to(dev).requires_grad_(True)
+    b1 = (0.1 * torch.randn(R, generator=g)).to(dev).requires_grad_(True)
+    W2 = r16(torch.randn(Cout, R, generator=g) / R ** 0.5).to(dev).requires_grad_(True)
+    b2 = (0.1 * torch.randn(Cout, generator=g)).to(dev).requires_grad_(True)
+    dout = torch.randn(2, M // 2, Cout, generator=g).to(dev)
+    assert ops.mlp_tc_ok(K, R, Cout)
+    out = ops.MlpFn.apply(inp, W1, b1, W2, b2)
+    out.backward(dout)
+    got = [out] + [t.grad for t in ((inp,) if need_dx else ()) + (W1, b1, W2, b2)]
+    ref_in = [t.detach().cpu().double().requires_grad_(True) for t in (inp, W1, b1, W2, b2)]
+    ri, rW1, rb1, rW2, rb2 = ref_in
+    rout = torch.nn.functional.gelu(ri @ rW1.t() + rb1) @ rW2.t() + rb2
+    rout.backward(dout.cpu().double())
+    want = [rout.detach()] + [t.grad for t in ((ri,) if need_dx else ()) + (rW1, rb1, rW2, rb2)]
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a.shape == b.shape
+        # output: one bf16 rounding (hidden activation); gradients: two more (incoming gradient, GELU' product)
+        assert O.rel_l2(a.detach().cpu().double(), b) < (2e-3 if i == 0 else 5e-3)

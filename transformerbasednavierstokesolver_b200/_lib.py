@@ -82,6 +82,9 @@ _SIGS = {
     "tbns_layernorm_fwd": (_i, [_fp] * 7 + [_i, _i, C.c_float, _fp]),
     "tbns_layernorm_bwd_ws_floats": (C.c_size_t, [_i]),
     "tbns_layernorm_bwd": (_i, [_fp] * 12 + [_i, _i, _fp]),
+    "tbns_ln_linear1_supported": (_i, [_i]),
+    "tbns_ln_linear1_fwd": (_i, [_fp] * 8 + [_i, _i, C.c_float, _fp]),
+    "tbns_ln_linear1_bwd": (_i, [_fp] * 11 + [_i, _i, _fp]),
     "tbns_pack_proj_weights": (_i, [_fp] * 7 + [_i, _i, _i, _fp]),
     "tbns_slice_groups": (_i, [_i, _i, _i]),
     "tbns_pa_slice_fwd": (_i, [_fp] * 7 + [_i] * 6 + [_fp]),

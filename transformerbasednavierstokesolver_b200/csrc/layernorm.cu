@@ -165,19 +165,25 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
 // between the two passes, dgamma / dbeta / column-sum accumulators live in registers, one combine through shared memory at
 // the end.  part: [cta][3][C] = dgamma | dbeta | column sums of the OUTPUT dx (= bias gradient of whatever produced the
 // tensor this gradient belongs to; see ops.py).
-template <int NV>
+//
+// R1 (rank-one dy, the model's last layer mlp2 = Linear(C -> 1) after ln_3): dy[row][c] = dy[row] * wvec[c] is formed on the
+// fly from the [rows] gradient of the scalar output, and the first two accumulators hold S_c = sum_r dy[r]*xhat[r][c] and
+// D = sum_r dy[r] instead, from which dgamma = w*S, dbeta = w*D, dW = gamma*S + beta*D, db = D.
+template <int NV, bool R1>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                         const float* __restrict__ gamma, const float* __restrict__ dres,
                                                                         float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
-                                                                        float* __restrict__ part, int rows) {
+                                                                        float* __restrict__ part, int rows,
+                                                                        const float* __restrict__ wvec) {
   constexpr int C = NV * 128;
   __shared__ __align__(16) float sm[LN_WARPS][3][C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 g4[NV], ag[NV], ab[NV], as[NV];
+  float4 g4[NV], w4[R1 ? NV : 1], ag[NV], ab[NV], as[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     g4[k] = *reinterpret_cast<const float4*>(gamma + lane * 4 + k * 128);
+    if (R1) w4[R1 ? k : 0] = *reinterpret_cast<const float4*>(wvec + lane * 4 + k * 128);
     ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[k] = ag[k];
     as[k] = ag[k];
@@ -188,9 +194,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_reg_kernel(const 
     const float mu = mean[row], rs = rstd[row];
     float4 d4[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
+    const float dsc = R1 ? dy[row] : 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      d4[k] = *reinterpret_cast<const float4*>(dy + off + k * 128);
+      if (R1) {
+        const float4 w = w4[R1 ? k : 0];
+        d4[k] = make_float4(dsc * w.x, dsc * w.y, dsc * w.z, dsc * w.w);
+      } else {
+        d4[k] = *reinterpret_cast<const float4*>(dy + off + k * 128);
+      }
       const float4 xv = *reinterpret_cast<const float4*>(x + off + k * 128);
       xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       const float gx = d4[k].x * g4[k].x, gy = d4[k].y * g4[k].y, gz = d4[k].z * g4[k].z, gw = d4[k].w * g4[k].w;
@@ -214,8 +226,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_reg_kernel(const 
         __nv_bfloat162 h2[2] = {__floats2bfloat162_rn(o.x, o.y), __floats2bfloat162_rn(o.z, o.w)};
         *reinterpret_cast<uint2*>(dx16 + off + k * 128) = *reinterpret_cast<uint2*>(h2);
       }
-      ag[k].x += d4[k].x * xh[k].x; ag[k].y += d4[k].y * xh[k].y; ag[k].z += d4[k].z * xh[k].z; ag[k].w += d4[k].w * xh[k].w;
-      ab[k].x += d4[k].x; ab[k].y += d4[k].y; ab[k].z += d4[k].z; ab[k].w += d4[k].w;
+      if (R1) {
+        ag[k].x += dsc * xh[k].x; ag[k].y += dsc * xh[k].y; ag[k].z += dsc * xh[k].z; ag[k].w += dsc * xh[k].w;
+        ab[k].x += dsc; ab[k].y += dsc; ab[k].z += dsc; ab[k].w += dsc;
+      } else {
+        ag[k].x += d4[k].x * xh[k].x; ag[k].y += d4[k].y * xh[k].y; ag[k].z += d4[k].z * xh[k].z; ag[k].w += d4[k].w * xh[k].w;
+        ab[k].x += d4[k].x; ab[k].y += d4[k].y; ab[k].z += d4[k].z; ab[k].w += d4[k].w;
+      }
       as[k].x += o.x; as[k].y += o.y; as[k].z += o.z; as[k].w += o.w;
     }
   }
@@ -242,6 +259,28 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restri
     float s = 0.f;
     for (int i = 0; i < rows; ++i) s += in[(long long)i * ld + j];
     out[j] = s;
+  }
+}
+
+// Tall partial buffers (hundreds of rows, a few hundred columns): 32 row lanes x 32 column lanes per CTA.  Row lane l adds
+// rows l, l+32, ... in ascending order, then the lanes are combined in lane order: fixed order, bit-reproducible, and the
+// loads of a thread are independent so the pass is not a chain of exposed latencies.
+__global__ void __launch_bounds__(1024) reduce_rows_par_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, long long ld) {
+  __shared__ float red[32][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float acc = 0.f;
+  if (c < cols) {
+#pragma unroll 4
+    for (int r = rl; r < rows; r += 32) acc += in[(long long)r * ld + c];
+  }
+  red[rl][cl] = acc;
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+    float s = red[0][cl];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) s += red[i][cl];
+    out[c] = s;
   }
 }
 
@@ -301,6 +340,11 @@ extern "C" size_t tbns_layernorm_bwd_ws_floats(int C) { return (size_t)LN_BWD_CT
 extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long cols, void* stream) {
   TBNS_REQUIRE(in && out && rows >= 0 && cols >= 0, "tbns_reduce_rows: bad args");
   if (cols == 0) return TBNS_OK;
+  if (rows >= 64 && cols <= 148LL * 32 * 8) {
+    reduce_rows_par_kernel<<<(unsigned)((cols + 31) / 32), 1024, 0, (cudaStream_t)stream>>>(in, out, rows, (int)cols, cols);
+    TBNS_LAUNCH_CHECK();
+    return TBNS_OK;
+  }
   if (cols <= 0x7fffffffLL && (cols % 4 == 0) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && cols / 128 < 65535 * 32) {
     // 8 row-lanes x 32 float4 column-lanes per CTA, fixed summation order
     colsum_partial_kernel<<<dim3((unsigned)((cols + 127) / 128), 1), 256, 0, (cudaStream_t)stream>>>(in, cols, out, rows, (int)cols, rows);
@@ -325,23 +369,23 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
   if (aligned && (C == 128 || C == 256 || C == 512)) {
     int ctas = cdiv(rows, LN_WARPS * 2);
     if (ctas > LN_BWD_CTAS) ctas = LN_BWD_CTAS;
-    if (C == 128) layernorm_bwd_reg_kernel<1><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows);
-    else if (C == 256) layernorm_bwd_reg_kernel<2><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows);
-    else layernorm_bwd_reg_kernel<4><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows);
+    if (C == 128) layernorm_bwd_reg_kernel<1, false><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
+    else if (C == 256) layernorm_bwd_reg_kernel<2, false><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
+    else layernorm_bwd_reg_kernel<4, false><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
     TBNS_LAUNCH_CHECK();
     // ws rows are [dgamma | dbeta | colsum(dx)], width 3C: fixed-order reduction; a single launch when the caller's three
     // outputs are one contiguous [3][C] array
     if (dsum && dbeta == dgamma + C && dsum == dgamma + 2 * C) {
-      colsum_partial_kernel<<<dim3(cdiv(3 * C, 128), 1), 256, 0, st>>>(ws, 3LL * C, dgamma, ctas, 3 * C, ctas);
+      reduce_rows_par_kernel<<<cdiv(3 * C, 32), 1024, 0, st>>>(ws, dgamma, ctas, 3 * C, 3LL * C);
       TBNS_LAUNCH_CHECK();
       return TBNS_OK;
     }
-    colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws, 3LL * C, dgamma, ctas, C, ctas);
+    reduce_rows_par_kernel<<<cdiv(C, 32), 1024, 0, st>>>(ws, dgamma, ctas, C, 3LL * C);
     TBNS_LAUNCH_CHECK();
-    colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws + C, 3LL * C, dbeta, ctas, C, ctas);
+    reduce_rows_par_kernel<<<cdiv(C, 32), 1024, 0, st>>>(ws + C, dbeta, ctas, C, 3LL * C);
     TBNS_LAUNCH_CHECK();
     if (dsum) {
-      colsum_partial_kernel<<<dim3(cdiv(C, 128), 1), 256, 0, st>>>(ws + 2 * C, 3LL * C, dsum, ctas, C, ctas);
+      reduce_rows_par_kernel<<<cdiv(C, 32), 1024, 0, st>>>(ws + 2 * C, dsum, ctas, C, 3LL * C);
       TBNS_LAUNCH_CHECK();
     }
     return TBNS_OK;
@@ -438,4 +482,84 @@ extern "C" int tbns_colsum_bf16(const void* in16, long long ld, float* out, floa
   colsum16_partial_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in16), ld, ws, rows, cols, rows_per_chunk);
   TBNS_LAUNCH_CHECK();
   return tbns_reduce_rows(ws, out, chunks, cols, stream);
+}
+
+// ---- last layer: mlp2(ln_3(fx)) with out_dim = 1  (model/Transolver_Structured_Mesh_2D.py:72-73) -------------------------
+// forward: LayerNorm and the C -> 1 projection in one pass over the row (nothing but [rows] scalars is written);
+// backward: the rank-one variant of the register-resident LayerNorm backward above.
+namespace tbns {
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_linear1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, const float* __restrict__ w,
+                                                                     const float* __restrict__ b, float* __restrict__ out,
+                                                                     float* __restrict__ mean, float* __restrict__ rstd, int rows, int C,
+                                                                     float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + warp;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * C;
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mu = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float a = v.x - mu, bb = v.y - mu, cc = v.z - mu, dd = v.w - mu;
+    q += (a * a + bb * bb) + (cc * cc + dd * dd);
+  }
+  const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
+  float dot = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    const float4 ww = *reinterpret_cast<const float4*>(w + c);
+    dot += (((v.x - mu) * rs * g.x + be.x) * ww.x + ((v.y - mu) * rs * g.y + be.y) * ww.y) +
+           (((v.z - mu) * rs * g.z + be.z) * ww.z + ((v.w - mu) * rs * g.w + be.w) * ww.w);
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    out[row] = dot + b[0];
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+}
+}  // namespace tbns
+
+extern "C" int tbns_ln_linear1_supported(int C) { return (C == 128 || C == 256 || C == 512) ? 1 : 0; }
+
+extern "C" int tbns_ln_linear1_fwd(const float* x, const float* gamma, const float* beta, const float* w, const float* b, float* out,
+                                   float* mean, float* rstd, int rows, int C, float eps, void* stream) {
+  TBNS_REQUIRE(x && gamma && beta && w && b && out && mean && rstd, "tbns_ln_linear1_fwd: null pointer");
+  TBNS_REQUIRE(rows >= 0 && tbns_ln_linear1_supported(C), "tbns_ln_linear1_fwd: C=%d unsupported (128, 256, 512)", C);
+  TBNS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                 reinterpret_cast<uintptr_t>(w)) & 15) == 0, "tbns_ln_linear1_fwd: pointers must be 16-byte aligned");
+  if (rows == 0) return TBNS_OK;
+  ln_linear1_fwd_kernel<<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, w, b, out, mean, rstd, rows, C, eps);
+  TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
+}
+
+/* sums: [3][C] = S (sum_r dout[r]*xhat[r][c]) | D (sum_r dout[r], replicated over c) | column sums of dx */
+extern "C" int tbns_ln_linear1_bwd(const float* dout, const float* w, const float* x, const float* mean, const float* rstd,
+                                   const float* gamma, const float* dres, float* dx, void* dx16, float* sums, float* ws, int rows,
+                                   int C, void* stream) {
+  TBNS_REQUIRE(dout && w && x && mean && rstd && gamma && dx && sums && ws, "tbns_ln_linear1_bwd: null pointer");
+  TBNS_REQUIRE(rows > 0 && tbns_ln_linear1_supported(C), "tbns_ln_linear1_bwd: C=%d unsupported (128, 256, 512)", C);
+  TBNS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(gamma) |
+                 reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(dx16)) & 15) == 0,
+               "tbns_ln_linear1_bwd: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(dx16);
+  int ctas = cdiv(rows, LN_WARPS * 2);
+  if (ctas > LN_BWD_CTAS) ctas = LN_BWD_CTAS;
+  if (C == 128) layernorm_bwd_reg_kernel<1, true><<<ctas, LN_WARPS * 32, 0, st>>>(dout, x, mean, rstd, gamma, dres, dx, o16, ws, rows, w);
+  else if (C == 256) layernorm_bwd_reg_kernel<2, true><<<ctas, LN_WARPS * 32, 0, st>>>(dout, x, mean, rstd, gamma, dres, dx, o16, ws, rows, w);
+  else layernorm_bwd_reg_kernel<4, true><<<ctas, LN_WARPS * 32, 0, st>>>(dout, x, mean, rstd, gamma, dres, dx, o16, ws, rows, w);
+  TBNS_LAUNCH_CHECK();
+  reduce_rows_par_kernel<<<cdiv(3 * C, 32), 1024, 0, st>>>(ws, sums, ctas, 3 * C, 3LL * C);
+  TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
 }

@@ -15,7 +15,7 @@ ACTIVATION = {'gelu': nn.GELU, 'tanh': nn.Tanh, 'sigmoid': nn.Sigmoid, 'relu': n
 
 class MLP(nn.Module):
     """linear_pre -> [linears] -> linear_post; parameter names follow the reference so checkpoints load.
-    Used as-is (PyTorch) for `preprocess`; inside a block it is only a parameter container — the block runs
+    `preprocess` runs through ops.MlpFn in bf16 mode (PyTorch modules in fp32 mode); inside a block it is only a parameter container — the block runs
     the fused LayerNorm+MLP kernels instead."""
 
     def __init__(self, n_input, n_hidden, n_output, n_layers=1, act='gelu', res=True):
@@ -30,6 +30,11 @@ class MLP(nn.Module):
         self.linears = nn.ModuleList([nn.Sequential(nn.Linear(n_hidden, n_hidden), act_cls()) for _ in range(n_layers)])
 
     def forward(self, x):
+        pre, post = self.linear_pre[0], self.linear_post
+        if (x.is_cuda and self.n_layers == 0 and self.act_name == 'gelu' and config.get_default_precision() == "bf16"
+                and x.dtype == torch.float32 and ops.mlp_tc_ok(self.n_input, self.n_hidden, self.n_output)):
+            # bf16 mode: both Linears on the tensor cores (libtbns), GELU fused into the first one's epilogue
+            return ops.MlpFn.apply(x, pre.weight, pre.bias, post.weight, post.bias)
         x = self.linear_pre(x)
         for layer in self.linears:
             x = layer(x) + x if self.res else layer(x)

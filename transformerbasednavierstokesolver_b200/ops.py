@@ -162,6 +162,21 @@ def weight_bf16(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     return w16
 
 
+def weight_bf16_padded(W: torch.Tensor, Kp: int, transpose: bool = False) -> torch.Tensor:
+    """like weight_bf16 for a weight [R, K] whose K is zero-padded to Kp (tensor-core contractions take K in units of 64):
+    [R, Kp] or, transposed, [Kp, R]."""
+    key = (W.data_ptr(), transpose, Kp)
+    hit = _W16_CACHE.get(key)
+    if hit is not None and hit[0] == W._version:
+        return hit[1]
+    with torch.no_grad():
+        wp = torch.zeros(W.shape[0], Kp, device=W.device, dtype=torch.float32)
+        wp[:, :W.shape[1]] = W.detach()
+        w16 = cast_bf16(wp.t().contiguous() if transpose else wp)
+    _W16_CACHE[key] = (W._version, w16)
+    return w16
+
+
 def tc_supported(Cin: int, N: int, taps: int) -> bool:
     return bool(_lib.load().tbns_gemm_tc_supported(Cin, N, taps))
 
@@ -650,29 +665,119 @@ class LnMlpFn(torch.autograd.Function):
         return dfx.view_as(fx), dg, db, dW1, db1, dW2, db2, None, None
 
 
+def mlp_tc_ok(K: int, R: int, Cout: int) -> bool:
+    Kp = -(-K // 64) * 64
+    return (tc_supported(Kp, R, 1) and tc_supported(R, Cout, 1) and tc_supported(R, Kp, 1) and tc_supported(Cout, R, 1)
+            and wgrad_supported(Cout, R, 1) and wgrad_supported(R, Kp, 1))
+
+
+class MlpFn(torch.autograd.Function):
+    """`preprocess`: Linear(K -> R) + GELU + Linear(R -> Cout) on the tensor cores (bf16 mode)
+    model/Transolver_Structured_Mesh_2D.py:13-38,165-166,206-207.  K (= fun_dim + 64 or + space_dim) is zero-padded to a
+    multiple of 64 so the input rows are whole TMA boxes."""
+
+    @staticmethod
+    def forward(ctx, inp, W1, b1, W2, b2):
+        K = inp.shape[-1]
+        M = inp.numel() // K
+        R, Cout = W1.shape[0], W2.shape[0]
+        Kp = -(-K // 64) * 64
+        dev = inp.device
+        in16 = torch.zeros(M, Kp, device=dev, dtype=torch.bfloat16)
+        in16[:, :K] = inp.reshape(M, K)
+        b1, b2 = b1.contiguous(), b2.contiguous()
+        pre16 = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
+        hid16 = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
+        gemm_tc(in16, weight_bf16_padded(W1, Kp), None, b1, 1, 1, M, Kp, R, act=1, aux_out=pre16, aux_bf16=1, C16=hid16, tag="pre_fc1")
+        out = torch.empty(*inp.shape[:-1], Cout, device=dev, dtype=torch.float32)
+        gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, tag="pre_fc2")
+        ctx.save_for_backward(in16, W1, W2, pre16, hid16)
+        ctx.K = K
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        in16, W1, W2, pre16, hid16 = ctx.saved_tensors
+        K = ctx.K
+        M, Kp = in16.shape
+        R, Cout = W1.shape[0], W2.shape[0]
+        f32 = dict(device=dout.device, dtype=torch.float32)
+        dout = dout.contiguous()
+        dout16, db2 = _take_grad16(dout)
+        if dout16 is None:
+            dout16 = cast_bf16(dout)
+        if db2 is None:
+            db2 = colsum(dout, M, Cout)
+        dW2 = torch.empty(Cout, R, **f32)
+        gemm_tc_wgrad(dout16, hid16, 1, 1, M, Cout, R, C=dW2, tag="pre_dW2")
+        dpre16 = torch.empty(M, R, device=dout.device, dtype=torch.bfloat16)
+        gemm_tc(dout16, weight_bf16(W2, transpose=True), None, None, 1, 1, M, Cout, R, act=2, aux_in=pre16, aux_bf16=1, C16=dpre16,
+                tag="pre_dpre")
+        db1 = colsum_bf16(dpre16, M, R)
+        dW1p = torch.empty(R, Kp, **f32)
+        gemm_tc_wgrad(dpre16, in16, 1, 1, M, R, Kp, C=dW1p, tag="pre_dW1")
+        dinp = None
+        if ctx.needs_input_grad[0]:
+            dxp = torch.empty(M, Kp, **f32)
+            gemm_tc(dpre16, weight_bf16_padded(W1, Kp, transpose=True), dxp, None, 1, 1, M, R, Kp, tag="pre_dx")
+            dinp = dxp[:, :K].reshape(*dout.shape[:-1], K)
+        return dinp, dW1p[:, :K], db1, dW2, db2
+
+
 class LnLinearFn(torch.autograd.Function):
-    """last layer: mlp2(ln_3(fx))   model/Transolver_Structured_Mesh_2D.py:72-73"""
+    """last layer: mlp2(ln_3(fx))   model/Transolver_Structured_Mesh_2D.py:72-73.
+    out_dim == 1 (every reference script) runs as one fused pass per direction (tbns_ln_linear1_fwd/_bwd); other widths go
+    through LayerNorm + the generic contraction."""
 
     @staticmethod
     def forward(ctx, fx, gamma, beta, W, b, eps, precision):
         fx = fx.contiguous()
         gamma, beta, W, b = (t.contiguous() for t in (gamma, beta, W, b))
         _chk(fx, gamma, beta, W, b)
+        lib = _lib.load()
         C_ = fx.shape[-1]
         M = fx.numel() // C_
         Od = W.shape[0]
-        x3, _, mean, rstd = layernorm_fwd(fx, gamma, beta, eps)
+        ctx.precision = precision
+        ctx.fused1 = bool(Od == 1 and lib.tbns_ln_linear1_supported(C_))
         out = torch.empty(*fx.shape[:-1], Od, device=fx.device, dtype=torch.float32)
+        if ctx.fused1:
+            mean = torch.empty(M, device=fx.device, dtype=torch.float32)
+            rstd = torch.empty_like(mean)
+            with _Timed("ln_linear1_fwd"):
+                check(lib.tbns_ln_linear1_fwd(_p(fx), _p(gamma), _p(beta), _p(W), _p(b), _p(out), _p(mean), _p(rstd), M, C_,
+                                              float(eps), _stream()), "tbns_ln_linear1_fwd")
+            _count(1)
+            ctx.save_for_backward(fx, gamma, beta, W, mean, rstd)
+            return out
+        x3, _, mean, rstd = layernorm_fwd(fx, gamma, beta, eps)
         gemm(M=M, N=Od, K=C_, A=x3, lda=C_, a_kind=0, B=W, ldb=C_, b_kind=0, C=out, ldc=Od, bias=b, precision=precision)
         ctx.save_for_backward(fx, gamma, W, x3, mean, rstd)
-        ctx.precision = precision
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        fx, gamma, W, x3, mean, rstd = ctx.saved_tensors
         precision = ctx.precision
         dout = dout.contiguous()
+        if ctx.fused1:
+            fx, gamma, beta, W, mean, rstd = ctx.saved_tensors
+            lib = _lib.load()
+            C_ = fx.shape[-1]
+            M = fx.numel() // C_
+            want16 = precision == TBNS_PREC_BF16
+            dfx = torch.empty_like(fx)
+            dfx16 = torch.empty(fx.shape, device=fx.device, dtype=torch.bfloat16) if want16 else None
+            sums = torch.empty(3, C_, device=fx.device, dtype=torch.float32)
+            ws = torch.empty(lib.tbns_layernorm_bwd_ws_floats(C_), device=fx.device, dtype=torch.float32)
+            with _Timed("ln_linear1_bwd"):
+                check(lib.tbns_ln_linear1_bwd(_p(dout), _p(W), _p(fx), _p(mean), _p(rstd), _p(gamma), None, _p(dfx), _p(dfx16),
+                                              _p(sums), _p(ws), M, C_, _stream()), "tbns_ln_linear1_bwd")
+            _count(2)
+            S, D = sums[0], sums[1, :1]
+            w = W[0]
+            _stash_grad16(dfx, dfx16, sums[2])
+            return dfx, w * S, w * D, (gamma * S + beta * D).view_as(W), D.clone(), None, None
+        fx, gamma, W, x3, mean, rstd = ctx.saved_tensors
         C_ = fx.shape[-1]
         M = fx.numel() // C_
         Od = W.shape[0]

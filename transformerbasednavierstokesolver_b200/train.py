@@ -32,12 +32,37 @@ class FlatGradients:
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, device=self.params[0].device, dtype=torch.float32)
         off = 0
+        self.views = []
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            p.grad = self.views[-1]
             off += p.numel()
 
     def zero(self):
         self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def begin(self):
+        """start of a backward pass: detach the views so autograd hands each parameter its gradient tensor as is
+        (no `grad += new` kernel per parameter, no zero fill of the flat buffer)."""
+        for p in self.params:
+            p.grad = None
+
+    def finish(self):
+        """end of a backward pass: gather the per-parameter gradients into the flat buffer with one multi-tensor copy and
+        point p.grad back at the views (parameters that received no gradient read as zero)."""
+        src, dst = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def all_reduce(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -85,12 +110,13 @@ def train_step(model, optimizer, scheduler, grads: Optional[FlatGradients], x, f
                batched: bool = True, max_grad_norm: Optional[float] = None) -> torch.Tensor:
     """One optimizer step with exp_ns.py:191-218 semantics; returns the (local) summed step loss as a 0-d tensor."""
     if grads is not None:
-        grads.zero()
+        grads.begin()
     else:
         optimizer.zero_grad(set_to_none=True)
     loss = step_loss(model, x, fx, yy, T, step, batched)
     loss.backward()
     if grads is not None:
+        grads.finish()
         grads.all_reduce()
     if max_grad_norm is not None:
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)  # global norm, after the all-reduce
@@ -106,7 +132,7 @@ def unrolled_train_step(sol_model, optimizer, scheduler, grads: Optional[FlatGra
     bsz = x.shape[0]
     look_ahead = sol_model.n
     if grads is not None:
-        grads.zero()
+        grads.begin()
     else:
         optimizer.zero_grad(set_to_none=True)
     loss = 0
@@ -117,6 +143,7 @@ def unrolled_train_step(sol_model, optimizer, scheduler, grads: Optional[FlatGra
         fx = torch.cat((fx[..., look_ahead * step:], yy[..., t:t + look_ahead * step]), dim=-1)
     loss.backward()
     if grads is not None:
+        grads.finish()
         grads.all_reduce()
     optimizer.step()
     if scheduler is not None:
@@ -187,9 +214,10 @@ class GraphedTrainStep:
 
     def _fwd_bwd(self):
         x, fx, yy = self.static
-        self.grads.zero()
+        self.grads.begin()
         loss = step_loss(self.model, x, fx, yy, self.T, self.step_, self.batched)
         loss.backward()
+        self.grads.finish()
         return loss.detach()
 
     def load(self, batch):
