@@ -413,14 +413,14 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const long long gr = grow[k];
-    if (gr < 0) continue;   // uniform over the four threads that share a row (and exchange with each other below)
+    const bool ok = gr >= 0;   // rows past the end of the tensor: no stores, but every lane stays in the warp shuffles below
     uint32_t mine[2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = cb + 8 * j;
       float x0 = v[k >> 1][4 * j + 2 * (k & 1)] + bias[j].x, x1 = v[k >> 1][4 * j + 2 * (k & 1) + 1] + bias[j].y;
       if (p.act == 1) {
-        if (K_AUXOUT || (GEN && p.aux_out)) {
+        if (ok && (K_AUXOUT || (GEN && p.aux_out))) {
           if (p.aux_bf16) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + gr * p.ldaux + c) = __floats2bfloat162_rn(x0, x1);
           else *reinterpret_cast<float2*>(p.aux_out + gr * p.ldaux + c) = make_float2(x0, x1);
         }
@@ -440,7 +440,7 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
         x0 = __uint_as_float(u0);
         x1 = __uint_as_float(u1);
       }
-      if (K_C || (GEN && p.C)) *reinterpret_cast<float2*>(p.C + gr * p.ldc + c) = make_float2(x0, x1);
+      if (ok && (K_C || (GEN && p.C))) *reinterpret_cast<float2*>(p.C + gr * p.ldc + c) = make_float2(x0, x1);
       if (K_C16 || (GEN && p.C16)) {
         // bf16 pairs are only 4 bytes: trade pairs with the neighbouring lane so that every thread owns 4 consecutive columns
         // (8 bytes) of column group j or j+1 and four threads fill one 32-byte sector of the row
@@ -453,7 +453,7 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
           o.x = even ? mine[0] : got;
           o.y = even ? got : mine[1];
           const int cc = even ? (c - 8) : (c - 2);   // even: group j-1 columns 2a..2a+3 ; odd: group j columns 2a-2..2a+1
-          *reinterpret_cast<uint2*>(p.C16 + gr * p.ldc16 + cc) = o;
+          if (ok) *reinterpret_cast<uint2*>(p.C16 + gr * p.ldc16 + cc) = o;
         }
       }
     }

@@ -32,15 +32,18 @@ __device__ __forceinline__ void st_scatter_col(uint8_t* tile, uint32_t panel_str
   for (int r = 0; r < ROWS; ++r) *reinterpret_cast<float*>(p + sw128_off(r, c)) = v[r];
 }
 
+// Shared memory is what limits residency here (each chunk is a chain of short dependent phases, so the SM wants many CTAs
+// in flight): 53 KB per CTA for G = 32, i.e. four CTAs per SM.
 template <int G>
 struct StFwdSmem {
-  static constexpr int XS = 0;                        // X tile [128 tokens][32] fp32 (TMA, SW128)
-  static constexpr int FS = XS + ST_TILE;             // F tile
-  static constexpr int FT = FS + ST_TILE;             // F^T: 4 panels x [32 d][32 tokens]; the MMA has M = 128 rows, rows >= 32 are
-                                                      // don't-care but must stay addressable: + 12 KB tail
-  static constexpr int WT = FT + 4 * ST_TP + 12288;   // w^T: 4 panels x [G][32 tokens]
-  static constexpr int WS = WT + 4 * G * 128;         // Ws [G][32] K-major
-  static constexpr int BAR = WS + G * 128;            // 2 mbarriers + tmem slot
+  static constexpr int FT = 0;                        // F^T: 4 panels x [32 d][32 tokens]; the MMA has M = 128 rows, so every panel
+                                                      // is read 16 KB deep: rows >= 32 are don't-care lanes of the accumulator and
+                                                      // simply alias the tiles that follow
+  static constexpr int XS = FT + 4 * ST_TP;           // X tile [128 tokens][32] fp32 (TMA, SW128)
+  static constexpr int FS = XS + ST_TILE;             // F tile; dead once F^T is written, so
+  static constexpr int WT = FS;                       // w^T (4 panels x [G][32 tokens]) is built over it
+  static constexpr int WS = WT + (4 * G * 128 > (int)ST_TILE ? 4 * G * 128 : (int)ST_TILE);   // Ws [G][32] K-major
+  static constexpr int BAR = WS + G * 128;            // mbarriers: X tile, F tile, mma ; tmem slot
   static constexpr int BS = BAR + 32;                 // bias [G]
   static constexpr int TOTAL = BS + G * 4 + 1024;
 };
@@ -57,8 +60,8 @@ __global__ void __launch_bounds__(ST_TOK) slice_fwd_tc_kernel(const __grid_const
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t bar_tma = base + S::BAR, bar_mma = bar_tma + 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR + 16);
+  const uint32_t bar_x = base + S::BAR, bar_f = bar_x + 8, bar_mma = bar_x + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR + 24);
   float* bsm = reinterpret_cast<float*>(gen + S::BS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -66,7 +69,8 @@ __global__ void __launch_bounds__(ST_TOK) slice_fwd_tc_kernel(const __grid_const
 
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXF) : "memory");
-    mbar_init(bar_tma, 1);
+    mbar_init(bar_x, 1);
+    mbar_init(bar_f, 1);
     mbar_init(bar_mma, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -89,18 +93,23 @@ __global__ void __launch_bounds__(ST_TOK) slice_fwd_tc_kernel(const __grid_const
   const float inv_tau = 1.0f / st_clamp_tau(temperature[h], clamp);
   constexpr uint32_t idesc = umma_idesc(2, G, 0, 0);   // tf32, M = 128, N = G, both operands K-major
 
-  uint32_t ph_tma = 0, ph_mma = 0;
+  uint32_t ph_mma = 0;
   float sacc = 0.f;
   int iter = 0;
+  auto issue_x = [&](int chunk) {
+    mbar_expect_tx(bar_x, ST_TILE);
+    tma_load_3d(base + S::XS, &tmXF, bar_x, h * ST_D, chunk * ST_TOK, b);
+  };
+  auto issue_f = [&](int chunk) {
+    mbar_expect_tx(bar_f, ST_TILE);
+    tma_load_3d(base + S::FS, &tmXF, bar_f, I + h * ST_D, chunk * ST_TOK, b);
+  };
+  if (tid == 0 && blockIdx.x < nchunk) issue_x(blockIdx.x);
   for (int chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x, ++iter) {
     const int n0 = chunk * ST_TOK;
-    if (tid == 0) {
-      mbar_expect_tx(bar_tma, 2 * ST_TILE);
-      tma_load_3d(base + S::XS, &tmXF, bar_tma, h * ST_D, n0, b);
-      tma_load_3d(base + S::FS, &tmXF, bar_tma, I + h * ST_D, n0, b);
-    }
-    mbar_wait(bar_tma, ph_tma);
-    ph_tma ^= 1;
+    const uint32_t ph = iter & 1;
+    if (tid == 0) issue_f(chunk);   // the F / w^T region was last read by the previous chunk's token MMA (waited for below)
+    mbar_wait(bar_x, ph);
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -108,6 +117,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_fwd_tc_kernel(const __grid_const
         umma_tf32(tmem, umma_desc_kmajor_sw128(base + S::XS + k * 32), umma_desc_kmajor_sw128(base + S::WS + k * 32), idesc, k != 0);
       umma_commit(bar_mma);
     }
+    mbar_wait(bar_f, ph);
     {
       // meanwhile: column `tid` of F^T (A operand of the token contraction)
       float f[ST_D];
@@ -118,9 +128,11 @@ __global__ void __launch_bounds__(ST_TOK) slice_fwd_tc_kernel(const __grid_const
       }
       st_scatter_col<ST_D>(gen + S::FT, ST_TP, tid, f);
     }
+    __syncthreads();   // every F row has been read: w^T may be written over the F tile
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     tc_fence_after();
+    if (tid == 0 && chunk + (int)gridDim.x < nchunk) issue_x(chunk + gridDim.x);   // the logits MMA was the X tile's only reader
     {
       float l[G];
       tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), l);
@@ -179,6 +191,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_fwd_tc_kernel(const __grid_const
     }
     mbar_wait(bar_mma, ph_mma);   // operand tiles may be overwritten by the next chunk
     ph_mma ^= 1;
+    __syncthreads();              // ... once the threads summing rows of w^T are done with it as well
   }
   tc_fence_after();
   float* pbase = part + (((long long)b * H + h) * gridDim.x + blockIdx.x) * G * (ST_D + 1);
@@ -231,18 +244,21 @@ __device__ __forceinline__ float st_rna(float x) {
 template <int G>
 struct StBwdSmem {
   static constexpr int KP = G / 32;                    // 128-byte k-panels of a K = G operand
-  static constexpr int XS = 0;                         // X tile (TMA); later k-panel 0 of the w tile
-  static constexpr int FS = XS + ST_TILE;              // F tile (TMA); later k-panel 1 of the w tile (G = 64)
-  static constexpr int DL = FS + ST_TILE;              // dL tile [128 tokens][G] K-major, KP panels
-  static constexpr int XT = DL + KP * ST_TILE;         // X^T: 4 panels x [32 d][32 tokens] (+12 KB addressable tail, M = 128 rows)
-  static constexpr int LT = XT + 4 * ST_TP + 12288;    // dL^T: 4 panels x [G][32 tokens]
+  static constexpr int XS = 0;                         // 2 stages x { X tile, F tile } (TMA); within a stage the X tile later
+  static constexpr int STAGE = 2 * ST_TILE;            // becomes k-panel 0 of the w tile and the F tile k-panel 1 (G = 64) or,
+                                                       // for G = 32, the dL tile (F is dead once the first MMA group has read it)
+  static constexpr int DL = 2 * STAGE;                 // dL tile [128 tokens][G] K-major, KP panels (own region only for G = 64)
+  static constexpr int XT = DL + (KP == 1 ? 0 : KP * (int)ST_TILE);   // X^T: 4 panels x [32 d][32 tokens]; M = 128 rows are read:
+                                                       // the don't-care 12 KB tail aliases dL^T
+  static constexpr int LT = XT + 4 * ST_TP;            // dL^T: 4 panels x [G][32 tokens]
   static constexpr int WS = LT + 4 * G * 128;          // Ws   [G][32]   K-major (B of the logits)
   static constexpr int DT = WS + G * 128;              // dTt  [G][32]   K-major (B of dwv)
   static constexpr int WST = DT + G * 128;             // Ws^T [32][G]   K-major, KP panels of [32][128 B] (B of dX)
   static constexpr int DTT = WST + KP * 4096;          // dTt^T[32][G]   (B of dF)
-  static constexpr int BAR = DTT + KP * 4096;
+  static constexpr int BAR = DTT + KP * 4096;          // mbarriers: tma[2], mma ; tmem slot
   static constexpr int MISC = BAR + 32;                // bias [G], ds [G], red[4]
-  static constexpr int TOTAL = MISC + (2 * G + 8) * 4 + 1024;
+  static constexpr int TOTAL = MISC + (2 * G + 8) * 4; // no alignment slack: the kernel declares its dynamic smem 1024-aligned
+                                                       // (G = 32: 115 016 B, two CTAs per SM)
 };
 
 // grid (groups, H, B), block 128
@@ -257,12 +273,12 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
   constexpr int KP = S::KP;
   constexpr int TMEM_COLS = 256;                 // L [G] | dwv [G] | dF [32] | dX [32] | dWs^T [G]
   constexpr uint32_t C_L = 0, C_DW = G, C_DF = 2 * G, C_DX = 2 * G + 32, C_WS = 2 * G + 64;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t bar_tma = base + S::BAR, bar_mma = bar_tma + 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR + 16);
+  extern __shared__ __align__(1024) uint8_t smem_al[];   // SW128 tiles need 1024-byte aligned bases
+  const uint32_t base = smem_u32(smem_al);
+  if (base & 1023u) __trap();
+  uint8_t* gen = smem_al;
+  const uint32_t bar_tma = base + S::BAR, bar_mma = bar_tma + 16;   // bar_tma: one per stage
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR + 24);
   float* bsm = reinterpret_cast<float*>(gen + S::MISC);
   float* dss = bsm + G;
   float* red = dss + G;
@@ -274,6 +290,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXF) : "memory");
     mbar_init(bar_tma, 1);
+    mbar_init(bar_tma + 8, 1);
     mbar_init(bar_mma, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -314,18 +331,27 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
   constexpr uint32_t idesc_g = umma_idesc(2, G, 0, 0);    // N = G
   constexpr uint32_t idesc_d = umma_idesc(2, 32, 0, 0);   // N = dim_head
 
-  uint32_t ph_tma = 0, ph_mma = 0;
+  uint32_t ph_mma = 0;
   float dbs_acc = 0.f, dtau_acc = 0.f;
   int iter = 0;
+  // two-stage TMA ring: the X / F tiles of this CTA's next chunk are in flight while the current chunk is processed
+  auto issue = [&](int chunk, int stage) {
+    const uint32_t bar = bar_tma + stage * 8, dst = base + S::XS + stage * S::STAGE;
+    mbar_expect_tx(bar, 2 * ST_TILE);
+    tma_load_3d(dst, &tmXF, bar, h * ST_D, chunk * ST_TOK, b);
+    tma_load_3d(dst + ST_TILE, &tmXF, bar, I + h * ST_D, chunk * ST_TOK, b);
+  };
+  if (tid == 0 && blockIdx.x < nchunk) issue(blockIdx.x, 0);
   for (int chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x, ++iter) {
     const int n0 = chunk * ST_TOK;
     const bool valid = n0 + tid < N;
     const long long row = (long long)b * N + n0 + tid;
-    if (tid == 0) {
-      mbar_expect_tx(bar_tma, 2 * ST_TILE);
-      tma_load_3d(base + S::XS, &tmXF, bar_tma, h * ST_D, n0, b);
-      tma_load_3d(base + S::FS, &tmXF, bar_tma, I + h * ST_D, n0, b);
-    }
+    const int stage = iter & 1;
+    const uint32_t xs = S::XS + stage * S::STAGE, fs = xs + ST_TILE;
+    const uint32_t dl = KP == 1 ? fs : (uint32_t)S::DL;
+    // the other stage's tiles (and the w / dL tiles written over them) were last read by the MMAs of the previous
+    // iteration, which were waited for before its closing barrier
+    if (tid == 0 && chunk + (int)gridDim.x < nchunk) issue(chunk + gridDim.x, stage ^ 1);
     // this token's deslice gradient row (issued early: overlaps the TMA / MMA latency)
     float dwv[G];
     if (valid) {
@@ -345,16 +371,15 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
 #pragma unroll
       for (int g = 0; g < G; ++g) dwv[g] = 0.f;
     }
-    mbar_wait(bar_tma, ph_tma);
-    ph_tma ^= 1;
+    mbar_wait(bar_tma + stage * 8, (iter >> 1) & 1);
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k)   // L = X Ws^T
-        umma_tf32(tmem + C_L, umma_desc_kmajor_sw128(base + S::XS + k * 32), umma_desc_kmajor_sw128(base + S::WS + k * 32), idesc_g, k != 0);
+        umma_tf32(tmem + C_L, umma_desc_kmajor_sw128(base + xs + k * 32), umma_desc_kmajor_sw128(base + S::WS + k * 32), idesc_g, k != 0);
 #pragma unroll
       for (int k = 0; k < 4; ++k)   // F dTt^T
-        umma_tf32(tmem + C_DW, umma_desc_kmajor_sw128(base + S::FS + k * 32), umma_desc_kmajor_sw128(base + S::DT + k * 32), idesc_g, k != 0);
+        umma_tf32(tmem + C_DW, umma_desc_kmajor_sw128(base + fs + k * 32), umma_desc_kmajor_sw128(base + S::DT + k * 32), idesc_g, k != 0);
       umma_commit(bar_mma);
     }
     {
@@ -362,7 +387,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
       float x[ST_D];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(gen + S::XS + sw128_off(tid, c));
+        const float4 v = *reinterpret_cast<const float4*>(gen + xs + sw128_off(tid, c));
         x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
       }
       st_scatter_col<ST_D>(gen + S::XT, ST_TP, tid, x);
@@ -409,9 +434,9 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
       // dL row -> K-major A operand of dX = dL Ws; dL column -> dL^T (B operand of dWs^T += X^T dL)
 #pragma unroll
       for (int c = 0; c < G / 4; ++c) {
-        *reinterpret_cast<float4*>(gen + S::XS + (c >> 3) * ST_TILE + sw128_off(tid, c & 7)) =
+        *reinterpret_cast<float4*>(gen + xs + (c >> 3) * ST_TILE + sw128_off(tid, c & 7)) =
             make_float4(L[4 * c], L[4 * c + 1], L[4 * c + 2], L[4 * c + 3]);
-        *reinterpret_cast<float4*>(gen + S::DL + (c >> 3) * ST_TILE + sw128_off(tid, c & 7)) =
+        *reinterpret_cast<float4*>(gen + dl + (c >> 3) * ST_TILE + sw128_off(tid, c & 7)) =
             make_float4(dwv[4 * c], dwv[4 * c + 1], dwv[4 * c + 2], dwv[4 * c + 3]);
       }
       st_scatter_col<G>(gen + S::LT, G * 128, tid, dwv);
@@ -424,8 +449,8 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
 #pragma unroll
       for (int k = 0; k < G / 8; ++k) {   // dF = w dTt ; dX = dL Ws   (K = G)
         const uint32_t ko = (k >> 2) * ST_TILE + (k & 3) * 32, kb = (k >> 2) * 4096 + (k & 3) * 32;
-        umma_tf32(tmem + C_DF, umma_desc_kmajor_sw128(base + S::XS + ko), umma_desc_kmajor_sw128(base + S::DTT + kb), idesc_d, k != 0);
-        umma_tf32(tmem + C_DX, umma_desc_kmajor_sw128(base + S::DL + ko), umma_desc_kmajor_sw128(base + S::WST + kb), idesc_d, k != 0);
+        umma_tf32(tmem + C_DF, umma_desc_kmajor_sw128(base + xs + ko), umma_desc_kmajor_sw128(base + S::DTT + kb), idesc_d, k != 0);
+        umma_tf32(tmem + C_DX, umma_desc_kmajor_sw128(base + dl + ko), umma_desc_kmajor_sw128(base + S::WST + kb), idesc_d, k != 0);
       }
 #pragma unroll
       for (int kp = 0; kp < 4; ++kp)     // dWs^T[d][g] += sum_t X^T[d][t] dL^T[g][t]

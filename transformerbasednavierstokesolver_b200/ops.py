@@ -11,6 +11,7 @@ No CPU path exists: non-CUDA inputs raise.
 from __future__ import annotations
 
 import ctypes as ct
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -146,35 +147,35 @@ def cast_bf16(t: torch.Tensor) -> torch.Tensor:
 _W16_CACHE = {}
 
 
-def weight_bf16(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
-    """bf16 (optionally transposed) copy of a weight matrix as a K-major tensor-core operand, cached until the fp32 master
-    changes (optimizer step / load_state_dict bump `_version`)."""
-    key = (W.data_ptr(), transpose)
+def _w16_cached(W: torch.Tensor, key_extra, build) -> torch.Tensor:
+    """bf16 operand copies of weights, cached per tensor OBJECT (weak reference: a recycled address or id never matches)
+    until the fp32 master changes (optimizer step / load_state_dict bump `_version`)."""
+    key = (id(W),) + key_extra
     hit = _W16_CACHE.get(key)
-    if hit is not None and hit[0] == W._version and hit[1].shape == ((W.shape[1], W.shape[0]) if transpose else W.shape):
-        return hit[1]
+    if hit is not None and hit[0]() is W and hit[1] == W._version and hit[2] == W.data_ptr():
+        return hit[3]
     with torch.no_grad():
-        src = W.detach().t().contiguous() if transpose else W.detach().contiguous()
-        w16 = cast_bf16(src)
+        w16 = build()
     if len(_W16_CACHE) > 4096:
         _W16_CACHE.clear()
-    _W16_CACHE[key] = (W._version, w16)
+    _W16_CACHE[key] = (weakref.ref(W), W._version, W.data_ptr(), w16)
     return w16
+
+
+def weight_bf16(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """bf16 (optionally transposed) copy of a weight matrix as a K-major tensor-core operand."""
+    return _w16_cached(W, (transpose, 0),
+                       lambda: cast_bf16(W.detach().t().contiguous() if transpose else W.detach().contiguous()))
 
 
 def weight_bf16_padded(W: torch.Tensor, Kp: int, transpose: bool = False) -> torch.Tensor:
     """like weight_bf16 for a weight [R, K] whose K is zero-padded to Kp (tensor-core contractions take K in units of 64):
     [R, Kp] or, transposed, [Kp, R]."""
-    key = (W.data_ptr(), transpose, Kp)
-    hit = _W16_CACHE.get(key)
-    if hit is not None and hit[0] == W._version:
-        return hit[1]
-    with torch.no_grad():
+    def build():
         wp = torch.zeros(W.shape[0], Kp, device=W.device, dtype=torch.float32)
         wp[:, :W.shape[1]] = W.detach()
-        w16 = cast_bf16(wp.t().contiguous() if transpose else wp)
-    _W16_CACHE[key] = (W._version, w16)
-    return w16
+        return cast_bf16(wp.t().contiguous() if transpose else wp)
+    return _w16_cached(W, (transpose, Kp), build)
 
 
 def tc_supported(Cin: int, N: int, taps: int) -> bool:
