@@ -122,7 +122,7 @@ def test_gemm_bf16_mode_rounds_operands(dev):
 # ------------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,C", [(1000, 256), (37, 64), (5, 30), (4096, 128)])
+@pytest.mark.parametrize("rows,C", [(1000, 256), (37, 64), (5, 30), (4096, 128), (1001, 256), (77, 512), (1, 128)])
 def test_layernorm(dev, rows, C):
     ops = _ops()
     g = torch.Generator().manual_seed(rows + C)

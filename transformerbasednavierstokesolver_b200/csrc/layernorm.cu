@@ -74,6 +74,68 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const floa
   }
 }
 
+// Register-resident forward for C = 128*NV: each warp keeps a whole row in registers (one HBM read, no re-reads through L1)
+// and works on TWO rows per iteration so that 2*NV independent 16-byte loads are in flight per lane.
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta, float* __restrict__ y,
+                                                                        __nv_bfloat16* __restrict__ y16, float* __restrict__ mean,
+                                                                        float* __restrict__ rstd, int rows, float eps) {
+  constexpr int C = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 g4[NV], b4[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    g4[k] = *reinterpret_cast<const float4*>(gamma + lane * 4 + k * 128);
+    b4[k] = *reinterpret_cast<const float4*>(beta + lane * 4 + k * 128);
+  }
+  const float invC = 1.f / (float)C;
+  const int stride = gridDim.x * LN_WARPS * 2;
+  for (int row0 = (blockIdx.x * LN_WARPS + warp) * 2; row0 < rows; row0 += stride) {
+    float4 v[2][NV];
+    const bool has2 = row0 + 1 < rows;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        v[r][k] = (r == 0 || has2) ? *reinterpret_cast<const float4*>(x + (long long)(row0 + r) * C + lane * 4 + k * 128)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r == 1 && !has2) break;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) s += (v[r][k].x + v[r][k].y) + (v[r][k].z + v[r][k].w);
+      const float mu = warp_sum(s) * invC;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const float a = v[r][k].x - mu, b = v[r][k].y - mu, c = v[r][k].z - mu, d = v[r][k].w - mu;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+      const float rs = rsqrtf(warp_sum(q) * invC + eps);
+      const long long off = (long long)(row0 + r) * C + lane * 4;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float4 o;
+        o.x = (v[r][k].x - mu) * rs * g4[k].x + b4[k].x;
+        o.y = (v[r][k].y - mu) * rs * g4[k].y + b4[k].y;
+        o.z = (v[r][k].z - mu) * rs * g4[k].z + b4[k].z;
+        o.w = (v[r][k].w - mu) * rs * g4[k].w + b4[k].w;
+        if (y) *reinterpret_cast<float4*>(y + off + k * 128) = o;
+        if (y16) {
+          __nv_bfloat162 h2[2] = {__floats2bfloat162_rn(o.x, o.y), __floats2bfloat162_rn(o.z, o.w)};
+          *reinterpret_cast<uint2*>(y16 + off + k * 128) = *reinterpret_cast<uint2*>(h2);
+        }
+      }
+      if (lane == 0) {
+        mean[row0 + r] = mu;
+        rstd[row0 + r] = rs;
+      }
+    }
+  }
+}
+
 // dx = (g - mean(g) - xhat*mean(g*xhat)) * rstd (+ dres), g = dy*gamma.  Per-CTA partial dgamma/dbeta -> part[cta][2][C].
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -330,6 +392,19 @@ extern "C" int tbns_layernorm_fwd(const float* x, const float* gamma, const floa
   TBNS_REQUIRE(x && gamma && beta && (y || y16) && mean && rstd, "tbns_layernorm_fwd: null pointer");
   TBNS_REQUIRE(rows >= 0 && C > 0, "tbns_layernorm_fwd: bad dims");
   if (rows == 0) return TBNS_OK;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                         reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(y16)) & 15) == 0;
+  if (aligned && (C == 128 || C == 256 || C == 512)) {
+    int ctas = cdiv(rows, LN_WARPS * 2);
+    if (ctas > 148 * 8) ctas = 148 * 8;   // 8 CTAs of 8 warps per SM, grid-stride over row pairs
+    __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(y16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 128) layernorm_fwd_reg_kernel<1><<<ctas, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, o16, mean, rstd, rows, eps);
+    else if (C == 256) layernorm_fwd_reg_kernel<2><<<ctas, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, o16, mean, rstd, rows, eps);
+    else layernorm_fwd_reg_kernel<4><<<ctas, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, o16, mean, rstd, rows, eps);
+    TBNS_LAUNCH_CHECK();
+    return TBNS_OK;
+  }
   layernorm_fwd_kernel<<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, reinterpret_cast<__nv_bfloat16*>(y16), mean, rstd, rows, C, eps);
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;

@@ -56,7 +56,13 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
   const float* pin = part + bh * nchunk * G * (D + 1);
   for (int o = tid; o < G * (D + 1); o += nt) {
     float acc = 0.f;
-    for (int c = 0; c < nchunk; ++c) acc += pin[(long long)c * G * (D + 1) + o];
+    int c = 0;
+    for (; c + 3 < nchunk; c += 4) {   // four independent loads in flight, same (ascending) summation order
+      const float p0 = pin[(long long)c * G * (D + 1) + o], p1 = pin[(long long)(c + 1) * G * (D + 1) + o];
+      const float p2 = pin[(long long)(c + 2) * G * (D + 1) + o], p3 = pin[(long long)(c + 3) * G * (D + 1) + o];
+      acc += p0; acc += p1; acc += p2; acc += p3;
+    }
+    for (; c < nchunk; ++c) acc += pin[(long long)c * G * (D + 1) + o];
     const int g = o / (D + 1), dd = o - g * (D + 1);
     if (dd == D) {
       ssum[g] = acc;
@@ -234,6 +240,20 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_bwd_kernel(const flo
       const float* w = Wo + h * D + dd;          // stride I per output channel c
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       int c = 0;
+      // to_out.weight comes from L2 (~0.5 us per dependent round trip): keep 16 loads in flight per thread
+      for (; c + 15 < Cout; c += 16, w += 16 * (long long)I) {
+        float wv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) wv[j] = __ldg(w + j * (long long)I);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 av = *reinterpret_cast<const float4*>(a + c + j);
+          a0 = fmaf(av.x, wv[j], a0);
+          a1 = fmaf(av.y, wv[j + 1], a1);
+          a2 = fmaf(av.z, wv[j + 2], a2);
+          a3 = fmaf(av.w, wv[j + 3], a3);
+        }
+      }
       for (; c + 3 < Cout; c += 4, w += 4 * (long long)I) {
         const float4 av = *reinterpret_cast<const float4*>(a + c);
         a0 = fmaf(av.x, __ldg(w), a0);

@@ -11,6 +11,7 @@ No CPU path exists: non-CUDA inputs raise.
 from __future__ import annotations
 
 import ctypes as ct
+import os
 import weakref
 from typing import Optional, Tuple
 
@@ -279,16 +280,67 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, want16: bool = False, wan
     return dx, dx16, dg, db
 
 
+# ------------------------------------------------------------------------------------------------
+# Weight-gradient work (token-contraction GEMMs, their split-K reductions, bias column sums, the small deterministic
+# reductions) is off the critical path of backward: it is issued on a side stream, forked after its inputs are ready and
+# joined before the autograd Function returns, so it fills the SMs that the latency-bound kernels of the data-gradient
+# chain leave idle.  Under CUDA-graph capture the fork/join become parallel branches of the graph.
+# Discipline: tensors read by side-stream kernels stay referenced until _join_side(); tensors allocated while the side
+# stream is current belong to its allocator pool.  TBNS_SIDE_STREAM=0 runs everything in order on one stream.
+# ------------------------------------------------------------------------------------------------
+_SIDE_STREAMS = {}
+_USE_SIDE = os.environ.get("TBNS_SIDE_STREAM", "1") != "0"
+
+
+def _side():
+    dev = torch.cuda.current_device()
+    s = _SIDE_STREAMS.get(dev)
+    if s is None:
+        s = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
+class _OnSide:
+    """launches inside the block go to the side stream, ordered after everything issued so far on the current stream"""
+
+    def __enter__(self):
+        self.ctx = None
+        if _USE_SIDE:
+            side = _side()
+            side.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def _join_side():
+    if _USE_SIDE:
+        torch.cuda.current_stream().wait_stream(_side())
+
+
 # bf16 copies of gradients handed from one fused backward stage to the next (producer: LayerNorm backward, consumer: the
 # tensor-core contractions of the stage autograd runs next on the very same tensor).  Keyed by storage address.
 _GRAD16 = {}
 
 
-def _stash_grad16(t: torch.Tensor, t16: Optional[torch.Tensor], colsum_: Optional[torch.Tensor] = None):
+def _stash_grad16(t: torch.Tensor, t16: Optional[torch.Tensor] = None, colsum_: Optional[torch.Tensor] = None):
+    """Every fused backward stage calls this on the gradient it returns: with side products to hand them on, without to drop
+    whatever an older tensor left under the same storage address."""
     if t16 is not None or colsum_ is not None:
-        if len(_GRAD16) > 64:
-            _GRAD16.clear()
         _GRAD16[t.data_ptr()] = (t16, tuple(t.shape), t._version, colsum_)
+    else:
+        _GRAD16.pop(t.data_ptr(), None)
+
+
+def _begin_forward():
+    """side products only live within one backward pass: any forward call ends the previous one"""
+    if _GRAD16:
+        _GRAD16.clear()
 
 
 def _take_grad16(t: torch.Tensor):
@@ -302,6 +354,7 @@ def _take_grad16(t: torch.Tensor):
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):
+        _begin_forward()
         x = x.contiguous()
         y, _, mean, rstd = layernorm_fwd(x, gamma.contiguous(), beta.contiguous(), eps)
         ctx.save_for_backward(x, mean, rstd, gamma)
@@ -311,6 +364,7 @@ class LayerNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, mean, rstd, gamma = ctx.saved_tensors
         dx, _, dg, db = layernorm_bwd(dy.contiguous(), x, mean, rstd, gamma.contiguous())
+        _stash_grad16(dx)
         return dx, dg, db, None
 
 
@@ -466,8 +520,9 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
       check(lib.tbns_pa_token_attn_bwd(_p(dP), _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(tok), _p(q), _p(k), _p(v), _p(A), _p(O),
                                      _p(dTt), _p(ds), _p(dWqkv_part), _p(dWo_part), B, H, D, G, Cout, st), "tbns_pa_token_attn_bwd")
     _count(3)  # token_attn_bwd, slice_bwd, dtau_finish
-    dWqkv = reduce_rows(dWqkv_part, B * H, 3 * D * D).view(3, D, D)
-    dWo = reduce_rows(dWo_part, B, Cout * I).view(Cout, I)
+    with _OnSide():
+        dWqkv = reduce_rows(dWqkv_part, B * H, 3 * D * D).view(3, D, D)
+        dWo = reduce_rows(dWo_part, B, Cout * I).view(Cout, I)
     # (1') slice backward (+ bias gradients of the projections)
     dXF = None if tc else torch.empty(B * N, I2, **f32)
     dXF16 = torch.empty(B * N, I2, device=dev, dtype=torch.bfloat16) if tc else None
@@ -477,10 +532,11 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
         with _Timed("slice_bwd"):
             check(lib.tbns_pa_slice_bwd_tc(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw16), _p(dTt), _p(ds), _p(dXF16), _p(dWs_part),
                                            _p(dtau_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd_tc")
-        # projection-bias gradients from token-reduced quantities: db_x = (sum_t dL).Ws, db_fx = (sum_t w).dTt
-        dbs_bh = dWs_part.view(B, H, groups, G, D + 1)[..., D].sum(2)
-        dbx = (dbs_bh.sum(0) @ Ws).reshape(I)
-        dbfx = torch.einsum("bhg,bhgd->hd", s, dTt).reshape(I)
+        with _OnSide():
+            # projection-bias gradients from token-reduced quantities: db_x = (sum_t dL).Ws, db_fx = (sum_t w).dTt
+            dbs_bh = dWs_part.view(B, H, groups, G, D + 1)[..., D].sum(2)
+            dbx = (dbs_bh.sum(0) @ Ws).reshape(I)
+            dbfx = torch.einsum("bhg,bhgd->hd", s, dTt).reshape(I)
     else:
         dbcat_part = torch.empty(B * groups, H * 2 * D, **f32)
         with _Timed("slice_bwd"):
@@ -489,18 +545,26 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
                   "tbns_pa_slice_bwd")
         dbc = reduce_rows(dbcat_part, B * groups, H * 2 * D).view(H, 2, D)
         dbx, dbfx = dbc[:, 0, :].reshape(I), dbc[:, 1, :].reshape(I)
-    dWsb = reduce_rows(dWs_part, B * H * groups, G * (D + 1)).view(G, D + 1)
-    dWs, dbs = dWsb[:, :D].contiguous(), dWsb[:, D].contiguous()
-    dtemp = torch.empty(H, **f32)
-    check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, groups, int(structured), st), "tbns_pa_dtau_finish")
+    with _OnSide():
+        dWsb = reduce_rows(dWs_part, B * H * groups, G * (D + 1)).view(G, D + 1)
+        dWs, dbs = dWsb[:, :D].contiguous(), dWsb[:, D].contiguous()
+        dtemp = torch.empty(H, **f32)
+        check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, groups, int(structured), _stream()),
+              "tbns_pa_dtau_finish")
     # (1a') projections: dgrad, wgrad (scattered straight into Conv2d / Linear weight layout)
     dx = torch.empty(B, N, C_, **f32)
+    if tc:
+        with _OnSide():
+            dWx = torch.empty(Wx_shape, **f32)
+            dWfx = torch.empty(Wx_shape, **f32)
+            gemm_tc_wgrad(xs, dXF16, B, Hg, Wg, C_, I2, taps=taps, scatter=(dWx, dWfx), I=I, tag="proj_wgrad")
+        gemm_tc(dXF16, Wd16, dx, None, B, Hg, Wg, I2, C_, taps, 1, tag="proj_dgrad")
+        keep = (dXF16, xs, dWs_part, dtau_part, dWqkv_part, dWo_part, dTt, s, dw16, dP)
+        return dx, dict(temperature=dtemp.view(1, H, 1, 1), Wx=dWx, bx=dbx, Wfx=dWfx, bfx=dbfx, Ws=dWs, bs=dbs,
+                        Wq=dWqkv[0], Wk=dWqkv[1], Wv=dWqkv[2], Wo=dWo, bo=dbo, _keep=keep)
     dWx = torch.empty(Wx_shape, **f32)
     dWfx = torch.empty(Wx_shape, **f32)
-    if tc:
-        gemm_tc(dXF16, Wd16, dx, None, B, Hg, Wg, I2, C_, taps, 1, tag="proj_dgrad")
-        gemm_tc_wgrad(xs, dXF16, B, Hg, Wg, C_, I2, taps=taps, scatter=(dWx, dWfx), I=I, tag="proj_wgrad")
-    elif structured:
+    if structured:
         gemm(M=B * N, N=C_, K=9 * I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=dx, ldc=C_, conv_mode=1, Hg=Hg, Wg=Wg,
              Cin=I2, flip=1, precision=precision, tag="proj_dgrad")
         gemm(M=9 * C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, conv_mode=2, Hg=Hg, Wg=Wg, Cin=C_,
@@ -510,8 +574,9 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
              tag="proj_dgrad")
         gemm(M=C_, N=I2, K=B * N, A=x, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, Cin=C_, precision=precision,
              split_k=_split_k(C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=1, tag="proj_wgrad")
+    keep = (dXF, dWs_part, dtau_part, dWqkv_part, dWo_part, dTt, s, dw, dP)   # read by side-stream launches: alive until the join
     return dx, dict(temperature=dtemp.view(1, H, 1, 1), Wx=dWx, bx=dbx, Wfx=dWfx, bfx=dbfx, Ws=dWs, bs=dbs,
-                    Wq=dWqkv[0], Wk=dWqkv[1], Wv=dWqkv[2], Wo=dWo, bo=dbo)
+                    Wq=dWqkv[0], Wk=dWqkv[1], Wv=dWqkv[2], Wo=dWo, bo=dbo, _keep=keep)
 
 
 class PhysicsAttentionFn(torch.autograd.Function):
@@ -520,6 +585,7 @@ class PhysicsAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, residual, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, packed, heads, grid, precision):
+        _begin_forward()
         x = x.contiguous()
         if residual is not None:
             residual = residual.contiguous()
@@ -540,6 +606,9 @@ class PhysicsAttentionFn(torch.autograd.Function):
         dout = dout.contiguous()
         dx, g = pa_backward(dout, xshape, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
                             Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16)
+        _join_side()
+        g.pop("_keep", None)
+        _stash_grad16(dx)
         return (dx, dout if has_res else None, g["temperature"], g["Wx"], g["bx"], g["Wfx"], g["bfx"], g["Ws"], g["bs"], g["Wq"],
                 g["Wk"], g["Wv"], g["Wo"], g["bo"], None, None, None, None)
 
@@ -551,6 +620,7 @@ class AttnBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, fx, ln_w, ln_b, eps, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, packed, heads, grid, precision):
+        _begin_forward()
         fx = fx.contiguous()
         Wf, Wd, bcat, Wf16, Wd16 = packed
         ln_w, ln_b = ln_w.contiguous(), ln_b.contiguous()
@@ -578,6 +648,8 @@ class AttnBlockFn(torch.autograd.Function):
                              dbo=dsum)
         dfx, dfx16, dlw, dlb, dfsum = layernorm_bwd(dx1, fx, mean, rstd, ln_w, dres=dout, want16=precision == TBNS_PREC_BF16,
                                                     want_sum=True)
+        _join_side()                        # weight-gradient work of pa_backward overlapped the LayerNorm backward above
+        g.pop("_keep", None)
         _stash_grad16(dfx, dfx16, dfsum)   # column sums of dfx = to-be bias gradient of the previous block's mlp.linear_post
         return (dfx, dlw, dlb, None, g["temperature"], g["Wx"], g["bx"], g["Wfx"], g["bfx"], g["Ws"], g["bs"], g["Wq"], g["Wk"],
                 g["Wv"], g["Wo"], g["bo"], None, None, None, None)
@@ -589,6 +661,7 @@ class AttnBlockFn(torch.autograd.Function):
 class LnMlpFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, fx, gamma, beta, W1, b1, W2, b2, eps, precision):
+        _begin_forward()
         fx = fx.contiguous()
         gamma, beta, W1, b1, W2, b2 = (t.contiguous() for t in (gamma, beta, W1, b1, W2, b2))
         _chk(fx, gamma, beta, W1, b1, W2, b2)
@@ -638,16 +711,19 @@ class LnMlpFn(torch.autograd.Function):
         if hid.dtype == torch.bfloat16:   # tensor-core mode
             if dout16 is None:
                 dout16 = cast_bf16(dout)
-            gemm_tc_wgrad(dout16, hid, 1, 1, M, Cout, R, C=dW2, tag="mlp_dW2")
+            W2t16, W1t16 = weight_bf16(W2, transpose=True), weight_bf16(W1, transpose=True)
+            with _OnSide():
+                gemm_tc_wgrad(dout16, hid, 1, 1, M, Cout, R, C=dW2, tag="mlp_dW2")
             dpre16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
-            gemm_tc(dout16, weight_bf16(W2, transpose=True), None, None, 1, 1, M, Cout, R, act=2, aux_in=pre, aux_bf16=1, C16=dpre16,
-                    tag="mlp_dpre")
-            db1 = colsum_bf16(dpre16, M, R)
-            dW1 = torch.empty(R, C_, **f32)
-            gemm_tc_wgrad(dpre16, x2, 1, 1, M, R, C_, C=dW1, tag="mlp_dW1")
+            gemm_tc(dout16, W2t16, None, None, 1, 1, M, Cout, R, act=2, aux_in=pre, aux_bf16=1, C16=dpre16, tag="mlp_dpre")
+            with _OnSide():
+                db1 = colsum_bf16(dpre16, M, R)
+                dW1 = torch.empty(R, C_, **f32)
+                gemm_tc_wgrad(dpre16, x2, 1, 1, M, R, C_, C=dW1, tag="mlp_dW1")
             dx2 = torch.empty(M, C_, **f32)
-            gemm_tc(dpre16, weight_bf16(W1, transpose=True), dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
+            gemm_tc(dpre16, W1t16, dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
             dfx, dfx16, dg, db, dfsum = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout, want16=True, want_sum=True)
+            _join_side()
             dfx = dfx.view_as(fx)
             _stash_grad16(dfx, dfx16, dfsum)   # the attention stage's backward consumes dfx next: bf16 copy + to_out bias gradient
             return dfx, dg, db, dW1, db1, dW2, db2, None, None
@@ -663,7 +739,9 @@ class LnMlpFn(torch.autograd.Function):
         dx2 = torch.empty(M, C_, **f32)
         gemm(M=M, N=C_, K=R, A=dpre, lda=R, a_kind=0, B=W1, ldb=C_, b_kind=1, C=dx2, ldc=C_, precision=precision)
         dfx, _, dg, db = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout)  # + residual branch
-        return dfx.view_as(fx), dg, db, dW1, db1, dW2, db2, None, None
+        dfx = dfx.view_as(fx)
+        _stash_grad16(dfx)
+        return dfx, dg, db, dW1, db1, dW2, db2, None, None
 
 
 def mlp_tc_ok(K: int, R: int, Cout: int) -> bool:
@@ -679,6 +757,7 @@ class MlpFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, inp, W1, b1, W2, b2):
+        _begin_forward()
         K = inp.shape[-1]
         M = inp.numel() // K
         R, Cout = W1.shape[0], W2.shape[0]
@@ -732,6 +811,7 @@ class LnLinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, fx, gamma, beta, W, b, eps, precision):
+        _begin_forward()
         fx = fx.contiguous()
         gamma, beta, W, b = (t.contiguous() for t in (gamma, beta, W, b))
         _chk(fx, gamma, beta, W, b)
