@@ -233,36 +233,67 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_bwd_kernel(const flo
     for (int o = tid; o < G * Cout; o += nt) dPs[o] = dPh[o];
     for (int o = tid; o < GD; o += nt) Os[o] = Oh[o];
     __syncthreads();
-    // dO[g,d] = sum_c dP[g,c] Wo[c,h*D+d]
-    for (int o = tid; o < GD; o += nt) {
-      const int g = o / D, dd = o - g * D;
-      const float* a = dPs + g * Cout;
-      const float* w = Wo + h * D + dd;          // stride I per output channel c
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int c = 0;
-      // to_out.weight comes from L2 (~0.5 us per dependent round trip): keep 16 loads in flight per thread
-      for (; c + 15 < Cout; c += 16, w += 16 * (long long)I) {
-        float wv[16];
+    // dO[g,d] = sum_c dP[g,c] Wo[c,h*D+d].  The head's slice of to_out.weight streams through a double-buffered window of
+    // 32 output channels in shared memory: every 128-byte line is fetched from L2 once per CTA (not once per warp - with
+    // 20 batches x 32 warps hammering the same 32 KB per head that was an L2-bandwidth bound of ~50 us), and the loads of
+    // window k+1 are in flight while window k is consumed.
+    {
+      constexpr int CH = 32;
+      float* Wc = Os + GD;   // [2][CH][D]
+      const int per = CH * D;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float pre[2];
+      const int nck = (Cout + CH - 1) / CH;
+      auto fetch = [&](int ck) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) wv[j] = __ldg(w + j * (long long)I);
+        for (int r = 0; r < 2; ++r) {
+          const int idx = tid + r * nt;
+          const int c = ck * CH + idx / D;
+          pre[r] = (idx < per && c < Cout) ? __ldg(Wo + (long long)c * I + h * D + (idx % D)) : 0.f;
+        }
+      };
+      auto commit = [&](int buf) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 av = *reinterpret_cast<const float4*>(a + c + j);
-          a0 = fmaf(av.x, wv[j], a0);
-          a1 = fmaf(av.y, wv[j + 1], a1);
-          a2 = fmaf(av.z, wv[j + 2], a2);
-          a3 = fmaf(av.w, wv[j + 3], a3);
+        for (int r = 0; r < 2; ++r) {
+          const int idx = tid + r * nt;
+          if (idx < per) Wc[buf * per + idx] = pre[r];
+        }
+      };
+      fetch(0);
+      commit(0);
+      __syncthreads();
+      for (int ck = 0; ck < nck; ++ck) {
+        if (ck + 1 < nck) fetch(ck + 1);
+        const float* wc = Wc + (ck & 1) * per;
+        const int c0 = ck * CH;
+        const int cn = min(CH, Cout - c0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int o = tid + r * nt;
+          if (o < GD) {
+            const int g = o / D, dd = o - g * D;
+            const float* a = dPs + g * Cout + c0;
+            float sacc = acc[r];
+            if (cn == CH) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) sacc = fmaf(a[j], wc[j * D + dd], sacc);
+            } else {
+              for (int j = 0; j < cn; ++j) sacc = fmaf(a[j], wc[j * D + dd], sacc);
+            }
+            acc[r] = sacc;
+          }
+        }
+        if (ck + 1 < nck) commit((ck + 1) & 1);   // the buffer read in iteration ck-1: every thread is past that barrier
+        __syncthreads();
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int o = tid + r * nt;
+        if (o < GD) {
+          const int g = o / D, dd = o - g * D;
+          dO[g * DS + dd] = acc[r];
         }
       }
-      for (; c + 3 < Cout; c += 4, w += 4 * (long long)I) {
-        const float4 av = *reinterpret_cast<const float4*>(a + c);
-        a0 = fmaf(av.x, __ldg(w), a0);
-        a1 = fmaf(av.y, __ldg(w + I), a1);
-        a2 = fmaf(av.z, __ldg(w + 2 * (long long)I), a2);
-        a3 = fmaf(av.w, __ldg(w + 3 * (long long)I), a3);
-      }
-      for (; c < Cout; ++c, w += I) a0 = fmaf(a[c], __ldg(w), a0);
-      dO[g * DS + dd] = (a0 + a1) + (a2 + a3);
     }
     // dWo_part[b, c, h*D+d] = sum_g dP[g,c] O[g,d]
     if ((D & 3) == 0) {
@@ -522,8 +553,8 @@ extern "C" int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const fl
   size_t smem = token_bwd_smem(D, G);
   TBNS_REQUIRE(smem <= SMEM_LIMIT, "tbns_pa_token_attn_bwd: dim_head=%d slice_num=%d exceed shared memory", D, G);
   int stage = 0;
-  const size_t extra = sizeof(float) * ((size_t)G * Cout + (size_t)G * D);
-  if (smem + extra <= SMEM_LIMIT) {
+  const size_t extra = sizeof(float) * ((size_t)G * Cout + (size_t)G * D + (size_t)2 * 32 * D);   // dP tile, O, to_out window x2
+  if (smem + extra <= SMEM_LIMIT && G * D <= 4 * TOKEN_THREADS && 32 * D <= 2 * TOKEN_THREADS) {
     stage = 1;
     smem += extra;
   }

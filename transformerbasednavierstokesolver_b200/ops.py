@@ -504,8 +504,9 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
     if tc:
         if dout16 is None:
             dout16 = cast_bf16(dout)
+        with _OnSide():   # dw is not needed before the slice backward: it runs beside dP -> token attention backward
+            gemm_tc(dout16, P, dw, None, B, 1, N, Cout, HG, w_batched=1, C16=dw16, tag="deslice_dw")
         gemm_tc_wgrad(w, dout16, B, 1, N, HG, Cout, batched=1, C=dP, tag="deslice_dP")
-        gemm_tc(dout16, P, dw, None, B, 1, N, Cout, HG, w_batched=1, C16=dw16, tag="deslice_dw")
     else:
         gemm(M=HG, N=Cout, K=N, A=w, lda=HG, a_kind=1, B=dout, ldb=Cout, b_kind=1, C=dP, ldc=Cout, batch=B, sA=N * HG, sB=N * Cout,
              sC=HG * Cout, precision=precision, split_k=_split_k(HG, Cout, N, B), tag="deslice_dP")
@@ -528,6 +529,8 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
     dXF16 = torch.empty(B * N, I2, device=dev, dtype=torch.bfloat16) if tc else None
     dWs_part = torch.empty(B * H * groups, G * (D + 1), **f32)
     dtau_part = torch.empty(B * H * groups, **f32)
+    if tc:
+        _join_side()   # dw
     if slice_tc:
         with _Timed("slice_bwd"):
             check(lib.tbns_pa_slice_bwd_tc(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw16), _p(dTt), _p(ds), _p(dXF16), _p(dWs_part),
