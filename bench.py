@@ -48,7 +48,7 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0 = index, [], None, None
 
     def start(self):
         try:
@@ -60,18 +60,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """start of the timed region (nvidia-smi itself is started before the warm-up: it needs up to a second to come up)"""
+        self.t0 = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        window = "timed region"
+        rows = [r for t, r in self.rows if self.t0 is None or t >= self.t0]
+        if not any(len(r) >= 6 and r[0].replace(".", "").isdigit() for r in rows):
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (same load)"   # region shorter than one sample period
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def conv_fprop_flops(batch_tokens: int) -> float:
@@ -166,6 +174,9 @@ def run_ours(args):
     dev_pool = [tuple(t.to(dev) for t in b) for b in pool]
     batched = bool(args.batched)
     gstep = None
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()   # long before the timed region: nvidia-smi needs up to a second for its first sample
     if graphed:
         ops.LAUNCHES = 0
         gstep = train.GraphedTrainStep(model, opt, sched, grads, dev_pool[0], T_OUT, STEP, batched=batched, warmup=3)
@@ -193,7 +204,7 @@ def run_ours(args):
     def timed(fn, steps, sampler=None):
         barrier()
         if sampler:
-            sampler.start()
+            sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ops.LAUNCHES = 0
         e0.record()
@@ -216,13 +227,14 @@ def run_ours(args):
     # device-resident timing, with CUDA-event pairs around the dominant kernel (projection conv fprop)
     if not graphed:
         ops.PROFILE = {}
-    ms_dev, launches, clocks = timed(step_device, args.steps, ClockSampler(local) if rank == 0 else None)
+    ms_dev, launches, clocks = timed(step_device, args.steps, sampler)
     prof, ops.PROFILE = ops.PROFILE, None
     prof_ms = ms_dev
     if graphed:
         # kernels inside a replayed graph cannot be bracketed by events: time the dominant kernel in eager replays of the
         # same step (same shapes, same buffers) right after the timed region
         ops.PROFILE = {}
+        side_saved, ops._USE_SIDE = ops._USE_SIDE, False   # per-launch times of kernels running alone, not beside the wgrad branch
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pe0.record()
         for i in range(3):
@@ -231,6 +243,7 @@ def run_ours(args):
         pe1.record()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
+        ops._USE_SIDE = side_saved
         prof_ms = pe0.elapsed_time(pe1)
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
@@ -262,12 +275,13 @@ def run_ours(args):
                     # (profiles/ncu_r01_conv_fprop_persistent.md); algorithmic minimum 2*M*C + 4*M*2I + 2*9C*2I = 212 MB
                     "traffic": 163.44e6 if batched else None, "traffic_unit": "bytes/launch (ncu)",
                     "peak_source": pk["source"] + " (sustained bf16 cuBLAS)", "avg_launch_ms": avg_ms, "launches_timed": len(durs),
-                    "share_of_step": sum(durs) / prof_ms,
+                    # warm launch time per step / graph-timed step time (eager replays only provide the per-launch durations)
+                    "share_of_step": (sum(durs) / (3 if graphed else args.steps)) / (ms_dev / args.steps),
                     "timed": "eager replays after the graph-timed region" if graphed else "inside the timed region"}
             for tag in ("proj_dgrad", "proj_wgrad"):
                 if prof.get(tag):
                     d2 = [a.elapsed_time(b) for a, b in prof[tag]]
-                    roof[tag + "_share_of_step"] = sum(d2) / prof_ms
+                    roof[tag + "_share_of_step"] = (sum(d2) / (3 if graphed else args.steps)) / (ms_dev / args.steps)
             # warm per-kernel-family device time per step (CUDA events around every tagged libtbns launch, eager replays)
             nprof = 3 if graphed else args.steps
             roof["kernel_ms_per_step"] = {t: round(sum(a.elapsed_time(b) for a, b in v) / nprof, 3) for t, v in sorted(prof.items())}
