@@ -56,7 +56,10 @@ def test_batched_teacher_forcing_equals_loop_on_gpu():
         pkg.set_default_precision("bf16")
 
 
-def test_graphed_step_matches_eager_steps():
+@pytest.mark.parametrize("buckets", [1, 2])
+def test_graphed_step_matches_eager_steps(buckets):
+    """CUDA-graph replay of the optimizer step (one backward graph, or backward cut into `buckets` stage graphs whose
+    gradient ranges are all-reduced separately under data parallelism) against the eager loop."""
     import transformerbasednavierstokesolver_b200 as pkg
     from transformerbasednavierstokesolver_b200 import train
     dev = torch.device("cuda:0")
@@ -71,7 +74,8 @@ def test_graphed_step_matches_eager_steps():
         g2 = train.FlatGradients(m2.parameters())
         o2 = torch.optim.AdamW(m2.parameters(), lr=torch.tensor(1e-3, device=dev), weight_decay=1e-5, fused=True, capturable=True)
         state0 = copy.deepcopy(m2.state_dict())
-        gs = train.GraphedTrainStep(m2, o2, None, g2, batches[0], T=3, step=1, batched=True, warmup=2)
+        gs = train.GraphedTrainStep(m2, o2, None, g2, batches[0], T=3, step=1, batched=True, warmup=2, buckets=buckets)
+        assert gs.nb == buckets
         # warm-up and capture advanced the weights / optimizer state: restart both from the initial point
         m2.load_state_dict(state0)
         for st in o2.state.values():

@@ -10,10 +10,15 @@ single-GPU run with the same global batch.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
 import torch.distributed as dist
+
+
+# diagnostic only (measures what the exchange costs): replicas drift apart without it
+_NO_ALLREDUCE = os.environ.get("TBNS_DEBUG_NO_ALLREDUCE", "0") == "1"
 
 
 def rel_l2_sum(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
@@ -65,7 +70,7 @@ class FlatGradients:
             p.grad = v
 
     def all_reduce(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not _NO_ALLREDUCE:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
 
@@ -180,38 +185,141 @@ def synthetic_ns_batch(batch: int, h: int, T_in: int, T: int, seed: int, device=
 
 
 class GraphedTrainStep:
-    """Optimizer step replayed from CUDA graphs: at cfg 1 a step is ~3900 kernel launches of 5-200 us each, so launch
+    """Optimizer step replayed from CUDA graphs: at cfg 1 a step is ~370 kernel launches of 3-160 us each, so launch
     latency matters for the eager loop (and dominates it when the teacher-forced calls are not batched).
-    Two graphs are captured once: (1) zero-grad + forward + backward, (2) AdamW; the NCCL gradient all-reduce runs
-    eagerly between them (collectives are kept out of capture on purpose: replicas replay independently and a captured
-    collective can deadlock against host-side scheduling).  Inputs live in static device buffers (`load` copies a host
-    or device batch in, asynchronously).  libtbns kernels are plain stream launches on caller-owned memory, so they
-    capture like any other kernel: TMA descriptors are kernel parameters and are frozen into the graph together with the
-    static buffer addresses.  The optimizer must be built with capturable=True and a tensor lr (the host-side scheduler
-    writes the new lr into that tensor after each replay)."""
+
+    buckets == 1: two graphs are captured once - (1) forward + backward + gradient gather, (2) AdamW - and the NCCL gradient
+    all-reduce runs eagerly between them (collectives are kept out of capture on purpose: replicas replay independently and
+    a captured collective can deadlock against host-side scheduling).
+
+    buckets == K > 1 (data parallel): backward is cut at K-1 block boundaries into K stages, each its own graph
+    (`torch.autograd.grad` from one boundary activation to the next).  Stage k's parameter gradients are a contiguous range
+    of the flat buffer (`FlatGradients` is re-laid out in stage order) whose all-reduce is launched asynchronously as soon as
+    the stage's graph is enqueued, so it runs beside the remaining stages; only the last bucket's all-reduce is exposed.
+
+    Inputs live in static device buffers (`load` copies a host or device batch in, asynchronously).  libtbns kernels are
+    plain stream launches on caller-owned memory, so they capture like any other kernel: TMA descriptors are kernel
+    parameters and are frozen into the graph together with the static buffer addresses.  The optimizer must be built with
+    capturable=True and a tensor lr (the host-side scheduler writes the new lr into that tensor after each replay)."""
 
     def __init__(self, model, optimizer, scheduler, grads: FlatGradients, example, T: int, step: int = 1,
-                 batched: bool = True, warmup: int = 3):
+                 batched: bool = True, warmup: int = 3, buckets: int = 1):
         self.model, self.opt, self.sched, self.grads = model, optimizer, scheduler, grads
         self.T, self.step_, self.batched = T, step, batched
         self.static = tuple(torch.empty_like(t, device=next(model.parameters()).device) for t in example)
         self.load(example)
+        blocks = list(getattr(model, "blocks", []))
+        self.nb = max(1, min(int(buckets), len(blocks)))
+        if self.nb > 1:
+            self._plan_stages(blocks)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):      # warm-up outside capture: allocator pools, packed-weight caches, smem opt-ins
-                self._fwd_bwd()
+                if self.nb > 1:
+                    for k in range(self.nb):
+                        self._stage(k)
+                    self._release()
+                else:
+                    self._fwd_bwd()
                 self.grads.all_reduce()
                 self.opt.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
-            self.loss = self._fwd_bwd()
+        self.g_stage = []
+        if self.nb > 1:
+            pool = None
+            for k in range(self.nb):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    out = self._stage(k)
+                    if k == 0:
+                        self.loss = out
+                pool = g.pool()
+                self.g_stage.append(g)
+            self._release()
+            self.g_fb = self.g_stage[0]
+        else:
+            self.g_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fb):
+                self.loss = self._fwd_bwd()
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
             self.opt.step()
 
+    # ---- staged backward (buckets > 1) -------------------------------------------------------------------------------
+    def _plan_stages(self, blocks):
+        n = len(blocks)
+        cuts = sorted({round(n * k / self.nb) for k in range(1, self.nb)} - {0, n})   # stage boundaries (block indices)
+        self.nb = len(cuts) + 1
+        self.cuts = cuts
+        # stage 0 runs first in backward: the blocks after the last cut; the last stage owns blocks before the first cut
+        # and everything that is not a block (preprocess, placeholder, ...)
+        edges = [0] + cuts + [n]
+        in_blocks = set()
+        stage_params = []
+        for k in range(self.nb):
+            lo, hi = edges[self.nb - 1 - k], edges[self.nb - k]
+            ps = [p for b in blocks[lo:hi] for p in b.parameters() if p.requires_grad]
+            in_blocks.update(id(p) for p in ps)
+            stage_params.append(ps)
+        stage_params[-1] = [p for p in self.model.parameters() if p.requires_grad and id(p) not in in_blocks] + stage_params[-1]
+        self.stage_params = stage_params
+        # flat gradient buffer in stage order: each stage is one contiguous range
+        fg = self.grads
+        fg.params = [p for ps in stage_params for p in ps]
+        off, fg.views, self.ranges = 0, [], []
+        for ps in stage_params:
+            start = off
+            for p in ps:
+                fg.views.append(fg.flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self.ranges.append((start, off))
+        assert off == fg.flat.numel()
+        for p, v in zip(fg.params, fg.views):
+            p.grad = v
+        self.stage_views = []
+        i = 0
+        for ps in stage_params:
+            self.stage_views.append(fg.views[i:i + len(ps)])
+            i += len(ps)
+        # boundary activations: the input of blocks[c] is the output of blocks[c-1]
+        self._acts = {}
+        for c in cuts:
+            blocks[c - 1].register_forward_hook(lambda mod, inp, out, c=c: self._acts.__setitem__(c, out))
+
+    def _stage(self, k):
+        """backward stage k (k = 0 also runs the forward).  Returns the detached loss for k == 0."""
+        out = None
+        if k == 0:
+            x, fx, yy = self.static
+            self._loss_t = step_loss(self.model, x, fx, yy, self.T, self.step_, self.batched)
+            out = self._loss_t.detach()
+            root, gout = self._loss_t, None
+        else:
+            root, gout = self._acts[self.cuts[self.nb - 1 - (k - 1) - 1]], self._gact
+        last = k == self.nb - 1
+        params = self.stage_params[k]
+        inputs = list(params) if last else [self._acts[self.cuts[self.nb - 2 - k]]] + list(params)
+        res = torch.autograd.grad(root, inputs, grad_outputs=gout, retain_graph=not last, allow_unused=True)
+        if not last:
+            self._gact, res = res[0], res[1:]
+        src, dst = [], []
+        for g, v in zip(res, self.stage_views[k]):
+            if g is None:
+                v.zero_()
+            else:
+                src.append(g)
+                dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        return out
+
+    def _release(self):
+        self._loss_t, self._gact = None, None
+        self._acts.clear()
+
+    # ---- single-graph backward (buckets == 1) ------------------------------------------------------------------------
     def _fwd_bwd(self):
         x, fx, yy = self.static
         self.grads.begin()
@@ -227,8 +335,19 @@ class GraphedTrainStep:
     def __call__(self, batch=None) -> torch.Tensor:
         if batch is not None:
             self.load(batch)
-        self.g_fb.replay()
-        self.grads.all_reduce()
+        if self.nb > 1:
+            multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not _NO_ALLREDUCE
+            works = []
+            for k, g in enumerate(self.g_stage):
+                g.replay()
+                if multi:   # this bucket's all-reduce runs beside the remaining backward stages
+                    a, b = self.ranges[k]
+                    works.append(dist.all_reduce(self.grads.flat[a:b], op=dist.ReduceOp.SUM, async_op=True))
+            for w in works:
+                w.wait()
+        else:
+            self.g_fb.replay()
+            self.grads.all_reduce()
         self.g_opt.replay()
         if self.sched is not None:
             self.sched.step()     # host-side schedule; writes the new lr into the device tensor the graph reads
