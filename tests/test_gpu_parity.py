@@ -384,3 +384,33 @@ def test_cfg5_rollout_shape_block_forward_bf16(dev):
     with torch.no_grad():
         first = m(x, fx=f)
     assert torch.allclose(first[..., 0], roll[..., 0], atol=1e-5)
+
+
+def test_cfg1_ten_step_rollout_bf16_error_unchanged(dev):
+    """BASELINE cfg 1 model (NS 64x64, 8 layers, n_hidden 256, 8 heads, slice_num 32, unified_pos) in bf16 mode: the 10-step
+    closed-loop rollout (exp_ns.py:225-241) against the oracle run in fp32 on the SAME random-init weights, and the
+    accumulated rollout error against a synthetic target ("unchanged 10-step autoregressive rollout error", north_star)."""
+    import transformerbasednavierstokesolver_b200 as pkg
+    from oracle import model as OM
+    from transformerbasednavierstokesolver_b200 import train
+    from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Model
+    torch.manual_seed(21)
+    pkg.set_default_precision("bf16")
+    m = Model(space_dim=2, n_layers=8, n_hidden=256, n_head=8, fun_dim=10, out_dim=1, slice_num=32, ref=8, unified_pos=1, H=64, W=64,
+              mlp_ratio=1)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x, f, yy = train.synthetic_ns_batch(1, 64, 10, 10, seed=9)
+    with torch.no_grad():
+        ref = OM.rollout(x, f, lambda a, b: OM.model_forward(a, b, sd, 8, 8, grid=(64, 64), unified_pos=True, ref=8), T=10)
+    m = m.to(dev)
+    roll = train.rollout(m, x.to(dev), f.to(dev), T=10, step=1).cpu()
+    assert roll.shape == ref.shape == (1, 4096, 10)
+    # weights here are NOT bf16-representable: every tensor-core operand rounding (per-layer budget 2e-3) counts against
+    # the fp32 reference, over 8 layers per call and 10 chained calls
+    r_all, r_first = O.rel_l2(roll, ref), O.rel_l2(roll[..., :1], ref[..., :1])
+    e_ref = float(O.rel_l2_sum(ref.reshape(1, -1), yy.reshape(1, -1)))
+    e_new = float(O.rel_l2_sum(roll.reshape(1, -1), yy.reshape(1, -1)))
+    print(f"cfg1 bf16 rollout: rel-L2 first call {r_first:.2e}, ten steps {r_all:.2e}; rollout error {e_new:.5f} vs {e_ref:.5f}")
+    assert r_first < 8 * 2e-3 / 2      # 8 layers, errors add incoherently: well inside 8 x the per-layer gate
+    assert r_all < 2e-2
+    assert abs(e_new - e_ref) < 5e-3 * abs(e_ref)   # "unchanged rollout error"
