@@ -184,6 +184,34 @@ def synthetic_ns_batch(batch: int, h: int, T_in: int, T: int, seed: int, device=
     return out
 
 
+class DeferredLoss:
+    """Per-step loss logging that does not drain the GPU: every step's scalar is copied to pinned host memory
+    asynchronously and read one step late (after the NEXT step has been enqueued), so the host never waits for the step
+    it has just launched.  `push` after each step, `flush` at the end; `values` holds one float per step."""
+
+    def __init__(self):
+        self.host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.ev = [torch.cuda.Event() for _ in range(2)]
+        self.n, self.values = 0, []
+
+    def push(self, loss_dev: torch.Tensor):
+        i = self.n & 1
+        self.host[i].copy_(loss_dev, non_blocking=True)
+        self.ev[i].record()
+        if self.n > 0:
+            self._read((self.n - 1) & 1)
+        self.n += 1
+
+    def _read(self, j):
+        self.ev[j].synchronize()
+        self.values.append(float(self.host[j]))
+
+    def flush(self):
+        if self.n > len(self.values):
+            self._read((self.n - 1) & 1)
+        return self.values
+
+
 class GraphedTrainStep:
     """Optimizer step replayed from CUDA graphs: at cfg 1 a step is ~370 kernel launches of 3-160 us each, so launch
     latency matters for the eager loop (and dominates it when the teacher-forced calls are not batched).
