@@ -285,7 +285,7 @@ def run_ours(args):
                     "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
                     # (profiles/ncu_r01_conv_fprop_persistent.md); algorithmic minimum 2*M*C + 4*M*2I + 2*9C*2I = 212 MB
-                    "traffic": 163.44e6 if batched else None, "traffic_unit": "bytes/launch (ncu)",
+                    "traffic": 160.65e6 if batched else None, "traffic_unit": "bytes/launch (ncu)",
                     "peak_source": pk["source"] + " (sustained bf16 cuBLAS)", "avg_launch_ms": avg_ms, "launches_timed": len(durs),
                     # warm launch time per step / graph-timed step time (eager replays only provide the per-launch durations)
                     "share_of_step": (sum(durs) / (3 if graphed else args.steps)) / (ms_dev / args.steps),
