@@ -82,7 +82,9 @@ typedef struct tbns_tc_desc {
   const void* W16;              /* bf16 weights [w_batched ? Bimg : 1][N][taps*Cin]                     */
   int N, w_batched;             /* w_batched=1: image b uses its own weight matrix (deslice: P[b])      */
   const float* bias;            /* [N] or NULL                                                          */
-  int act;                      /* as tbns_gemm_desc.act                                                */
+  int act;                      /* 0 / 1 / 2 as tbns_gemm_desc.act ; 3: GELU, aux_out receives GELU'(pre) instead of pre ;
+                                   4: multiply by aux_in[m,n] itself (the derivative stored by act 3): the backward
+                                   contraction then needs no transcendental                               */
   float* aux_out; const float* aux_in; long long ldaux;
   const float* residual; long long ldr;
   float* C; long long ldc;      /* fp32 output or NULL                                                  */

@@ -30,6 +30,8 @@ cases = {
     "conv_fprop 81920x2304x512": (lambda: ops.gemm_tc(x16, Wf16, XF, bias, B, Hg, Wg, C, I2, 9, 0), 2.0 * M * 9 * C * I2),
     "fc1 81920x256x256 +bias+gelu+pre16+bf16": (lambda: ops.gemm_tc(x16, W1, None, b1, 1, 1, M, C, C, act=1, aux_out=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
     "dpre 81920x256x256 gelu'(pre16)+bf16": (lambda: ops.gemm_tc(x16, W1, None, None, 1, 1, M, C, C, act=2, aux_in=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
+    "fc1d 81920x256x256 +bias+gelu+gelu'16+bf16 (act 3)": (lambda: ops.gemm_tc(x16, W1, None, b1, 1, 1, M, C, C, act=3, aux_out=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
+    "dpred 81920x256x256 *stored gelu'+bf16 (act 4)": (lambda: ops.gemm_tc(x16, W1, None, None, 1, 1, M, C, C, act=4, aux_in=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
     "dx2 81920x256x256 fp32 out": (lambda: ops.gemm_tc(x16, W1, out, None, 1, 1, M, C, C), 2.0 * M * C * C),
     "fc2 81920x256x256 +bias+res": (lambda: ops.gemm_tc(hid16, W1, out, b1, 1, 1, M, C, C, residual=res), 2.0 * M * C * C),
     "conv_wgrad 2304x512x81920": (lambda: ops.gemm_tc_wgrad(x16, dXF16, B, Hg, Wg, C, I2, taps=9, scatter=(dWx, dWfx), I=C), 2.0 * M * 9 * C * I2),

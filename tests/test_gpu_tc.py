@@ -107,6 +107,14 @@ def test_tc_epilogues_and_batched_weights():
     aux = (pre_ref / 3).float()
     _tc(_bf16(A), _bf16(W[0].contiguous()), out, None, Bimg, 1, Ntok, K, N, 1, 0, act=2, aux_in=aux)
     assert O.rel_l2(out.cpu(), (torch.einsum("bmk,nk->bmn", A64, W64[0]) * O.gelu_grad(aux.double())).cpu()) < 1e-5
+    # act 3: GELU with the DERIVATIVE GELU'(pre) as side output (bf16); act 4: multiply by that stored derivative
+    gp16 = torch.empty(Bimg, Ntok, N, device=dev, dtype=torch.bfloat16)
+    h16 = torch.empty(Bimg, Ntok, N, device=dev, dtype=torch.bfloat16)
+    _tc(_bf16(A), _bf16(W[0].contiguous()), None, bias, Bimg, 1, Ntok, K, N, 1, 0, act=3, aux_out=gp16, aux_bf16=1, C16=h16)
+    assert O.rel_l2(gp16.double().cpu(), O.gelu_grad(pre_ref).cpu()) < 3e-3      # bf16 rounding of the stored values
+    assert O.rel_l2(h16.double().cpu(), O.gelu(pre_ref).cpu()) < 3e-3
+    _tc(_bf16(A), _bf16(W[0].contiguous()), out, None, Bimg, 1, Ntok, K, N, 1, 0, act=4, aux_in=gp16, aux_bf16=1)
+    assert O.rel_l2(out.cpu(), (torch.einsum("bmk,nk->bmn", A64, W64[0]) * gp16.double()).cpu()) < 1e-5
 
 
 @pytest.mark.parametrize("Bimg,Hg,Wg,C,I2", [(2, 64, 64, 256, 512), (1, 85, 85, 128, 256), (3, 7, 33, 128, 64)])

@@ -357,11 +357,12 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
 // EPI < 0: every option is a runtime test on TcParams.  EPI >= 0: a bit set of EPI_* flags fixed at compile time, so the
 // short-K contractions (whose time is all epilogue) run straight-line code for exactly the options they use.
 enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_DGELU = 4, EPI_RES = 8, EPI_ROUND = 16, EPI_C = 32, EPI_C16 = 64, EPI_AUX16 = 128,
-             EPI_AUXOUT = 256 };
+             EPI_AUXOUT = 256, EPI_DERIV = 512 /* the aux stream holds GELU'(pre) instead of pre (act 3 / 4) */ };
 static int epi_code(const TcParams& p) {
-  return (p.bias ? EPI_BIAS : 0) | (p.act == 1 ? EPI_GELU : 0) | (p.act == 2 ? EPI_DGELU : 0) | (p.residual ? EPI_RES : 0) |
-         (p.round_tf32 ? EPI_ROUND : 0) | (p.C ? EPI_C : 0) | (p.C16 ? EPI_C16 : 0) | (p.aux_bf16 ? EPI_AUX16 : 0) |
-         (p.act == 1 && p.aux_out ? EPI_AUXOUT : 0);
+  const bool gelu = p.act == 1 || p.act == 3, mul = p.act == 2 || p.act == 4;
+  return (p.bias ? EPI_BIAS : 0) | (gelu ? EPI_GELU : 0) | (mul ? EPI_DGELU : 0) | (p.act >= 3 ? EPI_DERIV : 0) |
+         (p.residual ? EPI_RES : 0) | (p.round_tf32 ? EPI_ROUND : 0) | (p.C ? EPI_C : 0) | (p.C16 ? EPI_C16 : 0) |
+         (p.aux_bf16 ? EPI_AUX16 : 0) | (gelu && p.aux_out ? EPI_AUXOUT : 0);
 }
 
 template <int EPI>
@@ -373,7 +374,7 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
   } p;
   constexpr bool GEN = EPI < 0;
   p.bias = (GEN || (EPI & EPI_BIAS)) ? pp.bias : nullptr;
-  p.act = GEN ? pp.act : ((EPI & EPI_GELU) ? 1 : (EPI & EPI_DGELU) ? 2 : 0);
+  p.act = GEN ? pp.act : ((EPI & EPI_GELU) ? ((EPI & EPI_DERIV) ? 3 : 1) : (EPI & EPI_DGELU) ? ((EPI & EPI_DERIV) ? 4 : 2) : 0);
   p.aux_out = (GEN || (EPI & EPI_AUXOUT)) ? pp.aux_out : nullptr;
   p.aux_in = pp.aux_in;
   p.ldaux = pp.ldaux;
@@ -389,10 +390,11 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
                  K_C16 = !GEN && (EPI & EPI_C16), K_AUXOUT = !GEN && (EPI & EPI_AUXOUT);
   const int cb = n + 2 * (t & 3);
   float2 ld[4][4];   // [row k][column group j]
-  const float* src = p.act == 2 ? p.aux_in : p.residual;
-  const long long lds = p.act == 2 ? p.ldaux : p.ldr;
-  if (K_RES || p.act == 2 || (GEN && src)) {
-    const bool h16 = p.act == 2 && p.aux_bf16;
+  const bool mulaux = p.act == 2 || p.act == 4;   // multiply by GELU'(aux_in) / by aux_in itself
+  const float* src = mulaux ? p.aux_in : p.residual;
+  const long long lds = mulaux ? p.ldaux : p.ldr;
+  if (K_RES || mulaux || (GEN && src)) {
+    const bool h16 = mulaux && p.aux_bf16;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -419,16 +421,24 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
     for (int j = 0; j < 4; ++j) {
       const int c = cb + 8 * j;
       float x0 = v[k >> 1][4 * j + 2 * (k & 1)] + bias[j].x, x1 = v[k >> 1][4 * j + 2 * (k & 1) + 1] + bias[j].y;
-      if (p.act == 1) {
+      if (p.act == 1 || p.act == 3) {
+        float c0, d0, c1, d1;
+        gelu_parts(x0, c0, d0);
+        gelu_parts(x1, c1, d1);
         if (ok && (K_AUXOUT || (GEN && p.aux_out))) {
-          if (p.aux_bf16) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + gr * p.ldaux + c) = __floats2bfloat162_rn(x0, x1);
-          else *reinterpret_cast<float2*>(p.aux_out + gr * p.ldaux + c) = make_float2(x0, x1);
+          // side stream for backward: the pre-activation (act 1) or, cheaper for the consumer, GELU'(pre) itself (act 3)
+          const float a0 = p.act == 3 ? fmaf(x0, d0, c0) : x0, a1 = p.act == 3 ? fmaf(x1, d1, c1) : x1;
+          if (p.aux_bf16) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + gr * p.ldaux + c) = __floats2bfloat162_rn(a0, a1);
+          else *reinterpret_cast<float2*>(p.aux_out + gr * p.ldaux + c) = make_float2(a0, a1);
         }
-        x0 = gelu_fast(x0);
-        x1 = gelu_fast(x1);
+        x0 *= c0;
+        x1 *= c1;
       } else if (p.act == 2) {
         x0 *= gelu_grad_fast(ld[k][j].x);
         x1 *= gelu_grad_fast(ld[k][j].y);
+      } else if (p.act == 4) {
+        x0 *= ld[k][j].x;
+        x1 *= ld[k][j].y;
       } else if (K_RES || (GEN && p.residual)) {
         x0 += ld[k][j].x;
         x1 += ld[k][j].y;
@@ -812,6 +822,8 @@ static int launch_tcp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPa
       TBNS_EPI_CASE(EPI_C16)                                                        // dw (bf16 only)
       TBNS_EPI_CASE(EPI_BIAS | EPI_GELU | EPI_AUXOUT | EPI_AUX16 | EPI_C16)         // fc1: pre (bf16) + gelu (bf16)
       TBNS_EPI_CASE(EPI_DGELU | EPI_AUX16 | EPI_C16)                                // dpre = (dy W2) * gelu'(pre)
+      TBNS_EPI_CASE(EPI_BIAS | EPI_GELU | EPI_AUXOUT | EPI_AUX16 | EPI_C16 | EPI_DERIV)   // fc1: gelu'(pre) (bf16) + gelu (bf16)
+      TBNS_EPI_CASE(EPI_DGELU | EPI_AUX16 | EPI_C16 | EPI_DERIV)                    // dpre = (dy W2) * stored gelu' 
 #undef TBNS_EPI_CASE
       default: break;
     }
@@ -856,7 +868,7 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
   TBNS_REQUIRE(tbns_gemm_tc_supported(d.Cin, d.N, d.taps), "tbns_gemm_tc: unsupported shape Cin=%d N=%d taps=%d (need Cin%%64==0, N%%64==0)",
                d.Cin, d.N, d.taps);
   TBNS_REQUIRE(d.Bimg > 0 && d.Hg > 0 && d.Wg > 0, "tbns_gemm_tc: bad dims");
-  TBNS_REQUIRE(d.act >= 0 && d.act <= 2 && (d.act != 2 || d.aux_in), "tbns_gemm_tc: bad activation spec");
+  TBNS_REQUIRE(d.act >= 0 && d.act <= 4 && ((d.act != 2 && d.act != 4) || d.aux_in), "tbns_gemm_tc: bad activation spec");
   TBNS_REQUIRE(al16p(d.A16) && al16p(d.W16) && (!d.C || (al16p(d.C) && d.ldc % 4 == 0)) && (!d.C16 || (al16p(d.C16) && d.ldc16 % 8 == 0)) &&
                    (!d.bias || al16p(d.bias)) && (!d.residual || (al16p(d.residual) && d.ldr % 4 == 0)) &&
                    (!(d.aux_out || d.aux_in) || d.ldaux % 4 == 0) && (!d.aux_out || al16p(d.aux_out)) && (!d.aux_in || al16p(d.aux_in)),
@@ -912,7 +924,7 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
     if (BNp == 128) return launch_tcp<128, 6>(tmA, tmB, p, (int)m_tiles, st);
     return launch_tcp<64, 8>(tmA, tmB, p, (int)m_tiles, st);
   }
-  TBNS_REQUIRE(!d.aux_bf16, "tbns_gemm_tc: bf16 aux buffers need the persistent kernel");
+  TBNS_REQUIRE(!d.aux_bf16 && d.act <= 2, "tbns_gemm_tc: bf16 aux buffers / act 3, 4 need the persistent kernel");
   if (BN == 256) return launch_tc<256, 4>(tmA, tmB, p, (int)m_tiles, st);
   if (BN == 128) return short_k ? launch_tc<128, 3>(tmA, tmB, p, (int)m_tiles, st) : launch_tc<128, 6>(tmA, tmB, p, (int)m_tiles, st);
   return launch_tc<64, 8>(tmA, tmB, p, (int)m_tiles, st);

@@ -680,8 +680,8 @@ class LnMlpFn(torch.autograd.Function):
             # tensor-core MLP: bf16 operands; LN output and hidden activation only ever exist in bf16 (+ fp32 pre-activation
             # for GELU')
             hid16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
-            pre = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)   # GELU' input for backward: bf16 is plenty
-            gemm_tc(x2_16, weight_bf16(W1), None, b1, 1, 1, M, C_, R, act=1, aux_out=pre, aux_bf16=1, C16=hid16, tag="mlp_fc1")
+            pre = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)   # GELU'(pre-activation), written by fc1's epilogue (act 3)
+            gemm_tc(x2_16, weight_bf16(W1), None, b1, 1, 1, M, C_, R, act=3, aux_out=pre, aux_bf16=1, C16=hid16, tag="mlp_fc1")
             out = torch.empty(*fx.shape[:-1], Cout, device=fx.device, dtype=torch.float32)
             gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, residual=fx, tag="mlp_fc2")
             ctx.save_for_backward(fx, gamma, W1, W2, x2_16, mean, rstd, pre, hid16)
@@ -718,7 +718,7 @@ class LnMlpFn(torch.autograd.Function):
             with _OnSide():
                 gemm_tc_wgrad(dout16, hid, 1, 1, M, Cout, R, C=dW2, tag="mlp_dW2")
             dpre16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
-            gemm_tc(dout16, W2t16, None, None, 1, 1, M, Cout, R, act=2, aux_in=pre, aux_bf16=1, C16=dpre16, tag="mlp_dpre")
+            gemm_tc(dout16, W2t16, None, None, 1, 1, M, Cout, R, act=4, aux_in=pre, aux_bf16=1, C16=dpre16, tag="mlp_dpre")
             with _OnSide():
                 db1 = colsum_bf16(dpre16, M, R)
                 dW1 = torch.empty(R, C_, **f32)
@@ -771,7 +771,7 @@ class MlpFn(torch.autograd.Function):
         b1, b2 = b1.contiguous(), b2.contiguous()
         pre16 = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
         hid16 = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
-        gemm_tc(in16, weight_bf16_padded(W1, Kp), None, b1, 1, 1, M, Kp, R, act=1, aux_out=pre16, aux_bf16=1, C16=hid16, tag="pre_fc1")
+        gemm_tc(in16, weight_bf16_padded(W1, Kp), None, b1, 1, 1, M, Kp, R, act=3, aux_out=pre16, aux_bf16=1, C16=hid16, tag="pre_fc1")
         out = torch.empty(*inp.shape[:-1], Cout, device=dev, dtype=torch.float32)
         gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, tag="pre_fc2")
         ctx.save_for_backward(in16, W1, W2, pre16, hid16)
@@ -794,7 +794,7 @@ class MlpFn(torch.autograd.Function):
         dW2 = torch.empty(Cout, R, **f32)
         gemm_tc_wgrad(dout16, hid16, 1, 1, M, Cout, R, C=dW2, tag="pre_dW2")
         dpre16 = torch.empty(M, R, device=dout.device, dtype=torch.bfloat16)
-        gemm_tc(dout16, weight_bf16(W2, transpose=True), None, None, 1, 1, M, Cout, R, act=2, aux_in=pre16, aux_bf16=1, C16=dpre16,
+        gemm_tc(dout16, weight_bf16(W2, transpose=True), None, None, 1, 1, M, Cout, R, act=4, aux_in=pre16, aux_bf16=1, C16=dpre16,
                 tag="pre_dpre")
         db1 = colsum_bf16(dpre16, M, R)
         dW1p = torch.empty(R, Kp, **f32)
