@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
   float* Wvs = Wks + D * DS;
   float* Wos = Wvs + D * DS;  // [Cout][DS]    (stage != 0) this head's slice of to_out.weight
   float* Ps = Wos + Cout * DS;  // [G][Cout+1] (stage != 0)
+  float* Ou = sm + (((Ps - sm) + G * (Cout + 1) + 3) & ~3);  // [G][D] unpadded, 16-byte aligned copy of O for step 7 (stage != 0)
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
   const long long bh = (long long)b * H + h;
   const int I = H * D;
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
     float acc = 0.f;
     for (int g2 = 0; g2 < G; ++g2) acc = fmaf(A[g * AS + g2], v[g2 * DS + dd], acc);
     O[g * DS + dd] = acc;
+    if (stage) Ou[o] = acc;
     O_out[bh * GD + o] = acc;
   }
   __syncthreads();
@@ -156,16 +158,46 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
     }
     return;
   }
-  for (int o = tid; o < G * Cout; o += nt) {
-    const int g = o / Cout, c = o - g * Cout;
-    const float* ov = O + g * DS;
-    const float* wv = Wos + c * DS;
-    float acc = 0.f;
+  bool done7 = false;
+  if constexpr (DT > 0 && (DT & 3) == 0) {
+    if (nt % Cout == 0) {
+      // thread = one output channel c for the slice rows g0, g0 + nt/Cout, ...: its to_out row lives in registers and every
+      // O row is read with 16-byte broadcast loads (all lanes of a warp share g) - 4x fewer shared-memory instructions
+      const int c = tid % Cout, g0 = tid / Cout, gs = nt / Cout;
+      float w[DT];
+#pragma unroll
+      for (int dd = 0; dd < DT; ++dd) w[dd] = Wos[c * DS + dd];
+      for (int g = g0; g < G; g += gs) {
+        const float4* ov = reinterpret_cast<const float4*>(Ou + g * DT);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int q4 = 0; q4 < DT / 4; ++q4) {
+          const float4 o4 = ov[q4];
+          a0 = fmaf(o4.x, w[4 * q4], a0);
+          a1 = fmaf(o4.y, w[4 * q4 + 1], a1);
+          a0 = fmaf(o4.z, w[4 * q4 + 2], a0);
+          a1 = fmaf(o4.w, w[4 * q4 + 3], a1);
+        }
+        const float acc = a0 + a1;
+        Pout[(long long)g * Cout + c] = acc;
+        if (P16) P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(acc);
+        Ps[g * (Cout + 1) + c] = acc;
+      }
+      done7 = true;
+    }
+  }
+  if (!done7) {
+    for (int o = tid; o < G * Cout; o += nt) {
+      const int g = o / Cout, c = o - g * Cout;
+      const float* ov = O + g * DS;
+      const float* wv = Wos + c * DS;
+      float acc = 0.f;
 #pragma unroll 8
-    for (int dd = 0; dd < D; ++dd) acc = fmaf(ov[dd], wv[dd], acc);
-    Pout[(long long)g * Cout + c] = acc;
-    if (P16) P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(acc);
-    Ps[g * (Cout + 1) + c] = acc;
+      for (int dd = 0; dd < D; ++dd) acc = fmaf(ov[dd], wv[dd], acc);
+      Pout[(long long)g * Cout + c] = acc;
+      if (P16) P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(acc);
+      Ps[g * (Cout + 1) + c] = acc;
+    }
   }
   if (PT16) {
     __syncthreads();
@@ -468,7 +500,7 @@ static bool slice_shape_ok(int D, int G) {
 }
 
 static size_t token_fwd_smem(int D, int G) { return sizeof(float) * ((size_t)5 * G * (D + 1) + (size_t)G * (G + 1) + G + (size_t)3 * D * (D + 1)); }
-static size_t token_fwd_stage_smem(int D, int G, int Cout) { return sizeof(float) * ((size_t)Cout * (D + 1) + (size_t)G * (Cout + 1)); }
+static size_t token_fwd_stage_smem(int D, int G, int Cout) { return sizeof(float) * ((size_t)Cout * (D + 1) + (size_t)G * (Cout + 1) + (size_t)G * D + 4); }
 static size_t token_bwd_smem(int D, int G) { return sizeof(float) * ((size_t)8 * G * (D + 1) + (size_t)2 * G * (G + 1) + G + (size_t)3 * D * (D + 1)); }
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
