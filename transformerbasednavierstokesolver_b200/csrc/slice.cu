@@ -201,9 +201,24 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
   }
   if (PT16) {
     __syncthreads();
-    for (int o = tid; o < G * Cout; o += nt) {  // g fastest: coalesced rows of the transposed (K-major) bf16 copy
-      const int c = o / G, g = o - c * G;
-      PT16[((long long)b * Cout + c) * (H * G) + h * G + g] = __float2bfloat16_rn(Ps[g * (Cout + 1) + c]);
+    // transposed (K-major) bf16 copy: row c of image b holds this head's G slices contiguously
+    __nv_bfloat16* ptb = PT16 + (long long)b * Cout * (H * G) + h * G;
+    if ((G & 7) == 0 && ((H * G) & 7) == 0 && (reinterpret_cast<uintptr_t>(PT16) & 15) == 0) {
+      // one 16-byte store of 8 consecutive slices per thread; lanes walk consecutive c (stride Cout+1 in Ps: conflict-free)
+      const int G8 = G >> 3;
+      for (int o = tid; o < G8 * Cout; o += nt) {
+        const int c = o % Cout, g8 = (o / Cout) * 8;
+        const float* ps = Ps + g8 * (Cout + 1) + c;
+        __nv_bfloat162 q4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q4[j] = __floats2bfloat162_rn(ps[(2 * j) * (Cout + 1)], ps[(2 * j + 1) * (Cout + 1)]);
+        *reinterpret_cast<uint4*>(ptb + (long long)c * (H * G) + g8) = *reinterpret_cast<uint4*>(q4);
+      }
+    } else {
+      for (int o = tid; o < G * Cout; o += nt) {
+        const int c = o / G, g = o - c * G;
+        ptb[(long long)c * (H * G) + g] = __float2bfloat16_rn(Ps[g * (Cout + 1) + c]);
+      }
     }
   }
 }
@@ -306,7 +321,16 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_bwd_kernel(const flo
             const int g = o / D, dd = o - g * D;
             const float* a = dPs + g * Cout + c0;
             float sacc = acc[r];
-            if (cn == CH) {
+            if (cn == CH && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) {   // dP row: one 16-byte broadcast load per four channels
+                const float4 a4 = *reinterpret_cast<const float4*>(a + j);
+                sacc = fmaf(a4.x, wc[j * D + dd], sacc);
+                sacc = fmaf(a4.y, wc[(j + 1) * D + dd], sacc);
+                sacc = fmaf(a4.z, wc[(j + 2) * D + dd], sacc);
+                sacc = fmaf(a4.w, wc[(j + 3) * D + dd], sacc);
+              }
+            } else if (cn == CH) {
 #pragma unroll
               for (int j = 0; j < CH; ++j) sacc = fmaf(a[j], wc[j * D + dd], sacc);
             } else {
