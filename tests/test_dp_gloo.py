@@ -99,3 +99,28 @@ def test_rollout_feeds_predictions_back():
         im = model(x, fx=f)
         assert torch.allclose(im[..., 0], r[..., t], atol=1e-6)
         f = torch.cat((f[..., 1:], im), -1)
+
+
+def test_flat_gradients_gather_equals_accumulate():
+    """FlatGradients.begin()/finish() (autograd hands over whole gradient tensors, one multi-tensor copy into the flat
+    all-reduce buffer) == zero() + in-place accumulation; a parameter that receives no gradient reads as zero and
+    p.grad always ends up as a view of the flat buffer (what the optimizer and the all-reduce see)."""
+    torch.manual_seed(0)
+    model = TinyModel(4)
+    model.unused = torch.nn.Parameter(torch.ones(3))         # never touched by forward
+    x, fx, yy = train.synthetic_ns_batch(2, 6, 4, 3, seed=3)
+    g = train.FlatGradients(model.parameters())
+    g.zero()
+    train.step_loss(model, x, fx, yy, 3, 1, True).backward()
+    want = g.flat.clone()
+    g.flat.fill_(123.0)                                       # stale contents must not survive
+    g.begin()
+    assert all(p.grad is None for p in model.parameters())
+    train.step_loss(model, x, fx, yy, 3, 1, True).backward()
+    g.finish()
+    assert torch.equal(g.flat, want)
+    off = 0
+    for p in g.params:
+        assert p.grad.data_ptr() == g.flat.data_ptr() + 4 * off and p.grad.shape == p.shape
+        off += p.numel()
+    assert float(model.unused.grad.abs().sum()) == 0.0
