@@ -64,6 +64,38 @@ def pa_irregular(name, seed, dim, heads, dim_head, G, N, B, taus=None, slice_gai
     torch.save(fx, os.path.join(OUT, name))
 
 
+def pa_autoencoder(name, seed, dim, heads, dim_head, G, Hg, Wg, B):
+    """Physics_Attention_Structured_Mesh_2D_Auto_Encoder (model/Physics_Attention.py:122-227) in the call order of
+    Transolver_Encoder_block.decode (model/Transolver_Structured_Mesh2D_Encoder.py:86-94): encode(cache) -> reconstruct_fx
+    (replaces the cached slice weights by project_slice(weights)) -> decode (uses the REPLACED cache)."""
+    PA = ref.physics_attention()
+    torch.manual_seed(seed)
+    m = PA.Physics_Attention_Structured_Mesh_2D_Auto_Encoder(dim, heads=heads, dim_head=dim_head, dropout=0.0, slice_num=G, H=Hg, W=Wg)
+    with torch.no_grad():
+        m.in_project_slice.weight.mul_(3.0)
+        m.in_project_slice.bias.normal_(0, 0.3)
+        m.temperature.copy_(torch.linspace(0.3, 1.2, heads).reshape(1, heads, 1, 1))
+    m = m.double()
+    x = torch.randn(B, Hg * Wg, dim, dtype=torch.float64, requires_grad=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    fwd = m(x).detach().clone()                       # plain forward == the 2D module's
+    code = m.encode(x, cache_slice=True)
+    w_enc = m.slice_weights.detach().clone()          # [B,H,N,G]
+    rec = m.reconstruct_fx(code)
+    w_proj = m.slice_weights.detach().clone()
+    dec = m.decode(code)
+    r1 = torch.randn(rec.shape, generator=g, dtype=torch.float64)
+    r2 = torch.randn(dec.shape, generator=g, dtype=torch.float64)
+    ((rec * r1).sum() + (dec * r2).sum()).backward()
+    torch.save(dict(kind="Physics_Attention_Structured_Mesh_2D_Auto_Encoder",
+                    kwargs=dict(dim=dim, heads=heads, dim_head=dim_head, dropout=0.0, slice_num=G, H=Hg, W=Wg),
+                    state={k: v.detach().clone() for k, v in m.state_dict().items()}, x=x.detach().clone(), fwd=fwd,
+                    code=code.detach().clone(), w_enc=w_enc, w_proj=w_proj, rec=rec.detach().clone(), dec=dec.detach().clone(),
+                    r1=r1, r2=r2, dx=x.grad.clone(),
+                    grads={k: (p.grad.clone() if p.grad is not None else None) for k, p in m.named_parameters()}),
+               os.path.join(OUT, name))
+
+
 def block(name, seed, structured, hidden, heads, G, last, B, Hg=None, Wg=None, N=None, mlp_ratio=1, out_dim=1):
     torch.manual_seed(seed)
     if structured:
@@ -187,6 +219,8 @@ def main():
     block("block_structured_mid.pt", 21, True, hidden=32, heads=4, G=8, last=False, B=2, Hg=4, Wg=7)
     block("block_structured_last.pt", 22, True, hidden=32, heads=4, G=8, last=True, B=1, Hg=5, Wg=5, out_dim=2)
     block("block_irregular_last.pt", 23, False, hidden=32, heads=2, G=16, last=True, B=1, N=41, mlp_ratio=2)
+    pa_autoencoder("pa_autoencoder_small.pt", 15, dim=32, heads=4, dim_head=8, G=8, Hg=6, Wg=5, B=2)
+    pa_autoencoder("pa_autoencoder_head1.pt", 16, dim=32, heads=1, dim_head=32, G=16, Hg=7, Wg=4, B=1)   # shipped encoder checkpoints' shape
     ckpt_block("pa_ckpt_ep400_block3.pt", 31)
     model_2d("model_2d_unified.pt", 41, unified_pos=1)
     model_2d("model_2d_plainpos.pt", 42, unified_pos=0)

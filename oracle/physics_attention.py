@@ -243,6 +243,33 @@ def pa_forward(x, p: dict, heads: int, grid=None, residual=None):
     return out, dict(x=x, XF=XF, w=w, s=s, Tt=Tt, st=st, grid=grid, heads=heads, clamp=clamp)
 
 
+# ------------------------------------------------------------------------------------------------
+# auto-encoder variant: the pipeline cut after the token stage / restarted at the deslice
+# (Physics_Attention_Structured_Mesh_2D_Auto_Encoder, model/Physics_Attention.py:122-227).
+# Plain differentiable torch: parity tests take gradients of these functions with autograd in fp64.
+# Slice weights are kept in the [B,N,H,G] layout of this file (the reference caches [B,H,N,G]).
+# ------------------------------------------------------------------------------------------------
+def ae_encode(x, p: dict, heads: int, grid):
+    """encode() :185-212 -> (code = out_slice_token [B,H,G,D], slice weights [B,N,H,G])"""
+    XF = proj_fwd(x, p["in_project_x.weight"], p["in_project_x.bias"], p["in_project_fx.weight"], p["in_project_fx.bias"], grid)
+    w, s, Tt = slice_fwd(XF, p["in_project_slice.weight"], p["in_project_slice.bias"], p["temperature"], heads, True)
+    st = token_attn_fwd(s, Tt, p["to_q.weight"], p["to_k.weight"], p["to_v.weight"], p["to_out.0.weight"])
+    return st["O"], w
+
+
+def ae_project_slice(w, p: dict):
+    """reconstruct_fx() :215 - nn.Linear(slice_num, slice_num) over the slice index of the cached weights"""
+    return w @ p["project_slice.weight"].t() + p["project_slice.bias"]
+
+
+def ae_decode(code, w, p: dict):
+    """decode() :221-227 (and the tail of reconstruct_fx :217-219): deslice `code` with the given weights, then to_out"""
+    B, H, G, D = code.shape
+    Wo = p["to_out.0.weight"]
+    P = torch.einsum("bhgd,chd->bhgc", code, Wo.reshape(Wo.shape[0], H, D)).reshape(B, H * G, Wo.shape[0])
+    return deslice_out_fwd(w, P, p["to_out.0.bias"])
+
+
 def pa_backward(dout, p: dict, sv: dict):
     """returns (dx, grads dict keyed like PA_KEYS)."""
     dw, dP, dbo = deslice_out_bwd(dout, sv["w"], sv["st"]["P"])

@@ -93,3 +93,26 @@ def test_library_conv_switch_is_equivalent(golden):
     finally:
         O.USE_LIBRARY_CONV = False
     assert O.rel_l2(b, a) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["pa_autoencoder_small.pt", "pa_autoencoder_head1.pt"])
+def test_autoencoder_oracle_matches_golden(golden, name):
+    """Physics_Attention_Structured_Mesh_2D_Auto_Encoder (model/Physics_Attention.py:122-227): encode / reconstruct_fx /
+    decode in the order Transolver_Encoder_block.decode uses them; gradients of the oracle by autograd in fp64."""
+    fx = golden(name)
+    kw = fx["kwargs"]
+    p = {k: v.clone().requires_grad_(True) for k, v in fx["state"].items()}
+    x = fx["x"].clone().requires_grad_(True)
+    out, _ = O.pa_forward(x, p, kw["heads"], (kw["H"], kw["W"]))
+    assert O.rel_l2(out.detach(), fx["fwd"]) < TOL
+    code, w = O.ae_encode(x, p, kw["heads"], (kw["H"], kw["W"]))
+    assert O.rel_l2(code.detach(), fx["code"]) < TOL
+    assert O.rel_l2(w.detach().permute(0, 2, 1, 3), fx["w_enc"]) < TOL          # reference caches [B,H,N,G]
+    wp = O.ae_project_slice(w, p)
+    assert O.rel_l2(wp.detach().permute(0, 2, 1, 3), fx["w_proj"]) < TOL
+    rec, dec = O.ae_decode(code, wp, p), O.ae_decode(code, wp, p)                # decode runs on the REPLACED cache
+    assert O.rel_l2(rec.detach(), fx["rec"]) < TOL and O.rel_l2(dec.detach(), fx["dec"]) < TOL
+    ((rec * fx["r1"]).sum() + (dec * fx["r2"]).sum()).backward()
+    assert O.rel_l2(x.grad, fx["dx"]) < 1e-9
+    for k, g in fx["grads"].items():
+        assert O.rel_l2(p[k].grad, g) < 1e-9, k
