@@ -414,3 +414,69 @@ def test_cfg1_ten_step_rollout_bf16_error_unchanged(dev):
     assert r_first < 8 * 2e-3 / 2      # 8 layers, errors add incoherently: well inside 8 x the per-layer gate
     assert r_all < 2e-2
     assert abs(e_new - e_ref) < 5e-3 * abs(e_ref)   # "unchanged rollout error"
+
+
+@pytest.mark.parametrize("name", ["pa_autoencoder_small.pt", "pa_autoencoder_head1.pt"])
+def test_autoencoder_attention_matches_reference_golden(dev, golden, name):
+    """Physics_Attention_Structured_Mesh_2D_Auto_Encoder (model/Physics_Attention.py:122-227) in fp32 mode: forward, encode
+    (code + cached slice weights), reconstruct_fx (cache replaced by project_slice(cache)), decode on the replaced cache -
+    the call order of Transolver_Encoder_block.decode - and every gradient of sum(rec*r1) + sum(dec*r2)."""
+    import transformerbasednavierstokesolver_b200 as pkg
+    from transformerbasednavierstokesolver_b200.model import Physics_Attention as PA
+    fx = golden(name)
+    m = PA.Physics_Attention_Structured_Mesh_2D_Auto_Encoder(**fx["kwargs"])
+    m.load_state_dict({k: v.float() for k, v in fx["state"].items()})
+    m.precision = "fp32"
+    m = m.to(dev)
+    x = fx["x"].float().to(dev).requires_grad_(True)
+    assert O.rel_l2(m(x).detach().cpu(), fx["fwd"]) < FP32_OUT_TOL
+    code = m.encode(x, cache_slice=True)
+    assert O.rel_l2(code.detach().cpu(), fx["code"]) < FP32_OUT_TOL
+    assert O.rel_l2(m.slice_weights.detach().cpu(), fx["w_enc"]) < FP32_OUT_TOL
+    rec = m.reconstruct_fx(code)
+    assert O.rel_l2(m.slice_weights.detach().cpu(), fx["w_proj"]) < FP32_OUT_TOL
+    dec = m.decode(code)
+    assert O.rel_l2(rec.detach().cpu(), fx["rec"]) < FP32_OUT_TOL and O.rel_l2(dec.detach().cpu(), fx["dec"]) < FP32_OUT_TOL
+    ((rec * fx["r1"].float().to(dev)).sum() + (dec * fx["r2"].float().to(dev)).sum()).backward()
+    assert O.rel_l2(x.grad.cpu(), fx["dx"]) < 1e-4
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        assert O.rel_l2(p.grad.cpu(), fx["grads"][k]) < 1e-4, k
+
+
+def test_autoencoder_model_encode_decode_bf16_vs_oracle(dev):
+    """Transolver_Structured_Mesh2D_Encoder.Model at a tensor-core shape (n_hidden 128, 4 heads of 32, slice_num 32): decode(encode)
+    == forward, and the last block's encode / decode in bf16 mode against the fp32 oracle on bf16-representable weights."""
+    import transformerbasednavierstokesolver_b200 as pkg
+    from transformerbasednavierstokesolver_b200.model import Transolver_Structured_Mesh2D_Encoder as E
+    torch.manual_seed(31)
+    pkg.set_default_precision("bf16")
+    model = E.Model(space_dim=2, n_layers=2, n_hidden=128, n_head=4, fun_dim=1, out_dim=1, slice_num=32, ref=4, unified_pos=1, H=16, W=16)
+    with torch.no_grad():
+        for p_ in model.parameters():
+            p_.copy_(p_.bfloat16().float())
+    blk = model.blocks[-1]
+    sd = {k: v.detach().clone().double() for k, v in blk.state_dict().items()}
+    asd = {k[len("Attn."):]: v for k, v in sd.items() if k.startswith("Attn.")}
+    h = torch.randn(2, 256, 128).bfloat16().float()
+    x1, _, _ = O.layernorm_fwd(h.double(), sd["ln_1.weight"], sd["ln_1.bias"])
+    code_ref, w_ref = O.ae_encode(x1, asd, 4, (16, 16))
+    wp = O.ae_project_slice(w_ref, asd)
+    y = O.ae_decode(code_ref, wp, asd) + O.ae_decode(code_ref, wp, asd)
+    model = model.to(dev)
+    code = blk.encode(h.to(dev))
+    assert O.rel_l2(code.detach().cpu(), code_ref) < 3e-3
+    out = blk.decode(code)
+    y2, _ = O.ln_mlp_fwd(y, sd["ln_2.weight"], sd["ln_2.bias"], sd["mlp.linear_pre.0.weight"], sd["mlp.linear_pre.0.bias"],
+                         sd["mlp.linear_post.weight"], sd["mlp.linear_post.bias"])
+    ref_out, _ = O.ln_linear_fwd(y2, sd["ln_3.weight"], sd["ln_3.bias"], sd["mlp2.weight"], sd["mlp2.bias"])
+    assert O.rel_l2(out.detach().cpu(), ref_out) < 5e-3
+    from transformerbasednavierstokesolver_b200 import train
+    x, f, _ = train.synthetic_ns_batch(2, 16, 1, 1, seed=4, device=dev)
+    with torch.no_grad():
+        a = model(x, f)
+        b = model.decode(model.encode(x, f))
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert tuple(model.get_attention_slice().shape) == (2, 4, 256, 32)
+    out.sum().backward()   # gradients flow through decode, the projected cache and encode
+    assert all(p_.grad is not None and bool(torch.isfinite(p_.grad).all()) for p_ in blk.parameters())

@@ -13,10 +13,12 @@ from transformerbasednavierstokesolver_b200.model.SOL_Transolver_Structured_Mesh
 
 
 def test_registry_keys_match_reference():
-    for name, mod in (("Transolver_Irregular_Mesh", Transolver_Irregular_Mesh), ("Transolver_Structured_Mesh_2D", Transolver_Structured_Mesh_2D)):
+    from transformerbasednavierstokesolver_b200.model import Transolver_Structured_Mesh2D_Encoder
+    for name, mod in (("Transolver_Irregular_Mesh", Transolver_Irregular_Mesh), ("Transolver_Structured_Mesh_2D", Transolver_Structured_Mesh_2D),
+                      ("Transolver_Structured_Mesh2D_Encoder", Transolver_Structured_Mesh2D_Encoder)):
         assert model_dict.get_model(types.SimpleNamespace(model=name)) is mod
         assert hasattr(mod, "Model")
-    for name in ("Transolver_Structured_Mesh_3D", "Transolver_Structured_Mesh2D_Encoder"):   # registered by the reference, out of scope here
+    for name in ("Transolver_Structured_Mesh_3D",):   # registered by the reference, out of scope here
         with pytest.raises(NotImplementedError):
             model_dict.get_model(types.SimpleNamespace(model=name))
     with pytest.raises(KeyError):
@@ -65,3 +67,25 @@ def test_sol_wrapper_attributes():
     s = SOL_Transolver_Structured_Mesh_2D(space_dim=2, n_layers=1, n_hidden=16, n_head=2, fun_dim=3, slice_num=4, H=4, W=4, step=1, look_ahead=3)
     assert s.n == 3 and s.step == 1 and hasattr(s, "transolver_model")
     assert all(k.startswith("transolver_model.") for k in s.state_dict().keys())
+
+
+def test_autoencoder_module_contract(golden):
+    """Physics_Attention_Structured_Mesh_2D_Auto_Encoder / Transolver_Structured_Mesh2D_Encoder.Model: parameter names and
+    shapes of the reference (model/Physics_Attention.py:122-151, model/Transolver_Structured_Mesh2D_Encoder.py:99-160), the
+    slice-weight accessors in the reference layout [B, heads, N, slice_num], loud failure without a cache."""
+    from transformerbasednavierstokesolver_b200.model import Transolver_Structured_Mesh2D_Encoder as E
+    fx = golden("pa_autoencoder_small.pt")
+    m = PA.Physics_Attention_Structured_Mesh_2D_Auto_Encoder(**fx["kwargs"])
+    assert set(m.state_dict().keys()) == set(fx["state"].keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(fx["state"][k].shape), k
+    assert m.slice_weights is None
+    m.slice_weights = fx["w_enc"].float()
+    assert tuple(m.slice_weights.shape) == tuple(fx["w_enc"].shape) and torch.equal(m.slice_weights, fx["w_enc"].float())
+    m.slice_weights = None
+    model = E.Model(space_dim=2, n_layers=2, n_hidden=32, n_head=1, fun_dim=1, out_dim=1, slice_num=16, ref=4, unified_pos=1, H=8, W=8)
+    keys = set(model.state_dict().keys())
+    assert {"blocks.1.Attn.project_slice.weight", "blocks.0.Attn.project_slice.bias", "blocks.1.mlp2.weight", "placeholder",
+            "preprocess.linear_post.bias"} <= keys and "blocks.0.mlp2.weight" not in keys
+    assert model.get_attention_slice() is None
+    assert model.blocks[0].decode(torch.zeros(1)) is None          # reference prints and returns None for a non-last block

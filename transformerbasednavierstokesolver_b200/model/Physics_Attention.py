@@ -4,6 +4,8 @@ Same constructor arguments, attributes (`heads`, `dim_head`, `H`, `W`, `temperat
 names / shapes (so `state_dict()` round-trips with reference checkpoints) and `forward(x)` contract as
   Physics_Attention_Irregular_Mesh        reference model/Physics_Attention.py:6-57
   Physics_Attention_Structured_Mesh_2D    reference model/Physics_Attention.py:60-119
+  Physics_Attention_Structured_Mesh_2D_Auto_Encoder   reference model/Physics_Attention.py:122-227 (encode / decode /
+                                          reconstruct_fx on a cached, differentiable slice-weight tensor)
 but `forward` runs the sm_100a kernels of libtbns through `ops.PhysicsAttentionFn` (custom backward).
 """
 from __future__ import annotations
@@ -115,3 +117,65 @@ class Physics_Attention_Structured_Mesh_2D(_PhysicsAttentionBase):
         if N != self.H * self.W:
             raise RuntimeError(f"shape '[{B}, {self.H}, {self.W}, {C}]' is invalid for input of size {B * N * C}")
         return (self.H, self.W)
+
+
+class Physics_Attention_Structured_Mesh_2D_Auto_Encoder(Physics_Attention_Structured_Mesh_2D):
+    """Auto-encoder variant (reference model/Physics_Attention.py:122-227): `forward` is the 2D module's; `encode` stops
+    after the attention among slice tokens and returns them (the "code", [B, heads, slice_num, dim_head]), optionally
+    caching the slice weights; `decode` deslices a code with the cached weights and applies `to_out`; `reconstruct_fx`
+    first replaces the cache by `project_slice(cache)`.  The cache keeps its autograd history like the reference's.
+
+    `slice_weights` reads / writes the cache in the reference layout [B, heads, N, slice_num]; internally it is the
+    kernels' [B, N, heads*slice_num]."""
+
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0., slice_num=64, H=101, W=31, kernel=3):
+        super().__init__(dim, heads=heads, dim_head=dim_head, dropout=dropout, slice_num=slice_num, H=H, W=W, kernel=kernel)
+        self.project_slice = nn.Linear(slice_num, slice_num)
+        self._w = None
+
+    @property
+    def slice_weights(self):
+        if self._w is None:
+            return None
+        B, N, HG = self._w.shape
+        return self._w.view(B, N, self.heads, HG // self.heads).permute(0, 2, 1, 3)
+
+    @slice_weights.setter
+    def slice_weights(self, value):
+        if value is None:
+            self._w = None
+            return
+        B, H, N, G = value.shape
+        self._w = value.permute(0, 2, 1, 3).reshape(B, N, H * G).contiguous().float()
+
+    def _check(self, t):
+        if not t.is_cuda:
+            raise RuntimeError("Physics-Attention (B200) has no CPU path: move the module and its input to a CUDA device")
+        if self.training and self.dropout.p > 0.0:
+            raise NotImplementedError("dropout > 0 in training mode is not supported by the fused kernels")
+
+    def encode(self, x, cache_slice=False):
+        self._check(x)
+        grid = self._grid(tuple(x.shape))
+        prec = ops.PRECISIONS[self.precision or config.get_default_precision()]
+        code, w = ops.PaEncodeFn.apply(
+            x.float(), self.temperature, self.in_project_x.weight, self.in_project_x.bias, self.in_project_fx.weight,
+            self.in_project_fx.bias, self.in_project_slice.weight, self.in_project_slice.bias, self.to_q.weight, self.to_k.weight,
+            self.to_v.weight, self.to_out[0].weight, self._packed_weights(), self.heads, grid, prec)
+        if cache_slice:
+            self._w = w
+        return code
+
+    def decode(self, code):
+        self._check(code)
+        if self._w is None:
+            raise RuntimeError("decode() needs cached slice weights: call encode(x, cache_slice=True) or set slice_weights first")
+        prec = ops.PRECISIONS[self.precision or config.get_default_precision()]
+        lin = self.to_out[0]
+        return ops.PaDecodeFn.apply(code.float(), self._w, lin.weight, lin.bias, prec)
+
+    def reconstruct_fx(self, code):
+        if self._w is None:
+            raise RuntimeError("reconstruct_fx() needs cached slice weights: call encode(x, cache_slice=True) first")
+        self._w = ops.SliceLinearFn.apply(self._w, self.project_slice.weight, self.project_slice.bias)
+        return self.decode(code)

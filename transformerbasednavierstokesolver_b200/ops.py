@@ -582,6 +582,250 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
                     Wq=dWqkv[0], Wk=dWqkv[1], Wv=dWqkv[2], Wo=dWo, bo=dbo, _keep=keep)
 
 
+# ------------------------------------------------------------------------------------------------
+# auto-encoder variant (reference Physics_Attention_Structured_Mesh_2D_Auto_Encoder, model/Physics_Attention.py:122-227):
+# the same kernels with the pipeline cut after the token stage (encode) / restarted at the deslice (decode).
+# The slice weights are a differentiable fp32 tensor here ([B,N,H*G]; the reference caches [B,H,N,G]), so the slice stage
+# always runs the exact SIMT kernels; projections and deslice use the tensor-core kernels in bf16 mode when shapes allow.
+# The token-attention backward from dO works on G x D tensors per (batch, head) and is plain torch.
+# ------------------------------------------------------------------------------------------------
+EPS_NORM = 1e-5
+
+
+def pa_encode_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, heads: int, grid, precision: int, Wf16=None):
+    """-> (O [B,H,G,D], w [B,N,H*G] fp32, saved)   (encode(), reference :185-212)"""
+    lib = _lib.load()
+    B, N, C_ = x.shape
+    I2 = Wf.shape[0]
+    I = I2 // 2
+    H = heads
+    D = I // H
+    G = Ws.shape[0]
+    Cout = Wo.shape[0]
+    HG = H * G
+    f32 = dict(device=x.device, dtype=torch.float32)
+    st = _stream()
+    structured = grid is not None
+    taps = 9 if structured else 1
+    Hg, Wg = grid if structured else (1, N)
+    tc = (precision == TBNS_PREC_BF16 and Wf16 is not None and tc_supported(C_, I2, taps) and tc_supported(I2, C_, taps)
+          and wgrad_supported(C_, I2, taps))
+    XF = torch.empty(B * N, I2, **f32)
+    x16 = None
+    if tc:
+        x16 = cast_bf16(x)
+        gemm_tc(x16, Wf16, XF, bcat, B, Hg, Wg, C_, I2, taps, 0, tag="proj_fprop")
+    elif structured:
+        gemm(M=B * N, N=I2, K=9 * C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=9 * C_, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Hg,
+             Wg=Wg, Cin=C_, bias=bcat, precision=precision, tag="proj_fprop")
+    else:
+        gemm(M=B * N, N=I2, K=C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=C_, b_kind=0, C=XF, ldc=I2, bias=bcat, precision=precision,
+             tag="proj_fprop")
+    groups = lib.tbns_slice_groups(B, N, H)
+    w = torch.empty(B, N, HG, **f32)
+    part = torch.empty(B * H * groups * G * (D + 1), **f32)
+    check(lib.tbns_pa_slice_fwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w), None, _p(part), B, N, H, D, G, int(structured), st),
+          "tbns_pa_slice_fwd")
+    s = torch.empty(B, H, G, **f32)
+    Tt, tok, q, k, v, O = (torch.empty(B, H, G, D, **f32) for _ in range(6))
+    A = torch.empty(B, H, G, G, **f32)
+    P = torch.empty(B, HG, Cout, **f32)   # by-product of the token kernel (O.Wo_h^T), unused by encode
+    check(lib.tbns_pa_token_attn_fwd(_p(part), groups, _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(Tt), _p(tok), _p(q), _p(k), _p(v),
+                                     _p(A), _p(O), _p(P), None, None, B, H, D, G, Cout, st), "tbns_pa_token_attn_fwd")
+    _count(2)
+    return O, w, (XF, s, tok, q, k, v, A, x16 if tc else x)
+
+
+def pa_encode_backward(dO, dw, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, saved, heads: int, grid, precision: int,
+                       Wd16=None):
+    """gradients of encode w.r.t. its input and parameters from (dO [B,H,G,D] | None, dw [B,N,H*G] | None)"""
+    lib = _lib.load()
+    XF, s, tok, q, k, v, A, xs = saved
+    B, N, C_ = xshape
+    I2 = XF.shape[1]
+    I = I2 // 2
+    H = heads
+    D = I // H
+    G = Ws.shape[0]
+    HG = H * G
+    dev = XF.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    st = _stream()
+    structured = grid is not None
+    taps = 9 if structured else 1
+    Hg, Wg = grid if structured else (1, N)
+    tc = xs.dtype == torch.bfloat16
+    groups = lib.tbns_slice_groups(B, N, H)
+    # token attention backward from dO (SURVEY.md §8 a-bwd; oracle token_attn_bwd without the to_out fold)
+    if dO is None:
+        dTt = torch.zeros(B, H, G, D, **f32)
+        ds = torch.zeros(B, H, G, **f32)
+        dWq, dWk, dWv = (torch.zeros(D, D, **f32) for _ in range(3))
+    else:
+        dO = dO.contiguous()
+        dA = dO @ v.transpose(-1, -2)
+        dv = A.transpose(-1, -2) @ dO
+        dS = A * (dA - (dA * A).sum(-1, keepdim=True))
+        scale = D ** -0.5
+        dq = dS @ k * scale
+        dk = dS.transpose(-1, -2) @ q * scale
+        dtok = dq @ Wq + dk @ Wk + dv @ Wv
+        dWq = torch.einsum("bhgi,bhgj->ij", dq, tok)
+        dWk = torch.einsum("bhgi,bhgj->ij", dk, tok)
+        dWv = torch.einsum("bhgi,bhgj->ij", dv, tok)
+        inv = 1.0 / (s + EPS_NORM)
+        dTt = (dtok * inv[..., None]).contiguous()
+        ds = (-(dtok * tok).sum(-1) * inv).contiguous()
+    dw = torch.zeros(B, N, HG, **f32) if dw is None else dw.contiguous()
+    # slice backward (exact SIMT kernel: fp32 dw in, fp32 or bf16 dXF out)
+    dXF = None if tc else torch.empty(B * N, I2, **f32)
+    dXF16 = torch.empty(B * N, I2, device=dev, dtype=torch.bfloat16) if tc else None
+    dWs_part = torch.empty(B * H * groups, G * (D + 1), **f32)
+    dtau_part = torch.empty(B * H * groups, **f32)
+    dbcat_part = torch.empty(B * groups, H * 2 * D, **f32)
+    check(lib.tbns_pa_slice_bwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw), _p(dTt), _p(ds), _p(dXF), _p(dXF16), _p(dWs_part),
+                                _p(dtau_part), _p(dbcat_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd")
+    dbc = reduce_rows(dbcat_part, B * groups, H * 2 * D).view(H, 2, D)
+    dbx, dbfx = dbc[:, 0, :].reshape(I), dbc[:, 1, :].reshape(I)
+    dWsb = reduce_rows(dWs_part, B * H * groups, G * (D + 1)).view(G, D + 1)
+    dWs, dbs = dWsb[:, :D].contiguous(), dWsb[:, D].contiguous()
+    dtemp = torch.empty(H, **f32)
+    check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, groups, int(structured), st), "tbns_pa_dtau_finish")
+    _count(2)
+    # projections: dgrad, wgrad
+    dx = torch.empty(B, N, C_, **f32)
+    dWx = torch.empty(Wx_shape, **f32)
+    dWfx = torch.empty(Wx_shape, **f32)
+    if tc:
+        gemm_tc(dXF16, Wd16, dx, None, B, Hg, Wg, I2, C_, taps, 1, tag="proj_dgrad")
+        gemm_tc_wgrad(xs, dXF16, B, Hg, Wg, C_, I2, taps=taps, scatter=(dWx, dWfx), I=I, tag="proj_wgrad")
+    elif structured:
+        gemm(M=B * N, N=C_, K=9 * I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=dx, ldc=C_, conv_mode=1, Hg=Hg, Wg=Wg,
+             Cin=I2, flip=1, precision=precision, tag="proj_dgrad")
+        gemm(M=9 * C_, N=I2, K=B * N, A=xs, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, conv_mode=2, Hg=Hg, Wg=Wg, Cin=C_,
+             precision=precision, split_k=_split_k(9 * C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=9, tag="proj_wgrad")
+    else:
+        gemm(M=B * N, N=C_, K=I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=I2, b_kind=0, C=dx, ldc=C_, precision=precision,
+             tag="proj_dgrad")
+        gemm(M=C_, N=I2, K=B * N, A=xs, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, Cin=C_, precision=precision,
+             split_k=_split_k(C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=1, tag="proj_wgrad")
+    return dx, dict(temperature=dtemp.view(1, H, 1, 1), Wx=dWx, bx=dbx, Wfx=dWfx, bfx=dbfx, Ws=dWs, bs=dbs, Wq=dWq, Wk=dWk, Wv=dWv)
+
+
+class PaEncodeFn(torch.autograd.Function):
+    """(code, slice weights) = encode(x): both outputs are differentiable (decode / reconstruct_fx send gradient into the
+    cached slice weights, reference :214-227)."""
+
+    @staticmethod
+    def forward(ctx, x, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, packed, heads, grid, precision):
+        _begin_forward()
+        x = x.contiguous()
+        Wf, Wd, bcat, Wf16, Wd16 = packed
+        _chk(x, temperature, Ws, bs, Wq, Wk, Wv, Wo, Wf, Wd, bcat)
+        temperature_c = temperature.contiguous()
+        O, w, saved = pa_encode_forward(x, temperature_c, Wf, bcat, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
+                                        Wv.contiguous(), Wo.contiguous(), heads, grid, precision, Wf16)
+        ctx.save_for_backward(temperature_c, Wd, Ws, bs, Wq, Wk, Wv, *saved)
+        ctx.Wd16 = Wd16
+        ctx.cfg = (heads, grid, precision, tuple(Wx.shape), tuple(x.shape))
+        return O, w
+
+    @staticmethod
+    def backward(ctx, dO, dw):
+        heads, grid, precision, wshape, xshape = ctx.cfg
+        temperature, Wd, Ws, bs, Wq, Wk, Wv, *saved = ctx.saved_tensors
+        dx, g = pa_encode_backward(dO, dw, xshape, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(),
+                                   Wk.contiguous(), Wv.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16)
+        _stash_grad16(dx)
+        return (dx, g["temperature"], g["Wx"], g["bx"], g["Wfx"], g["bfx"], g["Ws"], g["bs"], g["Wq"], g["Wk"], g["Wv"], None,
+                None, None, None, None)
+
+
+class PaDecodeFn(torch.autograd.Function):
+    """out = to_out(deslice(code, w)) = w . (code . Wo_h^T) + bo   (decode(), reference :221-227)"""
+
+    @staticmethod
+    def forward(ctx, code, w, Wo, bo, precision):
+        _begin_forward()
+        code, w, Wo, bo = code.contiguous(), w.contiguous(), Wo.contiguous(), bo.contiguous()
+        _chk(code, w, Wo, bo)
+        B, H, G, D = code.shape
+        N, HG = w.shape[1], w.shape[2]
+        Cout = Wo.shape[0]
+        P = torch.einsum("bhgd,chd->bhgc", code, Wo.view(Cout, H, D)).reshape(B, HG, Cout).contiguous()
+        tc = (precision == TBNS_PREC_BF16 and tc_supported(HG, Cout, 1) and tc_supported(Cout, HG, 1) and wgrad_supported(HG, Cout, 1))
+        out = torch.empty(B, N, Cout, device=w.device, dtype=torch.float32)
+        if tc:
+            w16, P16 = cast_bf16(w), cast_bf16(P)
+            PT16 = cast_bf16(P.transpose(1, 2).contiguous())
+            gemm_tc(w16, PT16, out, bo, B, 1, N, HG, Cout, w_batched=1, tag="deslice_out")
+            ctx.save_for_backward(code, Wo, w16, P16)
+        else:
+            gemm(M=N, N=Cout, K=HG, A=w, lda=HG, a_kind=0, B=P, ldb=Cout, b_kind=1, C=out, ldc=Cout, batch=B, sA=N * HG,
+                 sB=HG * Cout, sC=N * Cout, bias=bo, precision=precision, tag="deslice_out")
+            ctx.save_for_backward(code, Wo, w, P)
+        ctx.precision = precision
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        code, Wo, w, P = ctx.saved_tensors
+        precision = ctx.precision
+        dout = dout.contiguous()
+        B, H, G, D = code.shape
+        N, HG = w.shape[1], w.shape[2]
+        Cout = Wo.shape[0]
+        f32 = dict(device=dout.device, dtype=torch.float32)
+        dbo = colsum(dout, B * N, Cout)
+        dP = torch.empty(B, HG, Cout, **f32)
+        dw = torch.empty(B, N, HG, **f32)
+        if w.dtype == torch.bfloat16:
+            dout16 = cast_bf16(dout)
+            gemm_tc_wgrad(w, dout16, B, 1, N, HG, Cout, batched=1, C=dP, tag="deslice_dP")
+            gemm_tc(dout16, P, dw, None, B, 1, N, Cout, HG, w_batched=1, tag="deslice_dw")
+        else:
+            gemm(M=HG, N=Cout, K=N, A=w, lda=HG, a_kind=1, B=dout, ldb=Cout, b_kind=1, C=dP, ldc=Cout, batch=B, sA=N * HG, sB=N * Cout,
+                 sC=HG * Cout, precision=precision, split_k=_split_k(HG, Cout, N, B), tag="deslice_dP")
+            gemm(M=N, N=HG, K=Cout, A=dout, lda=Cout, a_kind=0, B=P, ldb=Cout, b_kind=0, C=dw, ldc=HG, batch=B, sA=N * Cout,
+                 sB=HG * Cout, sC=N * HG, precision=precision, tag="deslice_dw")
+        dP4 = dP.view(B, H, G, Cout)
+        dcode = torch.einsum("bhgc,chd->bhgd", dP4, Wo.view(Cout, H, D))
+        dWo = torch.einsum("bhgc,bhgd->chd", dP4, code).reshape(Cout, H * D)
+        return dcode, dw, dWo, dbo, None
+
+
+class SliceLinearFn(torch.autograd.Function):
+    """project_slice: nn.Linear(slice_num, slice_num) over the slice index of the cached weights w [B,N,H*G]
+    (reconstruct_fx(), reference :215); exact fp32 contraction (K = slice_num)."""
+
+    @staticmethod
+    def forward(ctx, w, Wp, bp):
+        _begin_forward()
+        w, Wp, bp = w.contiguous(), Wp.contiguous(), bp.contiguous()
+        _chk(w, Wp, bp)
+        G = Wp.shape[0]
+        M = w.numel() // G
+        out = torch.empty_like(w)
+        gemm(M=M, N=G, K=G, A=w, lda=G, a_kind=0, B=Wp, ldb=G, b_kind=0, C=out, ldc=G, bias=bp, precision=TBNS_PREC_FP32)
+        ctx.save_for_backward(w, Wp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        w, Wp = ctx.saved_tensors
+        dout = dout.contiguous()
+        G = Wp.shape[0]
+        M = w.numel() // G
+        f32 = dict(device=w.device, dtype=torch.float32)
+        dw = torch.empty_like(w)
+        gemm(M=M, N=G, K=G, A=dout, lda=G, a_kind=0, B=Wp, ldb=G, b_kind=1, C=dw, ldc=G, precision=TBNS_PREC_FP32)
+        dWp = torch.empty(G, G, **f32)
+        gemm(M=G, N=G, K=M, A=dout, lda=G, a_kind=1, B=w, ldb=G, b_kind=1, C=dWp, ldc=G, precision=TBNS_PREC_FP32,
+             split_k=_split_k(G, G, M))
+        dbp = colsum(dout, M, G)
+        return dw, dWp, dbp
+
+
 class PhysicsAttentionFn(torch.autograd.Function):
     """y = PhysicsAttention(x) (+ residual).  Parameters arrive in reference layout; `packed` holds the packed projection
     weights (fp32 and bf16 copies; non-differentiable, refreshed by the module when the masters change)."""
