@@ -266,6 +266,9 @@ class GraphedTrainStep:
                 pool = g.pool()
                 self.g_stage.append(g)
             self._release()
+            for hk in self._hooks:      # only needed while the stages were traced: later eager forwards must not be retained
+                hk.remove()
+            self._hooks = []
             self.g_fb = self.g_stage[0]
         else:
             self.g_fb = torch.cuda.CUDAGraph()
@@ -313,8 +316,7 @@ class GraphedTrainStep:
             i += len(ps)
         # boundary activations: the input of blocks[c] is the output of blocks[c-1]
         self._acts = {}
-        for c in cuts:
-            blocks[c - 1].register_forward_hook(lambda mod, inp, out, c=c: self._acts.__setitem__(c, out))
+        self._hooks = [blocks[c - 1].register_forward_hook(lambda mod, inp, out, c=c: self._acts.__setitem__(c, out)) for c in cuts]
 
     def _stage(self, k):
         """backward stage k (k = 0 also runs the forward).  Returns the detached loss for k == 0."""
