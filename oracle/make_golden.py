@@ -188,6 +188,31 @@ def model_2d(name, seed, unified_pos, rollout_steps=3):
                os.path.join(OUT, name))
 
 
+def model_2d_time(name, seed):
+    """Time_Input=True (exp_plas.py:148,187): forward(x, fx, T) with the sinusoidal timestep embedding + time_fc"""
+    T = ref.transolver_2d()
+    torch.manual_seed(seed)
+    kw = dict(space_dim=2, n_layers=2, n_hidden=32, dropout=0.0, n_head=4, Time_Input=True, mlp_ratio=1, fun_dim=3,
+              out_dim=1, slice_num=8, ref=4, unified_pos=0, H=6, W=7)
+    m = T.Model(**kw).double()
+    m.time_fc.float()     # the reference builds the embedding with `.float()` (model/Embedding.py:81): time_fc can only run in fp32
+    _sharpen(m)
+    with torch.no_grad():
+        for p in m.time_fc.parameters():
+            p.normal_(0, 0.3)
+    x = torch.rand(2, 42, 2).double()
+    fx = torch.randn(2, 42, 3).double()
+    y = torch.randn(2, 42, 1).double()
+    tt = torch.tensor([[3.0], [7.5]], dtype=torch.float64)
+    loss_fn = ref.testloss().TestLoss(size_average=False)
+    out = m(x, fx, T=tt)
+    loss = loss_fn(out.reshape(2, -1), y.reshape(2, -1))
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    torch.save(dict(kind="model_2d", kwargs=kw, state={k: v.detach().clone() for k, v in m.state_dict().items()},
+                    x=x, fx=fx, y=y, T=tt, out=out.detach(), loss=loss.detach(), grads=grads), os.path.join(OUT, name))
+
+
 def model_irregular(name, seed):
     T = ref.transolver_irregular()
     torch.manual_seed(seed)
@@ -225,6 +250,7 @@ def main():
     model_2d("model_2d_unified.pt", 41, unified_pos=1)
     model_2d("model_2d_plainpos.pt", 42, unified_pos=0)
     model_irregular("model_irregular.pt", 43)
+    model_2d_time("model_2d_time.pt", 44)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -28,7 +28,18 @@ def mlp_fwd(x, sd, prefix):
     return h @ sd[prefix + "linear_post.weight"].t() + sd[prefix + "linear_post.bias"]
 
 
-def model_forward(x, fx, sd: dict, n_layers: int, heads: int, grid=None, unified_pos=False, ref=8, irregular=False):
+def timestep_embedding(timesteps, dim: int, max_period: float = 10000.0):
+    """sinusoidal embedding of (possibly fractional) time indices, model/Embedding.py:67-85: [..., dim] = cos | sin"""
+    half = dim // 2
+    freqs = torch.exp(-np.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(timesteps.dtype)
+    args = timesteps[:, None] * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[..., :1])], -1)
+    return emb
+
+
+def model_forward(x, fx, sd: dict, n_layers: int, heads: int, grid=None, unified_pos=False, ref=8, irregular=False, T=None):
     if unified_pos and grid is not None:
         x = unified_pos_table(grid[0], grid[1], ref, x.dtype).repeat(x.shape[0], 1, 1)
     if fx is not None:
@@ -37,6 +48,11 @@ def model_forward(x, fx, sd: dict, n_layers: int, heads: int, grid=None, unified
             h = h + sd["placeholder"][None, None, :]
     else:
         h = mlp_fwd(x, sd, "preprocess.") + sd["placeholder"][None, None, :]
+    if T is not None:   # Time_Input=True (exp_plas.py:148,187): model/Transolver_Structured_Mesh_2D.py:212-215
+        # the reference computes the embedding and time_fc in fp32 whatever the model dtype (Embedding.py:81 `.float()`)
+        e = timestep_embedding(T.float(), h.shape[-1])             # T [B,1] -> [B,1,C]; the reference repeats it over N first
+        e = torch.nn.functional.silu(e @ sd["time_fc.0.weight"].float().t() + sd["time_fc.0.bias"].float())
+        h = h + (e @ sd["time_fc.2.weight"].float().t() + sd["time_fc.2.bias"].float()).to(h.dtype)
     for i in range(n_layers):
         pre = f"blocks.{i}."
         bsd = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}

@@ -231,7 +231,7 @@ def test_block_fp32_matches_reference_golden(dev, golden, name):
         assert O.rel_l2(p.grad.cpu(), fx["grads"][k]) < FP32_GRAD_TOL, k
 
 
-@pytest.mark.parametrize("name", ["model_2d_unified.pt", "model_2d_plainpos.pt", "model_irregular.pt"])
+@pytest.mark.parametrize("name", ["model_2d_unified.pt", "model_2d_plainpos.pt", "model_irregular.pt", "model_2d_time.pt"])
 def test_model_fp32_matches_reference_golden(dev, golden, name):
     import transformerbasednavierstokesolver_b200 as pkg
     fx = golden(name)
@@ -247,7 +247,7 @@ def test_model_fp32_matches_reference_golden(dev, golden, name):
         x = fx["x"].float().to(dev)
         f = fx["fx"].float().to(dev) if "fx" in fx else None
         y = fx["y"].float().to(dev)
-        out = m(x, f)
+        out = m(x, f, T=fx["T"].float().to(dev)) if "T" in fx else m(x, f)   # Time_Input=True fixture: forward(x, fx, T)
         assert O.rel_l2(out.cpu(), fx["out"]) < FP32_OUT_TOL
         n = out.shape[0]
         loss = (torch.linalg.vector_norm(out.reshape(n, -1) - y.reshape(n, -1), dim=1) / torch.linalg.vector_norm(y.reshape(n, -1), dim=1)).sum()

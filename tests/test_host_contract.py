@@ -51,8 +51,8 @@ def test_trained_checkpoint_layout_loads_strict():
 
 
 def test_loud_failures():
-    with pytest.raises(NotImplementedError):
-        Transolver_Structured_Mesh_2D.Model(Time_Input=True)
+    mt = Transolver_Structured_Mesh_2D.Model(Time_Input=True, n_layers=1, n_hidden=16, n_head=2, slice_num=4, H=4, W=4)   # exp_plas.py:148
+    assert {"time_fc.0.weight", "time_fc.0.bias", "time_fc.2.weight", "time_fc.2.bias"} <= set(mt.state_dict().keys())
     with pytest.raises(NotImplementedError):
         PA.Physics_Attention_Structured_Mesh_2D(16, heads=2, dim_head=8, kernel=5)
     m = PA.Physics_Attention_Irregular_Mesh(16, heads=2, dim_head=8, dropout=0.1, slice_num=4)

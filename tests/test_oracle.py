@@ -116,3 +116,19 @@ def test_autoencoder_oracle_matches_golden(golden, name):
     assert O.rel_l2(x.grad, fx["dx"]) < 1e-9
     for k, g in fx["grads"].items():
         assert O.rel_l2(p[k].grad, g) < 1e-9, k
+
+
+def test_time_conditioned_model_oracle_matches_golden(golden):
+    """Time_Input=True (exp_plas.py:148,187): forward(x, fx, T) of the reference 2D model; the embedding and time_fc are fp32
+    in the reference whatever the model dtype (model/Embedding.py:81), hence the looser bound on time_fc gradients."""
+    from oracle import model as OM
+    fx = golden("model_2d_time.pt")
+    kw = fx["kwargs"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state"].items()}
+    out = OM.model_forward(fx["x"], fx["fx"], sd, kw["n_layers"], kw["n_head"], grid=(kw["H"], kw["W"]), T=fx["T"])
+    assert O.rel_l2(out.detach(), fx["out"]) < TOL
+    loss = O.rel_l2_sum(out.reshape(2, -1), fx["y"].reshape(2, -1))
+    assert abs(float(loss) - float(fx["loss"])) < 1e-12
+    loss.backward()
+    for k, g in fx["grads"].items():
+        assert O.rel_l2(sd[k].grad.double(), g.double()) < (1e-5 if k.startswith("time_fc") else 1e-8), k

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._blocks import MLP, Transolver_block as _Block, init_weights
+from ._blocks import MLP, Transolver_block as _Block, init_weights, time_conditioning
 from .Physics_Attention import Physics_Attention_Irregular_Mesh  # noqa: F401
 
 
@@ -21,7 +21,7 @@ class Model(nn.Module):
         super().__init__()
         self.__name__ = 'Transolver_1D'
         if Time_Input:
-            raise NotImplementedError("Time_Input=True (timestep embedding, exp_plas only) is outside the B200 hot path scope")
+            self.time_fc = nn.Sequential(nn.Linear(n_hidden, n_hidden), nn.SiLU(), nn.Linear(n_hidden, n_hidden))
         self.ref, self.unified_pos = ref, unified_pos
         self.Time_Input, self.n_hidden, self.space_dim = Time_Input, n_hidden, space_dim
         in_dim = fun_dim + (ref * ref if unified_pos else space_dim)
@@ -42,12 +42,12 @@ class Model(nn.Module):
         return torch.sqrt(((x[:, :, None, :] - lattice) ** 2).sum(-1)).contiguous()
 
     def forward(self, x, fx, T=None):
-        if T is not None:
-            raise NotImplementedError("time-conditioned forward is outside the B200 hot path scope")
         if self.unified_pos:
             x = self.get_grid(x, x.shape[0])
         fx = self.preprocess(torch.cat((x, fx), -1) if fx is not None else x)
         fx = fx + self.placeholder[None, None, :]   # irregular model adds it unconditionally (reference :148)
+        if T is not None:
+            fx = fx + time_conditioning(self.time_fc, T, self.n_hidden)
         for block in self.blocks:
             fx = block(fx)
         return fx

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._blocks import MLP, Transolver_block as _Block, init_weights
+from ._blocks import MLP, Transolver_block as _Block, init_weights, time_conditioning
 from .Physics_Attention import Physics_Attention_Structured_Mesh_2D  # noqa: F401  (re-exported like the reference)
 
 
@@ -23,7 +23,7 @@ class Model(nn.Module):
         super().__init__()
         self.__name__ = 'Transolver_2D'
         if Time_Input:
-            raise NotImplementedError("Time_Input=True (timestep embedding, exp_plas only) is outside the B200 hot path scope")
+            self.time_fc = nn.Sequential(nn.Linear(n_hidden, n_hidden), nn.SiLU(), nn.Linear(n_hidden, n_hidden))
         self.H, self.W, self.ref, self.unified_pos = H, W, ref, unified_pos
         self.Time_Input, self.n_hidden, self.space_dim = Time_Input, n_hidden, space_dim
         in_dim = fun_dim + (ref * ref if unified_pos else space_dim)
@@ -51,8 +51,6 @@ class Model(nn.Module):
         return d.reshape(1, self.H, self.W, self.ref * self.ref).repeat(batchsize, 1, 1, 1).contiguous()
 
     def forward(self, x, fx, T=None):
-        if T is not None:
-            raise NotImplementedError("time-conditioned forward is outside the B200 hot path scope")
         if self.unified_pos:
             if self.pos.device != x.device:
                 self.pos = self.pos.to(x.device)
@@ -61,6 +59,8 @@ class Model(nn.Module):
             fx = self.preprocess(torch.cat((x, fx), -1))
         else:
             fx = self.preprocess(x) + self.placeholder[None, None, :]
+        if T is not None:
+            fx = fx + time_conditioning(self.time_fc, T, self.n_hidden)
         for block in self.blocks:
             fx = block(fx)
         return fx

@@ -74,6 +74,26 @@ class Transolver_block(nn.Module):
         return fx
 
 
+def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    """sinusoidal embedding of (possibly fractional) time indices - reference model/Embedding.py:67-85 (fp32, cos | sin)"""
+    import math
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / half)
+    args = timesteps[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[..., :1])], dim=-1)
+    return emb
+
+
+def time_conditioning(time_fc: nn.Module, T: torch.Tensor, n_hidden: int) -> torch.Tensor:
+    """Time_Input=True (exp_plas.py:148,187): time_fc(timestep_embedding(T)) for T [B,1] -> [B,1,n_hidden], broadcast over the
+    mesh points by the caller (the reference repeats the embedding N times BEFORE the two Linears:
+    model/Transolver_Structured_Mesh_2D.py:212-215; per-row Linears commute with the repeat).  A few [B, n_hidden] torch ops
+    outside the attention path."""
+    return time_fc(timestep_embedding(T, n_hidden))
+
+
 def init_weights(module: nn.Module):
     """same distributions as the reference `_init_weights` (Transolver_Structured_Mesh_2D.py:174-181):
     Linear ~ trunc_normal(std 0.02), zero bias; LayerNorm affine = (1, 0); Conv2d keeps the torch default."""
