@@ -73,3 +73,22 @@ def test_no_cpu_path():
     m = Physics_Attention_Irregular_Mesh(16, heads=2, dim_head=8, slice_num=4)
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(torch.randn(1, 5, 16))
+
+
+def test_host_side_schedulers_fill_whole_waves(lib):
+    """pure host logic (no GPU): CTAs per (batch, head) of the slice kernels and the split-K factor of the token-contraction
+    GEMM are chosen against the 148-SM wave size; shape predicates of the tensor-core kernels."""
+    from transformerbasednavierstokesolver_b200 import ops
+    g = lib.tbns_slice_groups(20, 4096, 8)              # bench shape: 160 (b,h) pairs, 32 chunks of 128 tokens each
+    assert 1 <= g <= 32
+    ctas = 160 * g
+    assert ctas / (-(-ctas // 296) * 296) > 0.9         # two-CTA-per-SM backward kernel: >= 90 % of whole waves
+    assert lib.tbns_slice_groups(1, 100, 1) == 1        # one chunk: nothing to split
+    for tiles, kblocks in ((2, 1280), (36, 1280), (40, 64), (1, 16)):
+        s = ops._wgrad_split(tiles, kblocks)
+        assert 1 <= s <= max(1, kblocks // 4)            # at least four 64-token k-blocks per CTA
+    assert ops._wgrad_split(36, 1280) * 36 <= 148        # conv wgrad at the bench shape: a single wave
+    assert lib.tbns_gemm_tc_supported(256, 512, 9) == 1 and lib.tbns_gemm_tc_supported(74, 512, 1) == 0
+    assert lib.tbns_gemm_tc_wgrad_supported(256, 512, 9) == 1 and lib.tbns_gemm_tc_wgrad_supported(100, 512, 1) == 0
+    assert lib.tbns_pa_slice_tc_supported(32, 32) == 1 and lib.tbns_pa_slice_tc_supported(8, 32) == 0
+    assert lib.tbns_ln_linear1_supported(256) == 1 and lib.tbns_ln_linear1_supported(96) == 0
