@@ -96,6 +96,21 @@ def pa_autoencoder(name, seed, dim, heads, dim_head, G, Hg, Wg, B):
                os.path.join(OUT, name))
 
 
+def pa_structured3d(name, seed, dim, heads, dim_head, G, Hg, Wg, Dg, B):
+    PA = ref.physics_attention()
+    torch.manual_seed(seed)
+    m = PA.Physics_Attention_Structured_Mesh_3D(dim, heads=heads, dim_head=dim_head, dropout=0.0, slice_num=G, H=Hg, W=Wg, D=Dg)
+    with torch.no_grad():
+        m.in_project_slice.weight.mul_(3.0)
+        m.in_project_slice.bias.normal_(0, 0.3)
+        m.temperature.copy_(torch.linspace(0.08, 1.2, heads).reshape(1, heads, 1, 1))   # first head below the clamp bound
+    x = torch.randn(B, Hg * Wg * Dg, dim)
+    fx = _run(m, [x], seed)
+    fx["kwargs"] = dict(dim=dim, heads=heads, dim_head=dim_head, dropout=0.0, slice_num=G, H=Hg, W=Wg, D=Dg)
+    fx["kind"] = "Physics_Attention_Structured_Mesh_3D"
+    torch.save(fx, os.path.join(OUT, name))
+
+
 def block(name, seed, structured, hidden, heads, G, last, B, Hg=None, Wg=None, N=None, mlp_ratio=1, out_dim=1):
     torch.manual_seed(seed)
     if structured:
@@ -246,6 +261,7 @@ def main():
     block("block_irregular_last.pt", 23, False, hidden=32, heads=2, G=16, last=True, B=1, N=41, mlp_ratio=2)
     pa_autoencoder("pa_autoencoder_small.pt", 15, dim=32, heads=4, dim_head=8, G=8, Hg=6, Wg=5, B=2)
     pa_autoencoder("pa_autoencoder_head1.pt", 16, dim=32, heads=1, dim_head=32, G=16, Hg=7, Wg=4, B=1)   # shipped encoder checkpoints' shape
+    pa_structured3d("pa_structured3d_small.pt", 17, dim=16, heads=2, dim_head=8, G=8, Hg=4, Wg=3, Dg=5, B=2)
     ckpt_block("pa_ckpt_ep400_block3.pt", 31)
     model_2d("model_2d_unified.pt", 41, unified_pos=1)
     model_2d("model_2d_plainpos.pt", 42, unified_pos=0)

@@ -270,6 +270,24 @@ def ae_decode(code, w, p: dict):
     return deslice_out_fwd(w, P, p["to_out.0.bias"])
 
 
+# ------------------------------------------------------------------------------------------------
+# structured 3D variant (Physics_Attention_Structured_Mesh_3D, model/Physics_Attention.py:232-288): Conv3d 3x3x3 / pad 1
+# projections on tokens ordered n = (h*W + w)*D + d; everything after the projections is the 2D algebra (temperature
+# clamped).  Differentiable torch (library conv3d): parity tests take its gradients with autograd in fp64.
+# ------------------------------------------------------------------------------------------------
+def pa3d_forward(x, p: dict, heads: int, grid3):
+    Hg, Wg, Dg = grid3
+    B, N, C = x.shape
+    x5 = x.reshape(B, Hg, Wg, Dg, C).permute(0, 4, 1, 2, 3)
+    conv = torch.nn.functional.conv3d
+    xm = conv(x5, p["in_project_x.weight"], p["in_project_x.bias"], padding=1).permute(0, 2, 3, 4, 1).reshape(B, N, -1)
+    fm = conv(x5, p["in_project_fx.weight"], p["in_project_fx.bias"], padding=1).permute(0, 2, 3, 4, 1).reshape(B, N, -1)
+    XF = torch.cat([xm, fm], -1)
+    w, s, Tt = slice_fwd(XF, p["in_project_slice.weight"], p["in_project_slice.bias"], p["temperature"], heads, True)
+    st = token_attn_fwd(s, Tt, p["to_q.weight"], p["to_k.weight"], p["to_v.weight"], p["to_out.0.weight"])
+    return deslice_out_fwd(w, st["P"], p["to_out.0.bias"])
+
+
 def pa_backward(dout, p: dict, sv: dict):
     """returns (dx, grads dict keyed like PA_KEYS)."""
     dw, dP, dbo = deslice_out_bwd(dout, sv["w"], sv["st"]["P"])

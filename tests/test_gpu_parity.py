@@ -480,3 +480,48 @@ def test_autoencoder_model_encode_decode_bf16_vs_oracle(dev):
     assert tuple(model.get_attention_slice().shape) == (2, 4, 256, 32)
     out.sum().backward()   # gradients flow through decode, the projected cache and encode
     assert all(p_.grad is not None and bool(torch.isfinite(p_.grad).all()) for p_ in blk.parameters())
+
+
+def test_3d_attention_matches_reference_golden(dev, golden):
+    """Physics_Attention_Structured_Mesh_3D (model/Physics_Attention.py:232-288) in fp32 mode against the live-reference golden:
+    output, input gradient and every parameter gradient (Conv3d weights come back in [out, in, 3, 3, 3] layout)."""
+    from transformerbasednavierstokesolver_b200.model import Physics_Attention as PA
+    fx = golden("pa_structured3d_small.pt")
+    m = PA.Physics_Attention_Structured_Mesh_3D(**fx["kwargs"])
+    m.load_state_dict({k: v.float() for k, v in fx["state"].items()})
+    m.precision = "fp32"
+    m = m.to(dev)
+    x = fx["inputs"][0].float().to(dev).requires_grad_(True)
+    out = m(x)
+    assert O.rel_l2(out.detach().cpu(), fx["out"]) < FP32_OUT_TOL
+    out.backward(fx["dout"].float().to(dev))
+    assert O.rel_l2(x.grad.cpu(), fx["dinputs"][0]) < 1e-4
+    for k, p in m.named_parameters():
+        g = fx["grads"][k]
+        if float(g.abs().max()) == 0.0:
+            assert float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert O.rel_l2(p.grad.cpu(), g) < 1e-4, k
+
+
+def test_3d_model_bf16_forward_backward(dev):
+    """Transolver_Structured_Mesh_3D.Model at a tensor-core shape (n_hidden 128, 4 heads of 32, 8x8x8 mesh): bf16 mode against the
+    fp32 mode of the same weights, gradients finite."""
+    import transformerbasednavierstokesolver_b200 as pkg
+    from transformerbasednavierstokesolver_b200.model import Transolver_Structured_Mesh_3D as M3
+    torch.manual_seed(41)
+    try:
+        model = M3.Model(space_dim=3, n_layers=2, n_hidden=128, n_head=4, fun_dim=2, out_dim=1, slice_num=32, ref=2, unified_pos=1,
+                         H=8, W=8, D=8).to(dev)
+        x = torch.rand(2, 512, 3, device=dev)
+        f = torch.randn(2, 512, 2, device=dev)
+        pkg.set_default_precision("fp32")
+        with torch.no_grad():
+            ref = model(x, f)
+        pkg.set_default_precision("bf16")
+        out = model(x, f)
+        assert O.rel_l2(out.detach().cpu(), ref.cpu()) < 1e-2
+        out.square().sum().backward()
+        assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for n, p in model.named_parameters() if n != "placeholder")
+    finally:
+        pkg.set_default_precision("bf16")

@@ -18,9 +18,8 @@ def test_registry_keys_match_reference():
                       ("Transolver_Structured_Mesh2D_Encoder", Transolver_Structured_Mesh2D_Encoder)):
         assert model_dict.get_model(types.SimpleNamespace(model=name)) is mod
         assert hasattr(mod, "Model")
-    for name in ("Transolver_Structured_Mesh_3D",):   # registered by the reference, out of scope here
-        with pytest.raises(NotImplementedError):
-            model_dict.get_model(types.SimpleNamespace(model=name))
+    from transformerbasednavierstokesolver_b200.model import Transolver_Structured_Mesh_3D
+    assert model_dict.get_model(types.SimpleNamespace(model="Transolver_Structured_Mesh_3D")) is Transolver_Structured_Mesh_3D
     with pytest.raises(KeyError):
         model_dict.get_model(types.SimpleNamespace(model="Transolver_2D"))   # exp_ns.py's default is not a key in the reference either
 
@@ -89,3 +88,19 @@ def test_autoencoder_module_contract(golden):
             "preprocess.linear_post.bias"} <= keys and "blocks.0.mlp2.weight" not in keys
     assert model.get_attention_slice() is None
     assert model.blocks[0].decode(torch.zeros(1)) is None          # reference prints and returns None for a non-last block
+
+
+def test_3d_module_contract(golden):
+    """Physics_Attention_Structured_Mesh_3D / Transolver_Structured_Mesh_3D.Model: parameter names and shapes of the reference
+    (model/Physics_Attention.py:232-258, model/Transolver_Structured_Mesh_3D.py:78-145), grid-mismatch error."""
+    from transformerbasednavierstokesolver_b200.model import Transolver_Structured_Mesh_3D as M3
+    fx = golden("pa_structured3d_small.pt")
+    m = PA.Physics_Attention_Structured_Mesh_3D(**fx["kwargs"])
+    assert set(m.state_dict().keys()) == set(fx["state"].keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(fx["state"][k].shape), k
+    assert (m.H, m.W, m.D, m.dim_head) == (4, 3, 5, 8) and isinstance(m.in_project_x, torch.nn.Conv3d)
+    model = M3.Model(space_dim=3, n_layers=2, n_hidden=16, n_head=2, fun_dim=1, out_dim=1, slice_num=4, ref=2, unified_pos=1, H=3, W=4, D=2)
+    sd = model.state_dict()
+    assert tuple(sd["preprocess.linear_pre.0.weight"].shape) == (32, 1 + 8) and "blocks.1.mlp2.weight" in sd and "placeholder" in sd
+    assert tuple(model.pos.shape) == (1, 3, 4, 2, 8)

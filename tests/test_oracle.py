@@ -132,3 +132,20 @@ def test_time_conditioned_model_oracle_matches_golden(golden):
     loss.backward()
     for k, g in fx["grads"].items():
         assert O.rel_l2(sd[k].grad.double(), g.double()) < (1e-5 if k.startswith("time_fc") else 1e-8), k
+
+
+def test_3d_oracle_matches_golden(golden):
+    """Physics_Attention_Structured_Mesh_3D (model/Physics_Attention.py:232-288): oracle forward and its autograd gradients"""
+    fx = golden("pa_structured3d_small.pt")
+    kw = fx["kwargs"]
+    p = {k: v.clone().requires_grad_(True) for k, v in fx["state"].items()}
+    x = fx["inputs"][0].clone().requires_grad_(True)
+    out = O.pa3d_forward(x, p, kw["heads"], (kw["H"], kw["W"], kw["D"]))
+    assert O.rel_l2(out.detach(), fx["out"]) < TOL
+    out.backward(fx["dout"])
+    assert O.rel_l2(x.grad, fx["dinputs"][0]) < 1e-9
+    for k, g in fx["grads"].items():
+        if float(g.abs().max()) == 0.0:
+            assert float(p[k].grad.abs().max()) == 0.0, k
+        else:
+            assert O.rel_l2(p[k].grad, g) < 1e-9, k

@@ -6,6 +6,8 @@ names / shapes (so `state_dict()` round-trips with reference checkpoints) and `f
   Physics_Attention_Structured_Mesh_2D    reference model/Physics_Attention.py:60-119
   Physics_Attention_Structured_Mesh_2D_Auto_Encoder   reference model/Physics_Attention.py:122-227 (encode / decode /
                                           reconstruct_fx on a cached, differentiable slice-weight tensor)
+  Physics_Attention_Structured_Mesh_3D    reference model/Physics_Attention.py:232-288 (Conv3d projections as three passes
+                                          of the 2D implicit-GEMM kernels over H-shifted planes)
 but `forward` runs the sm_100a kernels of libtbns through `ops.PhysicsAttentionFn` (custom backward).
 """
 from __future__ import annotations
@@ -179,3 +181,46 @@ class Physics_Attention_Structured_Mesh_2D_Auto_Encoder(Physics_Attention_Struct
             raise RuntimeError("reconstruct_fx() needs cached slice weights: call encode(x, cache_slice=True) first")
         self._w = ops.SliceLinearFn.apply(self._w, self.project_slice.weight, self.project_slice.bias)
         return self.decode(code)
+
+
+class Physics_Attention_Structured_Mesh_3D(_PhysicsAttentionBase):
+    """for structured meshes in 3D space (reference :232-288): Conv3d 3x3x3 projections on tokens n = (h*W + w)*D + d,
+    temperature clamped to [0.1, 5] (:268).  `D` is the mesh depth as in the reference (the head width is `dim_head`)."""
+    structured = True
+
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0., slice_num=32, H=32, W=32, D=32, kernel=3):
+        super().__init__()
+        if kernel != 3:
+            raise NotImplementedError("only kernel=3 is supported (the reference never passes another value)")
+        self.H, self.W, self.D = H, W, D
+        self._build(dim, heads, dim_head, dropout, slice_num, lambda i, o: nn.Conv3d(i, o, kernel, 1, kernel // 2))
+        self._pack3_key = None
+        self._pack3 = None
+
+    def _packed3(self):
+        px, pfx = self.in_project_x, self.in_project_fx
+        key = (px.weight.data_ptr(), px.weight._version, px.bias._version, pfx.weight.data_ptr(), pfx.weight._version,
+               pfx.bias._version, px.weight.device)
+        if key != self._pack3_key:
+            with torch.no_grad():
+                bx, bfx = px.bias.detach().contiguous(), pfx.bias.detach().contiguous()
+                self._pack3 = [ops.pack_proj_weights(px.weight.detach()[:, :, kh].contiguous(), bx,
+                                                     pfx.weight.detach()[:, :, kh].contiguous(), bfx) for kh in range(3)]
+            self._pack3_key = key
+        return self._pack3
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("Physics-Attention (B200) has no CPU path: move the module and its input to a CUDA device")
+        if self.training and self.dropout.p > 0.0:
+            raise NotImplementedError("dropout > 0 in training mode is not supported by the fused kernels")
+        B, N, C = x.shape
+        if N != self.H * self.W * self.D:
+            raise RuntimeError(f"shape '[{B}, {self.H}, {self.W}, {self.D}, {C}]' is invalid for input of size {B * N * C}")
+        prec = ops.PRECISIONS[self.precision or config.get_default_precision()]
+        lin = self.to_out[0]
+        XF = ops.Conv3dProjFn.apply(x.float(), self.in_project_x.weight, self.in_project_x.bias, self.in_project_fx.weight,
+                                    self.in_project_fx.bias, self._packed3(), (self.H, self.W, self.D), prec)
+        code, w = ops.XFEncodeFn.apply(XF, self.temperature, self.in_project_slice.weight, self.in_project_slice.bias,
+                                       self.to_q.weight, self.to_k.weight, self.to_v.weight, lin.weight, self.heads, True)
+        return ops.PaDecodeFn.apply(code, w, lin.weight, lin.bias, prec)

@@ -621,27 +621,41 @@ def pa_encode_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, heads: i
     else:
         gemm(M=B * N, N=I2, K=C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=C_, b_kind=0, C=XF, ldc=I2, bias=bcat, precision=precision,
              tag="proj_fprop")
+    O, w, saved6 = _xf_encode_forward(XF, B, N, temperature, Ws, bs, Wq, Wk, Wv, Wo, heads, structured)
+    return O, w, (XF, *saved6, x16 if tc else x)
+
+
+def _xf_encode_forward(XF, B, N, temperature, Ws, bs, Wq, Wk, Wv, Wo, heads: int, clamp: bool):
+    """slice weights (exact SIMT kernel, fp32 output) + token attention from the projected features XF [B*N, 2I]
+    -> (O [B,H,G,D], w [B,N,H*G], (s, tok, q, k, v, A))"""
+    lib = _lib.load()
+    I = XF.shape[1] // 2
+    H = heads
+    D = I // H
+    G = Ws.shape[0]
+    Cout = Wo.shape[0]
+    HG = H * G
+    f32 = dict(device=XF.device, dtype=torch.float32)
+    st = _stream()
     groups = lib.tbns_slice_groups(B, N, H)
     w = torch.empty(B, N, HG, **f32)
     part = torch.empty(B * H * groups * G * (D + 1), **f32)
-    check(lib.tbns_pa_slice_fwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w), None, _p(part), B, N, H, D, G, int(structured), st),
+    check(lib.tbns_pa_slice_fwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w), None, _p(part), B, N, H, D, G, int(clamp), st),
           "tbns_pa_slice_fwd")
     s = torch.empty(B, H, G, **f32)
     Tt, tok, q, k, v, O = (torch.empty(B, H, G, D, **f32) for _ in range(6))
     A = torch.empty(B, H, G, G, **f32)
-    P = torch.empty(B, HG, Cout, **f32)   # by-product of the token kernel (O.Wo_h^T), unused by encode
+    P = torch.empty(B, HG, Cout, **f32)   # by-product of the token kernel (O.Wo_h^T), unused here
     check(lib.tbns_pa_token_attn_fwd(_p(part), groups, _p(Wq), _p(Wk), _p(Wv), _p(Wo), _p(s), _p(Tt), _p(tok), _p(q), _p(k), _p(v),
                                      _p(A), _p(O), _p(P), None, None, B, H, D, G, Cout, st), "tbns_pa_token_attn_fwd")
     _count(2)
-    return O, w, (XF, s, tok, q, k, v, A, x16 if tc else x)
+    return O, w, (s, tok, q, k, v, A)
 
 
-def pa_encode_backward(dO, dw, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, saved, heads: int, grid, precision: int,
-                       Wd16=None):
-    """gradients of encode w.r.t. its input and parameters from (dO [B,H,G,D] | None, dw [B,N,H*G] | None)"""
+def _xf_encode_backward(dO, dw, XF, B, N, temperature, Ws, bs, Wq, Wk, Wv, saved6, heads: int, clamp: bool, want16: bool):
+    """backward of _xf_encode_forward from (dO | None, dw | None) -> dXF (fp32, or bf16 when want16) and parameter gradients"""
     lib = _lib.load()
-    XF, s, tok, q, k, v, A, xs = saved
-    B, N, C_ = xshape
+    s, tok, q, k, v, A = saved6
     I2 = XF.shape[1]
     I = I2 // 2
     H = heads
@@ -651,10 +665,6 @@ def pa_encode_backward(dO, dw, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk
     dev = XF.device
     f32 = dict(device=dev, dtype=torch.float32)
     st = _stream()
-    structured = grid is not None
-    taps = 9 if structured else 1
-    Hg, Wg = grid if structured else (1, N)
-    tc = xs.dtype == torch.bfloat16
     groups = lib.tbns_slice_groups(B, N, H)
     # token attention backward from dO (SURVEY.md §8 a-bwd; oracle token_attn_bwd without the to_out fold)
     if dO is None:
@@ -678,20 +688,36 @@ def pa_encode_backward(dO, dw, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk
         ds = (-(dtok * tok).sum(-1) * inv).contiguous()
     dw = torch.zeros(B, N, HG, **f32) if dw is None else dw.contiguous()
     # slice backward (exact SIMT kernel: fp32 dw in, fp32 or bf16 dXF out)
-    dXF = None if tc else torch.empty(B * N, I2, **f32)
-    dXF16 = torch.empty(B * N, I2, device=dev, dtype=torch.bfloat16) if tc else None
+    dXF = None if want16 else torch.empty(B * N, I2, **f32)
+    dXF16 = torch.empty(B * N, I2, device=dev, dtype=torch.bfloat16) if want16 else None
     dWs_part = torch.empty(B * H * groups, G * (D + 1), **f32)
     dtau_part = torch.empty(B * H * groups, **f32)
     dbcat_part = torch.empty(B * groups, H * 2 * D, **f32)
     check(lib.tbns_pa_slice_bwd(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(dw), _p(dTt), _p(ds), _p(dXF), _p(dXF16), _p(dWs_part),
-                                _p(dtau_part), _p(dbcat_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd")
+                                _p(dtau_part), _p(dbcat_part), B, N, H, D, G, int(clamp), st), "tbns_pa_slice_bwd")
     dbc = reduce_rows(dbcat_part, B * groups, H * 2 * D).view(H, 2, D)
     dbx, dbfx = dbc[:, 0, :].reshape(I), dbc[:, 1, :].reshape(I)
     dWsb = reduce_rows(dWs_part, B * H * groups, G * (D + 1)).view(G, D + 1)
     dWs, dbs = dWsb[:, :D].contiguous(), dWsb[:, D].contiguous()
     dtemp = torch.empty(H, **f32)
-    check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, groups, int(structured), st), "tbns_pa_dtau_finish")
+    check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, groups, int(clamp), st), "tbns_pa_dtau_finish")
     _count(2)
+    return dXF, dXF16, dict(temperature=dtemp.view(1, H, 1, 1), bx=dbx, bfx=dbfx, Ws=dWs, bs=dbs, Wq=dWq, Wk=dWk, Wv=dWv)
+
+
+def pa_encode_backward(dO, dw, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, saved, heads: int, grid, precision: int,
+                       Wd16=None):
+    """gradients of encode w.r.t. its input and parameters from (dO [B,H,G,D] | None, dw [B,N,H*G] | None)"""
+    XF, s, tok, q, k, v, A, xs = saved
+    B, N, C_ = xshape
+    I2 = XF.shape[1]
+    I = I2 // 2
+    f32 = dict(device=XF.device, dtype=torch.float32)
+    structured = grid is not None
+    taps = 9 if structured else 1
+    Hg, Wg = grid if structured else (1, N)
+    tc = xs.dtype == torch.bfloat16
+    dXF, dXF16, g = _xf_encode_backward(dO, dw, XF, B, N, temperature, Ws, bs, Wq, Wk, Wv, (s, tok, q, k, v, A), heads, structured, tc)
     # projections: dgrad, wgrad
     dx = torch.empty(B, N, C_, **f32)
     dWx = torch.empty(Wx_shape, **f32)
@@ -709,7 +735,8 @@ def pa_encode_backward(dO, dw, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk
              tag="proj_dgrad")
         gemm(M=C_, N=I2, K=B * N, A=xs, lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, Cin=C_, precision=precision,
              split_k=_split_k(C_, I2, B * N), scatter=(dWx, dWfx), I=I, taps=1, tag="proj_wgrad")
-    return dx, dict(temperature=dtemp.view(1, H, 1, 1), Wx=dWx, bx=dbx, Wfx=dWfx, bfx=dbfx, Ws=dWs, bs=dbs, Wq=dWq, Wk=dWk, Wv=dWv)
+    g.update(Wx=dWx, Wfx=dWfx)
+    return dx, g
 
 
 class PaEncodeFn(torch.autograd.Function):
@@ -824,6 +851,107 @@ class SliceLinearFn(torch.autograd.Function):
              split_k=_split_k(G, G, M))
         dbp = colsum(dout, M, G)
         return dw, dWp, dbp
+
+
+# ------------------------------------------------------------------------------------------------
+# structured 3D variant (reference Physics_Attention_Structured_Mesh_3D, model/Physics_Attention.py:232-288):
+# the Conv3d 3x3x3 projections run as three passes of the 2D implicit-GEMM kernels, the rest is XF -> encode -> decode.
+# ------------------------------------------------------------------------------------------------
+class XFEncodeFn(torch.autograd.Function):
+    """(slice tokens after attention O, slice weights w) from already projected features XF [B,N,2I]"""
+
+    @staticmethod
+    def forward(ctx, XF, temperature, Ws, bs, Wq, Wk, Wv, Wo, heads, clamp):
+        _begin_forward()
+        B, N, I2 = XF.shape
+        XF2 = XF.contiguous().view(B * N, I2)
+        temperature_c = temperature.contiguous()
+        Ws, bs, Wq, Wk, Wv, Wo = (t.contiguous() for t in (Ws, bs, Wq, Wk, Wv, Wo))
+        _chk(XF2, temperature_c, Ws, bs, Wq, Wk, Wv, Wo)
+        O, w, saved6 = _xf_encode_forward(XF2, B, N, temperature_c, Ws, bs, Wq, Wk, Wv, Wo, heads, clamp)
+        ctx.save_for_backward(XF2, temperature_c, Ws, bs, Wq, Wk, Wv, *saved6)
+        ctx.cfg = (B, N, heads, clamp)
+        return O, w
+
+    @staticmethod
+    def backward(ctx, dO, dw):
+        B, N, heads, clamp = ctx.cfg
+        XF2, temperature, Ws, bs, Wq, Wk, Wv, *saved6 = ctx.saved_tensors
+        dXF, _, g = _xf_encode_backward(dO, dw, XF2, B, N, temperature, Ws, bs, Wq, Wk, Wv, tuple(saved6), heads, clamp, False)
+        return dXF.view(B, N, -1), g["temperature"], g["Ws"], g["bs"], g["Wq"], g["Wk"], g["Wv"], None, None, None
+
+
+class Conv3dProjFn(torch.autograd.Function):
+    """XF = [in_project_x(x) | in_project_fx(x)] for the Conv3d(3x3x3, pad 1) pair of the 3D module (reference :246-247,
+    :264-267; tokens n = (h*W + w)*D + d).  The (W, D) planes are the images of the 2D implicit-GEMM kernels (B*H of them);
+    the kernel's three H taps are three passes over H-shifted copies of the zero-padded input that accumulate in place
+    (bias in the first pass, `residual = XF` afterwards).  packs[kh] = pack_proj_weights of the kh-th (kW, kD) weight plane."""
+
+    @staticmethod
+    def forward(ctx, x, Wx, bx, Wfx, bfx, packs, grid3, precision):
+        _begin_forward()
+        x = x.contiguous()
+        _chk(x)
+        B, N, C_ = x.shape
+        Hg, Wg, Dg = grid3
+        I2 = packs[0][0].shape[0]
+        tc = (precision == TBNS_PREC_BF16 and all(pk[3] is not None and pk[4] is not None for pk in packs)
+              and tc_supported(C_, I2, 9) and tc_supported(I2, C_, 9) and wgrad_supported(C_, I2, 9))
+        xp = torch.zeros(B, Hg + 2, Wg, Dg, C_, device=x.device, dtype=torch.float32)
+        xp[:, 1:Hg + 1] = x.view(B, Hg, Wg, Dg, C_)
+        XF = torch.empty(B * N, I2, device=x.device, dtype=torch.float32)
+        planes = []
+        for kh in range(3):
+            A = xp[:, kh:kh + Hg].contiguous()
+            if tc:
+                A = cast_bf16(A)
+            planes.append(A)
+            Wf, _, bcat, Wf16, _ = packs[kh]
+            first = kh == 0
+            if tc:
+                gemm_tc(A, Wf16, XF, bcat if first else None, B * Hg, Wg, Dg, C_, I2, 9, 0, residual=None if first else XF,
+                        tag="proj3d_fprop")
+            else:
+                gemm(M=B * N, N=I2, K=9 * C_, A=A, lda=C_, a_kind=0, B=Wf, ldb=9 * C_, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Wg,
+                     Wg=Dg, Cin=C_, bias=bcat if first else None, residual=None if first else XF, ldr=I2, precision=precision,
+                     tag="proj3d_fprop")
+        ctx.save_for_backward(*planes)
+        ctx.packs = packs
+        ctx.cfg = (B, N, C_, grid3, I2, precision, tc, tuple(Wx.shape))
+        return XF.view(B, N, I2)
+
+    @staticmethod
+    def backward(ctx, dXF):
+        B, N, C_, (Hg, Wg, Dg), I2, precision, tc, wshape = ctx.cfg
+        planes = ctx.saved_tensors
+        I = I2 // 2
+        dev = dXF.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        dXF = dXF.contiguous().view(B * N, I2)
+        dbcat = colsum(dXF, B * N, I2)
+        dXF16 = cast_bf16(dXF) if tc else None
+        dxp = torch.zeros(B, Hg + 2, Wg, Dg, C_, **f32)
+        dWx = torch.empty(wshape, **f32)
+        dWfx = torch.empty(wshape, **f32)
+        for kh in range(3):
+            _, Wd, _, _, Wd16 = ctx.packs[kh]
+            dpl = torch.empty(B * N, C_, **f32)
+            dWx_k = torch.empty(wshape[0], wshape[1], 3, 3, **f32)
+            dWfx_k = torch.empty(wshape[0], wshape[1], 3, 3, **f32)
+            if tc:
+                gemm_tc(dXF16, Wd16, dpl, None, B * Hg, Wg, Dg, I2, C_, 9, 1, tag="proj3d_dgrad")
+                gemm_tc_wgrad(planes[kh], dXF16, B * Hg, Wg, Dg, C_, I2, taps=9, scatter=(dWx_k, dWfx_k), I=I, tag="proj3d_wgrad")
+            else:
+                gemm(M=B * N, N=C_, K=9 * I2, A=dXF, lda=I2, a_kind=0, B=Wd, ldb=9 * I2, b_kind=0, C=dpl, ldc=C_, conv_mode=1, Hg=Wg,
+                     Wg=Dg, Cin=I2, flip=1, precision=precision, tag="proj3d_dgrad")
+                gemm(M=9 * C_, N=I2, K=B * N, A=planes[kh], lda=C_, a_kind=1, B=dXF, ldb=I2, b_kind=1, conv_mode=2, Hg=Wg, Wg=Dg,
+                     Cin=C_, precision=precision, split_k=_split_k(9 * C_, I2, B * N), scatter=(dWx_k, dWfx_k), I=I, taps=9,
+                     tag="proj3d_wgrad")
+            dxp[:, kh:kh + Hg] += dpl.view(B, Hg, Wg, Dg, C_)
+            dWx[:, :, kh] = dWx_k
+            dWfx[:, :, kh] = dWfx_k
+        dx = dxp[:, 1:Hg + 1].reshape(B, N, C_)
+        return dx, dWx, dbcat[:I].contiguous(), dWfx, dbcat[I:].contiguous(), None, None, None
 
 
 class PhysicsAttentionFn(torch.autograd.Function):
