@@ -35,6 +35,8 @@ const char* tbns_last_error(void);
 int tbns_version(void);
 /* 1 when the runtime sees an sm_100 device; compute entry points fail otherwise. */
 int tbns_device_ok(void);
+/* multiProcessorCount of the current device (grid-sizing heuristics of the host side) */
+int tbns_sm_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Generic strided GEMM with the gathers/epilogues the path needs:  C[b] = epi(A[b] (M x K) * B[b] (K x N))

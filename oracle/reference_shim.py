@@ -1,7 +1,7 @@
-"""Import the *unmodified* reference modules from /root/reference (build container only).
+"""Import the *unmodified* reference modules: from /root/reference when it is mounted (build container), else from
+`oracle/_ref/` - the same files byte-compiled by `oracle/build_ref.py` (git-ignored, travels to the GPU box).
 
-TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box; callers must check
-`available()` first.  Two shims are needed:
+TEST / BASELINE INFRASTRUCTURE ONLY.  Callers must check `available()` first.  Two shims are needed:
   * `timm.models.layers.trunc_normal_` (timm is not installed) -> torch.nn.init.trunc_normal_
   * `get_grid` hard-codes `.cuda()` (model/Transolver_Structured_Mesh_2D.py:189,195): on a CPU-only
     host `torch.Tensor.cuda` is patched to identity while the model is constructed.
@@ -15,11 +15,28 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("TBNS_REFERENCE_ROOT", "/root/reference")
+_SRC_ROOT = os.environ.get("TBNS_REFERENCE_ROOT", "/root/reference")
+_PYC_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _root():
+    if os.path.isfile(os.path.join(_SRC_ROOT, "model", "Physics_Attention.py")):
+        return _SRC_ROOT
+    if os.path.isfile(os.path.join(_PYC_ROOT, "model", "Physics_Attention.pyc")):
+        return _PYC_ROOT
+    return None
+
+
+REF_ROOT = _root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "model", "Physics_Attention.py"))
+    return REF_ROOT is not None
+
+
+def kind() -> str:
+    """'source' (/root/reference mounted), 'compiled' (oracle/_ref) or 'absent'"""
+    return "absent" if REF_ROOT is None else ("source" if REF_ROOT == _SRC_ROOT else "compiled")
 
 
 def _install_shims():
@@ -34,6 +51,8 @@ def _install_shims():
         sys.modules["timm"] = timm
         sys.modules["timm.models"] = models
         sys.modules["timm.models.layers"] = layers
+    if REF_ROOT is None:
+        raise ImportError("reference not available: neither /root/reference nor oracle/_ref (run oracle/build_ref.py)")
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
 

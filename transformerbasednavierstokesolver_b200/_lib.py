@@ -73,6 +73,7 @@ _SIGS = {
     "tbns_last_error": (C.c_char_p, []),
     "tbns_version": (_i, []),
     "tbns_device_ok": (_i, []),
+    "tbns_sm_count": (_i, []),
     "tbns_gemm": (_i, [C.POINTER(GemmDesc), _fp]),
     "tbns_gemm_tc_supported": (_i, [_i, _i, _i]),
     "tbns_gemm_tc": (_i, [C.POINTER(TcDesc), _fp]),

@@ -14,7 +14,8 @@ void set_error(const char* fmt, ...) {
 }  // namespace tbns
 
 extern "C" const char* tbns_last_error(void) { return tbns::g_err; }
-extern "C" int tbns_version(void) { return 100; }
+extern "C" int tbns_version(void) { return 200; }
+extern "C" int tbns_sm_count(void) { return tbns::sm_count(); }
 extern "C" int tbns_device_ok(void) {
   int dev = 0, n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {

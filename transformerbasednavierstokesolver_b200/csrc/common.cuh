@@ -32,15 +32,37 @@ int splitk_reduce(const tbns_gemm_desc& d, cudaStream_t st);  // gemm_simt.cu
 
 #define TBNS_LAUNCH_CHECK() TBNS_CUDA(cudaGetLastError())
 
-// opt in to large dynamic shared memory once per kernel (not a stream operation: keep it out of CUDA-graph capture)
+// opt in to large dynamic shared memory once per kernel AND device (not a stream operation: keep it out of CUDA-graph
+// capture).  The attribute is per device, so the cache is indexed by the current device ordinal.
 #define TBNS_SMEM_OPT_IN(kernel, bytes)                                                                      \
   do {                                                                                                       \
-    static int _cur = -1;                                                                                    \
-    if (_cur < (int)(bytes)) {                                                                               \
+    static int _cur[TBNS_MAX_DEVICES];                                                                       \
+    int _dev = 0;                                                                                            \
+    TBNS_CUDA(cudaGetDevice(&_dev));                                                                         \
+    if (_dev < 0 || _dev >= TBNS_MAX_DEVICES) {                                                              \
+      tbns::set_error("device ordinal %d out of range", _dev);                                               \
+      return TBNS_ERR_INVALID;                                                                               \
+    }                                                                                                        \
+    if (_cur[_dev] < (int)(bytes)) {                                                                         \
       TBNS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));    \
-      _cur = (int)(bytes);                                                                                   \
+      _cur[_dev] = (int)(bytes);                                                                             \
     }                                                                                                        \
   } while (0)
+
+constexpr int TBNS_MAX_DEVICES = 64;
+
+// multiProcessorCount of the current device (cached per device)
+static inline int sm_count() {
+  static int cache[TBNS_MAX_DEVICES];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TBNS_MAX_DEVICES) return 148;
+  if (!cache[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

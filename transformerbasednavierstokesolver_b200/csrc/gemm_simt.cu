@@ -304,12 +304,12 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const tbns_gemm
 
 static void launch_splitk_reduce(const tbns_gemm_desc& d, int vecC, cudaStream_t st) {
   const long long total = (long long)d.batch * d.M * ((d.N + 3) / 4);
-  if (d.split_k >= 16 && total <= 148LL * 8 * 32) {
+  if (d.split_k >= 16 && total <= (long long)sm_count() * 8 * 32) {
     int blocks = (int)((total + 31) / 32);
     gemm_splitk_reduce_kernel<8><<<blocks, 256, 0, st>>>(d, vecC);
   } else {
     int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     gemm_splitk_reduce_kernel<1><<<blocks, 256, 0, st>>>(d, vecC);
   }
 }

@@ -794,12 +794,7 @@ template <int BN, int STAGES, int EPI>
 static int launch_tcp_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
   using S = TcpSmem<BN, STAGES>;
   TBNS_SMEM_OPT_IN((gemm_tc_persistent_kernel<BN, STAGES, EPI>), S::TOTAL);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    TBNS_CUDA(cudaGetDevice(&dev));
-    TBNS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sms = sm_count();
   const int total = m_tiles * (p.N / BN);
   const int grid = total < sms ? total : sms;
   gemm_tc_persistent_kernel<BN, STAGES, EPI><<<grid, TCP_THREADS, S::TOTAL, st>>>(tmA, tmB, p, total);
@@ -892,7 +887,7 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
   // outweighs the main loop, so run 128-wide tiles with a 3-stage ring (~99 KB) and let TWO CTAs share an SM: one CTA's
   // epilogue overlaps the other's TMA/MMA phase and twice as many epilogue warps are resident.
   const bool short_k = (d.taps * d.Cin) / TC_BK <= 8 && N % 128 == 0;
-  const int BN = short_k ? 128 : ((N % 256 == 0 && m_tiles * (N / 256) >= 148) ? 256 : (N % 128 == 0 ? 128 : 64));
+  const int BN = short_k ? 128 : ((N % 256 == 0 && m_tiles * (N / 256) >= sm_count()) ? 256 : (N % 128 == 0 ? 128 : 64));
   {
     const cuuint64_t K = (cuuint64_t)d.taps * d.Cin;
     cuuint64_t dims[3] = {K, (cuuint64_t)N, (cuuint64_t)(d.w_batched ? d.Bimg : 1)};

@@ -415,7 +415,7 @@ extern "C" size_t tbns_layernorm_bwd_ws_floats(int C) { return (size_t)LN_BWD_CT
 extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long cols, void* stream) {
   TBNS_REQUIRE(in && out && rows >= 0 && cols >= 0, "tbns_reduce_rows: bad args");
   if (cols == 0) return TBNS_OK;
-  if (rows >= 64 && cols <= 148LL * 32 * 8) {
+  if (rows >= 64 && cols <= (long long)sm_count() * 32 * 8) {
     reduce_rows_par_kernel<<<(unsigned)((cols + 31) / 32), 1024, 0, (cudaStream_t)stream>>>(in, out, rows, (int)cols, cols);
     TBNS_LAUNCH_CHECK();
     return TBNS_OK;
@@ -425,7 +425,7 @@ extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long
     colsum_partial_kernel<<<dim3((unsigned)((cols + 127) / 128), 1), 256, 0, (cudaStream_t)stream>>>(in, cols, out, rows, (int)cols, rows);
   } else {
     int blocks = (int)((cols + 127) / 128);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     reduce_rows_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(in, out, rows, cols, cols);
   }
   TBNS_LAUNCH_CHECK();

@@ -542,7 +542,8 @@ extern "C" int tbns_slice_groups(int B, int N, int H) {
   int best = 1;
   for (int g = 1; g <= nchunk; ++g) {
     const long long per = cdiv(nchunk, g);
-    const long long cost = 2 * ((bh * g + 295) / 296) * per + ((bh * g + 591) / 592) * per;
+    const long long s2 = 2LL * sm_count(), s4 = 4LL * sm_count();
+    const long long cost = 2 * ((bh * g + s2 - 1) / s2) * per + ((bh * g + s4 - 1) / s4) * per;
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best = g;
@@ -563,6 +564,7 @@ extern "C" int tbns_pa_slice_fwd(const float* XF, const float* Ws, const float* 
 #define X(d, g) if (D == d && G == g) return launch_slice_fwd<d, g>(XF, Ws, bs, temperature, w, reinterpret_cast<__nv_bfloat16*>(w16), part, B, N, H, groups, clamp, st);
   TBNS_SLICE_SHAPES(X)
 #undef X
+  set_error("tbns_pa_slice_fwd: dim_head=%d / slice_num=%d unsupported", D, G);
   return TBNS_ERR_UNSUPPORTED;
 }
 
@@ -647,6 +649,7 @@ extern "C" int tbns_pa_slice_bwd(const float* XF, const float* Ws, const float* 
 #define X(d, g) if (D == d && G == g) return launch_slice_bwd<d, g>(XF, Ws, bs, temperature, dw, dTt, ds, dXF, reinterpret_cast<__nv_bfloat16*>(dXF16), dWs_part, dtau_part, dbcat_part, B, N, H, groups, clamp, st);
   TBNS_SLICE_SHAPES(X)
 #undef X
+  set_error("tbns_pa_slice_bwd: dim_head=%d / slice_num=%d unsupported", D, G);
   return TBNS_ERR_UNSUPPORTED;
 }
 
@@ -664,7 +667,7 @@ extern "C" int tbns_pack_proj_weights(const float* Wx, const float* bx, const fl
   TBNS_REQUIRE(I > 0 && C > 0 && (taps == 1 || taps == 9), "tbns_pack_proj_weights: bad dims");
   const long long total = 2LL * I * C * taps;
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   pack_proj_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Wx, bx, Wfx, bfx, Wf, Wd, bcat, I, C, taps);
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;

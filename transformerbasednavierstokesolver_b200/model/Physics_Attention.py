@@ -22,6 +22,9 @@ class _PhysicsAttentionBase(nn.Module):
     structured = False
 
     def _build(self, dim, heads, dim_head, dropout, slice_num, proj_factory):
+        if dim_head not in (8, 16, 32, 64) or slice_num not in (4, 8, 16, 32, 64):
+            raise NotImplementedError(f"the slice kernels are built for dim_head in {{8,16,32,64}} and slice_num in {{4,8,16,32,64}} "
+                                      f"(got dim_head={dim_head}, slice_num={slice_num})")
         inner = dim_head * heads
         self.dim_head = dim_head
         self.heads = heads
@@ -45,9 +48,9 @@ class _PhysicsAttentionBase(nn.Module):
     def _packed_weights(self):
         px, pfx = self.in_project_x, self.in_project_fx
         key = (px.weight.data_ptr(), px.weight._version, px.bias._version, pfx.weight.data_ptr(), pfx.weight._version,
-               pfx.bias._version, px.weight.device)
+               pfx.bias._version, px.weight.device, ops.cache_context())
         if key != self._pack_key:
-            with torch.no_grad():
+            with torch.no_grad(), torch.cuda.device(px.weight.device):
                 self._packed = ops.pack_proj_weights(px.weight.detach().contiguous(), px.bias.detach().contiguous(),
                                                      pfx.weight.detach().contiguous(), pfx.bias.detach().contiguous())
             self._pack_key = key
@@ -200,9 +203,9 @@ class Physics_Attention_Structured_Mesh_3D(_PhysicsAttentionBase):
     def _packed3(self):
         px, pfx = self.in_project_x, self.in_project_fx
         key = (px.weight.data_ptr(), px.weight._version, px.bias._version, pfx.weight.data_ptr(), pfx.weight._version,
-               pfx.bias._version, px.weight.device)
+               pfx.bias._version, px.weight.device, ops.cache_context())
         if key != self._pack3_key:
-            with torch.no_grad():
+            with torch.no_grad(), torch.cuda.device(px.weight.device):
                 bx, bfx = px.bias.detach().contiguous(), pfx.bias.detach().contiguous()
                 self._pack3 = [ops.pack_proj_weights(px.weight.detach()[:, :, kh].contiguous(), bx,
                                                      pfx.weight.detach()[:, :, kh].contiguous(), bfx) for kh in range(3)]

@@ -79,5 +79,10 @@ class Model(nn.Module):
         if T is not None:
             fx = fx + time_conditioning(self.time_fc, T, self.n_hidden)
         for block in self.blocks:
-            fx = block(fx)
+            if self.use_checkpoint and torch.is_grad_enabled():
+                # activation checkpointing as in the reference (:186-187): the block's kernels re-run in backward
+                import torch.utils.checkpoint as checkpoint
+                fx = checkpoint.checkpoint(block, fx, use_reentrant=False)
+            else:
+                fx = block(fx)
         return fx

@@ -21,7 +21,36 @@ from . import _lib
 from ._lib import GemmDesc, TBNS_PREC_BF16, TBNS_PREC_FP32, check
 
 PRECISIONS = {"fp32": TBNS_PREC_FP32, "bf16": TBNS_PREC_BF16}
-_NUM_SMS = 148
+_SM_COUNT = {}
+
+
+def _num_sms() -> int:
+    """multiProcessorCount of the current device (148 on a B200), queried once per device; the B200 figure when no device is
+    visible (the host-side schedulers are unit-tested on CPU-only machines)"""
+    if not torch.cuda.is_available():
+        return 148
+    dev = torch.cuda.current_device()
+    n = _SM_COUNT.get(dev)
+    if n is None:
+        n = _SM_COUNT[dev] = int(torch.cuda.get_device_properties(dev).multi_processor_count)
+    return n
+
+
+def _on_device(fn):
+    """run an autograd-Function forward/backward with the tensors' device current (kernels launch on THAT device's current
+    stream even when the caller's current device is another one)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kw)
+                break
+        return fn(*args, **kw)
+    return wrapped
 
 # bookkeeping for bench.py: number of libtbns kernels launched, and (when PROFILE is a dict) CUDA-event pairs around
 # tagged launches, recorded on the launching stream
@@ -73,9 +102,10 @@ def _chk(*tensors):
 def _split_k(M: int, N: int, K: int, batch: int = 1) -> int:
     """pick a split so that small-output / long-K contractions (wgrad) still fill the 148 SMs."""
     tiles = ((M + 127) // 128) * ((N + 127) // 128) * batch
-    if tiles >= _NUM_SMS:
+    sms = _num_sms()
+    if tiles >= sms:
         return 1
-    s = (2 * _NUM_SMS + tiles - 1) // tiles
+    s = (2 * sms + tiles - 1) // tiles
     s = min(s, max(1, K // 256))
     return max(1, min(s, 64))
 
@@ -145,21 +175,56 @@ def cast_bf16(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# Derived weight copies (bf16 operands, packed projection weights) are cached per master tensor.  A cache entry is valid
+# while (a) the master's `_version` / address are unchanged, (b) the global WEIGHT GENERATION is unchanged and (c) it was
+# built in the same capture context.  (b) exists because CUDA-graph replays of the optimizer (and `.data` writes) change
+# the masters without touching `_version`: whoever mutates parameters behind autograd's back calls
+# `invalidate_weight_caches()` (train.GraphedTrainStep does after every optimizer replay, train.broadcast_parameters too).
+# (c) makes every graph capture re-record the cast / pack kernels (so replays refresh the copies from the current masters)
+# and keeps eager calls from reusing tensors that live in a graph's private pool.
+# ------------------------------------------------------------------------------------------------
 _W16_CACHE = {}
+_WEIGHT_GEN = 0
+_CAP_EPOCH = 0
+_WAS_CAPTURING = False
+
+
+def invalidate_weight_caches():
+    """call after parameters were modified in a way autograd's version counters do not see (graph replays, `.data` writes)"""
+    global _WEIGHT_GEN
+    _WEIGHT_GEN += 1
+
+
+def begin_capture():
+    """call right before a new CUDA-graph capture of code that uses this module: derived weights are rebuilt inside it"""
+    global _CAP_EPOCH
+    _CAP_EPOCH += 1
+
+
+def cache_context():
+    """(weight generation, capture tag): tag 0 = eager, otherwise the epoch of the capture in progress"""
+    global _CAP_EPOCH, _WAS_CAPTURING
+    cap = torch.cuda.is_current_stream_capturing()
+    if cap and not _WAS_CAPTURING:
+        _CAP_EPOCH += 1   # a capture nobody announced with begin_capture()
+    _WAS_CAPTURING = cap
+    return _WEIGHT_GEN, (_CAP_EPOCH if cap else 0)
 
 
 def _w16_cached(W: torch.Tensor, key_extra, build) -> torch.Tensor:
     """bf16 operand copies of weights, cached per tensor OBJECT (weak reference: a recycled address or id never matches)
-    until the fp32 master changes (optimizer step / load_state_dict bump `_version`)."""
+    until the fp32 master changes (see the validity rules above)."""
     key = (id(W),) + key_extra
+    ctx = cache_context()
     hit = _W16_CACHE.get(key)
-    if hit is not None and hit[0]() is W and hit[1] == W._version and hit[2] == W.data_ptr():
+    if hit is not None and hit[0]() is W and hit[1] == W._version and hit[2] == W.data_ptr() and hit[4] == ctx:
         return hit[3]
     with torch.no_grad():
         w16 = build()
     if len(_W16_CACHE) > 4096:
         _W16_CACHE.clear()
-    _W16_CACHE[key] = (weakref.ref(W), W._version, W.data_ptr(), w16)
+    _W16_CACHE[key] = (weakref.ref(W), W._version, W.data_ptr(), w16, ctx)
     return w16
 
 
@@ -205,9 +270,10 @@ def _wgrad_split(tiles: int, kblocks: int) -> int:
     """split-K factor of the token-contraction kernel: one CTA per SM (197 KB of shared memory each), so pick the smallest
     split whose CTA count fills whole waves of 148 SMs (>= 95 %), keeping >= 4 k-blocks per CTA."""
     best, best_eff = 1, 0.0
-    for s in range(1, max(1, min(148, kblocks // 4)) + 1):
+    sms = _num_sms()
+    for s in range(1, max(1, min(sms, kblocks // 4)) + 1):
         ctas = tiles * s
-        eff = ctas / (((ctas + _NUM_SMS - 1) // _NUM_SMS) * _NUM_SMS)
+        eff = ctas / (((ctas + sms - 1) // sms) * sms)
         if eff >= 0.95:
             return s
         if eff > best_eff + 1e-9:
@@ -323,36 +389,41 @@ def _join_side():
         torch.cuda.current_stream().wait_stream(_side())
 
 
-# bf16 copies of gradients handed from one fused backward stage to the next (producer: LayerNorm backward, consumer: the
-# tensor-core contractions of the stage autograd runs next on the very same tensor).  Keyed by storage address.
-_GRAD16 = {}
+# Side products of a fused backward stage (a bf16 copy of the gradient it returns, its column sums = the bias gradient of
+# the layer that produced the stream) are handed to the stage autograd runs next as an ATTRIBUTE OF THE RETURNED TENSOR
+# OBJECT.  PyTorch preserves the Python object of a live tensor, so the next custom Function's backward receives the very
+# same object when - and only when - autograd passes the gradient through untouched; whenever it builds a new tensor
+# (accumulation of several paths, hooks, casts) the attribute is simply absent and the consumer recomputes what it needs.
+# Nothing is keyed by address and nothing outlives the gradient tensor itself.
+HANDOFF_HITS = 0      # diagnostics (tests assert that the fused chain really hands over)
+HANDOFF_MISSES = 0
 
 
 def _stash_grad16(t: torch.Tensor, t16: Optional[torch.Tensor] = None, colsum_: Optional[torch.Tensor] = None):
-    """Every fused backward stage calls this on the gradient it returns: with side products to hand them on, without to drop
-    whatever an older tensor left under the same storage address."""
     if t16 is not None or colsum_ is not None:
-        _GRAD16[t.data_ptr()] = (t16, tuple(t.shape), t._version, colsum_)
-    else:
-        _GRAD16.pop(t.data_ptr(), None)
+        t._tbns_side = (t16, colsum_, t._version)
+    return t
 
 
 def _begin_forward():
-    """side products only live within one backward pass: any forward call ends the previous one"""
-    if _GRAD16:
-        _GRAD16.clear()
+    """kept as the single hook every forward stage calls (no global state left to reset)"""
+    return None
 
 
 def _take_grad16(t: torch.Tensor):
-    """-> (bf16 copy | None, column sums | None) left by the producer of gradient tensor `t`"""
-    e = _GRAD16.pop(t.data_ptr(), None)
-    if e is not None and e[1] == tuple(t.shape) and e[2] == t._version:
-        return e[0], e[3]
+    """-> (bf16 copy | None, column sums | None) attached by the producer of gradient tensor `t`"""
+    global HANDOFF_HITS, HANDOFF_MISSES
+    side = getattr(t, "_tbns_side", None)
+    if side is not None and side[2] == t._version:
+        HANDOFF_HITS += 1
+        return side[0], side[1]
+    HANDOFF_MISSES += 1
     return None, None
 
 
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, gamma, beta, eps):
         _begin_forward()
         x = x.contiguous()
@@ -361,6 +432,7 @@ class LayerNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         x, mean, rstd, gamma = ctx.saved_tensors
         dx, _, dg, db = layernorm_bwd(dy.contiguous(), x, mean, rstd, gamma.contiguous())
@@ -744,6 +816,7 @@ class PaEncodeFn(torch.autograd.Function):
     cached slice weights, reference :214-227)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, packed, heads, grid, precision):
         _begin_forward()
         x = x.contiguous()
@@ -758,6 +831,7 @@ class PaEncodeFn(torch.autograd.Function):
         return O, w
 
     @staticmethod
+    @_on_device
     def backward(ctx, dO, dw):
         heads, grid, precision, wshape, xshape = ctx.cfg
         temperature, Wd, Ws, bs, Wq, Wk, Wv, *saved = ctx.saved_tensors
@@ -772,6 +846,7 @@ class PaDecodeFn(torch.autograd.Function):
     """out = to_out(deslice(code, w)) = w . (code . Wo_h^T) + bo   (decode(), reference :221-227)"""
 
     @staticmethod
+    @_on_device
     def forward(ctx, code, w, Wo, bo, precision):
         _begin_forward()
         code, w, Wo, bo = code.contiguous(), w.contiguous(), Wo.contiguous(), bo.contiguous()
@@ -795,6 +870,7 @@ class PaDecodeFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         code, Wo, w, P = ctx.saved_tensors
         precision = ctx.precision
@@ -826,6 +902,7 @@ class SliceLinearFn(torch.autograd.Function):
     (reconstruct_fx(), reference :215); exact fp32 contraction (K = slice_num)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, w, Wp, bp):
         _begin_forward()
         w, Wp, bp = w.contiguous(), Wp.contiguous(), bp.contiguous()
@@ -838,6 +915,7 @@ class SliceLinearFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         w, Wp = ctx.saved_tensors
         dout = dout.contiguous()
@@ -861,6 +939,7 @@ class XFEncodeFn(torch.autograd.Function):
     """(slice tokens after attention O, slice weights w) from already projected features XF [B,N,2I]"""
 
     @staticmethod
+    @_on_device
     def forward(ctx, XF, temperature, Ws, bs, Wq, Wk, Wv, Wo, heads, clamp):
         _begin_forward()
         B, N, I2 = XF.shape
@@ -874,6 +953,7 @@ class XFEncodeFn(torch.autograd.Function):
         return O, w
 
     @staticmethod
+    @_on_device
     def backward(ctx, dO, dw):
         B, N, heads, clamp = ctx.cfg
         XF2, temperature, Ws, bs, Wq, Wk, Wv, *saved6 = ctx.saved_tensors
@@ -888,6 +968,7 @@ class Conv3dProjFn(torch.autograd.Function):
     (bias in the first pass, `residual = XF` afterwards).  packs[kh] = pack_proj_weights of the kh-th (kW, kD) weight plane."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, Wx, bx, Wfx, bfx, packs, grid3, precision):
         _begin_forward()
         x = x.contiguous()
@@ -921,6 +1002,7 @@ class Conv3dProjFn(torch.autograd.Function):
         return XF.view(B, N, I2)
 
     @staticmethod
+    @_on_device
     def backward(ctx, dXF):
         B, N, C_, (Hg, Wg, Dg), I2, precision, tc, wshape = ctx.cfg
         planes = ctx.saved_tensors
@@ -959,6 +1041,7 @@ class PhysicsAttentionFn(torch.autograd.Function):
     weights (fp32 and bf16 copies; non-differentiable, refreshed by the module when the masters change)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, x, residual, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, packed, heads, grid, precision):
         _begin_forward()
         x = x.contiguous()
@@ -975,6 +1058,7 @@ class PhysicsAttentionFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         heads, grid, precision, wshape, has_res, xshape = ctx.cfg
         temperature, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved = ctx.saved_tensors
@@ -994,6 +1078,7 @@ class AttnBlockFn(torch.autograd.Function):
     LayerNorm backward kernel and hands a bf16 copy of its result to the previous block's MLP backward."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, fx, ln_w, ln_b, eps, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, packed, heads, grid, precision):
         _begin_forward()
         fx = fx.contiguous()
@@ -1013,6 +1098,7 @@ class AttnBlockFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         heads, grid, precision, wshape, xshape = ctx.cfg
         fx, ln_w, mean, rstd, temperature, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved = ctx.saved_tensors
@@ -1035,6 +1121,7 @@ class AttnBlockFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 class LnMlpFn(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, fx, gamma, beta, W1, b1, W2, b2, eps, precision):
         _begin_forward()
         fx = fx.contiguous()
@@ -1070,6 +1157,7 @@ class LnMlpFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         fx, gamma, W1, W2, x2, mean, rstd, pre, hid = ctx.saved_tensors
         precision = ctx.precision
@@ -1131,6 +1219,7 @@ class MlpFn(torch.autograd.Function):
     multiple of 64 so the input rows are whole TMA boxes."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, inp, W1, b1, W2, b2):
         _begin_forward()
         K = inp.shape[-1]
@@ -1151,6 +1240,7 @@ class MlpFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         in16, W1, W2, pre16, hid16 = ctx.saved_tensors
         K = ctx.K
@@ -1185,6 +1275,7 @@ class LnLinearFn(torch.autograd.Function):
     through LayerNorm + the generic contraction."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, fx, gamma, beta, W, b, eps, precision):
         _begin_forward()
         fx = fx.contiguous()
@@ -1212,6 +1303,7 @@ class LnLinearFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         precision = ctx.precision
         dout = dout.contiguous()

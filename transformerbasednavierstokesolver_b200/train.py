@@ -77,8 +77,11 @@ class FlatGradients:
 def broadcast_parameters(model: torch.nn.Module, src: int = 0):
     """identical replicas: rank `src` wins (parameters and buffers)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        for t in list(model.parameters()) + list(model.buffers()):
-            dist.broadcast(t.data, src)
+        with torch.no_grad():
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.detach(), src)
+        from . import ops
+        ops.invalidate_weight_caches()   # the collective wrote into the masters behind autograd's version counters
 
 
 def teacher_forced_inputs(fx: torch.Tensor, yy: torch.Tensor, T: int, step: int = 1) -> torch.Tensor:
@@ -255,6 +258,9 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.g_stage = []
+        from . import ops
+        self._ops = ops
+        ops.begin_capture()   # derived weight copies (bf16 casts, packed projections) are re-recorded inside the graphs
         if self.nb > 1:
             pool = None
             for k in range(self.nb):
@@ -277,6 +283,7 @@ class GraphedTrainStep:
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
             self.opt.step()
+        ops.invalidate_weight_caches()
 
     # ---- staged backward (buckets > 1) -------------------------------------------------------------------------------
     def _plan_stages(self, blocks):
@@ -379,6 +386,7 @@ class GraphedTrainStep:
             self.g_fb.replay()
             self.grads.all_reduce()
         self.g_opt.replay()
+        self._ops.invalidate_weight_caches()   # the replay changed the masters without bumping their version counters
         if self.sched is not None:
             self.sched.step()     # host-side schedule; writes the new lr into the device tensor the graph reads
         return self.loss
