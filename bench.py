@@ -1,15 +1,19 @@
 #!/usr/bin/env python
 """bench.py — NS-64x64 Transolver training throughput (BASELINE.json metric) on N B200s of one node.
 
-Workload (config.workload): BASELINE.json configs[1] — Transolver_Structured_Mesh_2D, 64x64 grid, 8 layers, n_hidden 256,
-8 heads, slice_num 32, unified_pos 1, T_in = T = 10, per-GPU batch 2 (scripts/Transolver_NS.sh), bf16 operand mode,
-one optimizer step = exp_ns.py:191-218 (10 teacher-forced model calls, summed rel-L2, one backward, AdamW + OneCycleLR),
-batch sharded over ranks, gradients summed with one NCCL all-reduce.  Synthetic data, random-init weights.
+Default workload (config.workload): BASELINE.json configs[1] — Transolver_Structured_Mesh_2D, 64x64 grid, 8 layers,
+n_hidden 256, 8 heads, slice_num 32, unified_pos 1, T_in = T = 10, per-GPU batch 2 (scripts/Transolver_NS.sh), bf16 operand
+mode, one optimizer step = exp_ns.py:191-218 (10 teacher-forced model calls, summed rel-L2, one backward, AdamW +
+OneCycleLR), batch sharded over ranks, gradients summed with one NCCL all-reduce.  Synthetic data, random-init weights.
 
   python bench.py [--gpus N --steps K --warmup W]          -> one JSON line (ours)
-  python bench.py --impl reference [...]                   -> one JSON line: the reference algorithm (oracle port, torch CPU ops)
-                                                              timed on this box's host cores (kind "port": the reference is
-                                                              Python and cannot travel to the GPU box)
+  python bench.py --impl reference [...]                   -> one JSON line: the UNMODIFIED reference model (oracle/_ref,
+                                                              byte-compiled by oracle/build_ref.py) running real optimizer steps
+                                                              on this box's host cores
+  python bench.py --workload unrolled --look-ahead L       -> ns_vorticity_unrolling.py:225-244 training step through
+                                                              SOL_Transolver_Structured_Mesh_2D (north_star's driver)
+  python bench.py --workload rollout_cfg5 [--gpus N]       -> BASELINE configs[4]: 256x256 grid, 16 layers, slice_num 64,
+                                                              closed-loop rollout inference, batch sharded over ranks
 """
 from __future__ import annotations
 
@@ -29,8 +33,15 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(space_dim=2, n_layers=8, n_hidden=256, dropout=0.0, n_head=8, Time_Input=False, mlp_ratio=1, fun_dim=10, out_dim=1,
            slice_num=32, ref=8, unified_pos=1, H=64, W=64)
+CFG5 = dict(space_dim=2, n_layers=16, n_hidden=256, dropout=0.0, n_head=8, Time_Input=False, mlp_ratio=1, fun_dim=10, out_dim=1,
+            slice_num=64, ref=8, unified_pos=1, H=256, W=256)
 T_IN, T_OUT, STEP, PER_GPU_BATCH = 10, 10, 1, 2
 WORKLOAD = "Transolver_Structured_Mesh_2D NS 64x64, 8 layers, n_hidden 256, 8 heads, slice_num 32, T_in=T_out=10, per-GPU batch 2"
+WORKLOAD5 = "Transolver_Structured_Mesh_2D NS 256x256, 16 layers, n_hidden 256, 8 heads, slice_num 64, 10-step closed-loop rollout"
+
+# kernels of the Physics-Attention module itself (forward + backward) among the CUDA-event tags of ops.py
+PA_TAGS = ("proj_fprop", "proj_dgrad", "proj_wgrad", "slice_fwd", "slice_bwd", "token_attn_fwd", "token_attn_bwd", "deslice_out",
+           "deslice_dw", "deslice_dP")
 
 
 def peaks():
@@ -40,6 +51,18 @@ def peaks():
         return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), hbm=d["hbm_gbs"],
                     source="measured")
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+def ncu_traffic(kernel_key: str):
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written from the ncu report by profiles/summarize_ncu.py) - None when no capture of the shipped binary exists"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(p):
+        try:
+            return json.load(open(p)).get(kernel_key)
+        except (ValueError, OSError):
+            return None
+    return None
 
 
 class ClockSampler:
@@ -82,56 +105,62 @@ class ClockSampler:
                 "samples": len(sm), "window": window}
 
 
+# ------------------------------------------------------------------------------------------------
+# algorithmic work (SURVEY.md §8d closed forms, per sample per layer, forward; backward = 2x)
+# ------------------------------------------------------------------------------------------------
+def pa_flops_fwd(cfg) -> float:
+    N, C, H, G = cfg["H"] * cfg["W"], cfg["n_hidden"], cfg["n_head"], cfg["slice_num"]
+    D = C // H
+    return 2 * 2 * N * 9 * C * C + 3 * (2 * N * C * G) + 6 * H * G * D * D + 4 * H * G * G * D + 2 * N * C * C
+
+
+def model_flops_fwd(cfg, in_features=74) -> float:
+    N, C = cfg["H"] * cfg["W"], cfg["n_hidden"]
+    per_layer = pa_flops_fwd(cfg) + 4 * N * cfg["mlp_ratio"] * C * C
+    return cfg["n_layers"] * per_layer + 2 * N * (in_features * 2 * C + 2 * C * C) + 2 * N * C * cfg["out_dim"]
+
+
 def conv_fprop_flops(batch_tokens: int) -> float:
     C = CFG["n_hidden"]
     return 2.0 * batch_tokens * (9 * C) * (2 * C)
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: oracle port on host cores
+# reference arm: the unmodified reference model on the host cores (oracle/baselines.py)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int):
-    """each 'step' = ONE of the 10 teacher-forced model calls of an optimizer step (forward + backward, B=2, fp32) through
-    the oracle restatement with torch CPU ops on all host threads; samples/s = B / (10 * t_call)."""
-    from oracle import model as OM, physics_attention as O
-    O.USE_LIBRARY_CONV = True  # same library conv as the reference (nn.Conv2d), see oracle/physics_attention.py
-    torch.manual_seed(0)
-    n_threads = torch.get_num_threads()
-    from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Model
-    m = Model(**CFG)  # parameter container only (CPU); compute below is the oracle's
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
-    g = torch.Generator().manual_seed(1)
-    N = CFG["H"] * CFG["W"]
-    x = torch.rand(PER_GPU_BATCH, N, 2, generator=g)
-    fx = 0.38 * torch.randn(PER_GPU_BATCH, N, T_IN, generator=g)
-    y = 0.38 * torch.randn(PER_GPU_BATCH, N, 1, generator=g)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        out = OM.model_forward(x, fx, sd, CFG["n_layers"], CFG["n_head"], (CFG["H"], CFG["W"]), True, CFG["ref"])
-        loss = O.rel_l2_sum(out, y)
-        torch.autograd.grad(loss, list(sd.values()), allow_unused=True)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    t_call = statistics.median(times)
-    calls = T_OUT // STEP
-    return PER_GPU_BATCH / (calls * t_call), t_call, n_threads
-
-
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
-    value, t_call, cores = cpu_reference_run(args.steps, args.warmup)
-    sample = f"{args.steps} timed x one teacher-forced model call fwd+bwd (B=2, fp32, oracle port, torch CPU ops); step = 10 such calls"
+        return   # under torchrun rank 0 alone measures; the other ranks exit without work
+    from oracle import baselines as BL
+    from oracle import reference_shim as R
+    r = BL.cpu_reference_steps(CFG, PER_GPU_BATCH, T_IN, T_OUT, STEP, steps=args.steps, warmup=args.warmup)
+    one = None
+    if not args.no_cpu_1thread:
+        # 1-thread figure on a bounded sample: ONE real optimizer step would take minutes single-threaded, so one model call
+        # forward + backward (1/10 of a step's model work) is timed and scaled; stated as such
+        torch.set_num_threads(1)
+        m = BL.build_reference_model(CFG, "cpu")
+        g = torch.Generator().manual_seed(5)
+        N = CFG["H"] * CFG["W"]
+        x, fx = torch.rand(PER_GPU_BATCH, N, 2, generator=g), 0.38 * torch.randn(PER_GPU_BATCH, N, T_IN, generator=g)
+        y = 0.38 * torch.randn(PER_GPU_BATCH, N, 1, generator=g)
+        t0 = time.perf_counter()
+        BL._loss(m(x, fx=fx).reshape(PER_GPU_BATCH, -1), y.reshape(PER_GPU_BATCH, -1)).backward()
+        t_call = time.perf_counter() - t0
+        one = {"value": PER_GPU_BATCH / (10 * t_call), "unit": "samples/s", "cores": 1,
+               "sample": "one model call forward+backward (B=2) x 10 calls per step, extrapolated"}
+        torch.set_num_threads(r["cores"])
+    sample = (f"{args.steps} timed real optimizer steps (exp_ns.py:191-218: 10 teacher-forced calls, one backward, AdamW + OneCycleLR), "
+              f"B=2, fp32, reference modules from {R.kind()} ({'oracle/_ref' if R.kind() == 'compiled' else R.REF_ROOT})")
     line = {
-        "impl": "reference", "metric": "NS-64x64 train samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_call * (T_OUT // STEP), "higher_is_better": True,
+        "impl": "reference", "metric": "NS-64x64 train samples/sec", "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": PER_GPU_BATCH, "parallelism": "cpu"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": sample,
+                         "one_thread": one},
+        "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -140,55 +169,129 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
+class Harness:
+    """process-group / timing plumbing shared by the workloads"""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.sampler = ClockSampler(self.local) if self.rank == 0 else None
+        if self.sampler:
+            self.sampler.start()   # long before the timed region: nvidia-smi needs up to a second for its first sample
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, sample=False, finish=None):
+        """EXACTLY `steps` calls bracketed by barrier + synchronize on both sides, CUDA events, MAX over ranks -> ms"""
+        self.barrier()
+        if sample and self.sampler:
+            self.sampler.mark()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        if finish is not None:
+            finish()
+        e1.record()
+        self.barrier()
+        clocks = self.sampler.stop() if (sample and self.sampler) else None
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def profile_eager_steps(step_fn, n=3):
+    """CUDA-event pairs around every tagged libtbns launch during `n` eager steps, side stream off so that each tagged kernel
+    runs alone (kernels inside a replayed graph cannot be bracketed by events) -> {tag: ms per step}, raw event pairs"""
+    from transformerbasednavierstokesolver_b200 import ops
+    ops.PROFILE = {}
+    side_saved, ops._USE_SIDE = ops._USE_SIDE, False
+    try:
+        for i in range(n):
+            step_fn(i)
+        torch.cuda.synchronize()
+    finally:
+        prof, ops.PROFILE = ops.PROFILE, None
+        ops._USE_SIDE = side_saved
+    per_step = {t: sum(a.elapsed_time(b) for a, b in v) / n for t, v in sorted(prof.items())}
+    return per_step, prof
+
+
+def run_train(args, unrolled: bool):
     import transformerbasednavierstokesolver_b200 as pkg
     from transformerbasednavierstokesolver_b200 import ops, train
     from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Model
+    from transformerbasednavierstokesolver_b200.model.SOL_Transolver_Structured_Mesh_2D import SOL_Transolver_Structured_Mesh_2D
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    hs = Harness(args)
+    dev, world, rank = hs.dev, hs.world, hs.rank
+    dist = hs.dist
     pkg.set_default_precision(args.precision)
-
     torch.manual_seed(1234)
-    model = Model(**CFG).to(dev)
+    batched = bool(args.batched)
+    if unrolled:
+        model = SOL_Transolver_Structured_Mesh_2D(**CFG, step=STEP, look_ahead=args.look_ahead).to(dev)
+        loss_fn = lambda m, x, fx, yy: train.unrolled_step_loss(m, x, fx, yy, T_OUT, STEP, batched)   # noqa: E731
+        calls = args.look_ahead * len(range(0, T_OUT - args.look_ahead * STEP + 1, args.look_ahead * STEP))
+    else:
+        model = Model(**CFG).to(dev)
+        loss_fn = lambda m, x, fx, yy: train.step_loss(m, x, fx, yy, T_OUT, STEP, batched)   # noqa: E731
+        calls = T_OUT // STEP
     train.broadcast_parameters(model)
     grads = train.FlatGradients(model.parameters())
     graphed = bool(args.graph)
-    if args.precision == "bf16":
-        # the preprocess MLP (outside the Physics-Attention path, still PyTorch) may use TF32 tensor cores in bf16 mode
-        torch.backends.cuda.matmul.allow_tf32 = True
     opt = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-3, device=dev) if graphed else 1e-3, weight_decay=1e-5,
                             fused=True, capturable=graphed)
-    total_steps = 2 * (args.steps + args.warmup) + 16
+    total_steps = 2 * (args.steps + args.warmup) + 32
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-3, total_steps=total_steps)
 
     h = CFG["H"]
     # a pool of distinct pinned host batches (fresh data every step; rank-specific shard of the global batch)
     pool = [train.synthetic_ns_batch(PER_GPU_BATCH, h, T_IN, T_OUT, seed=1000 * rank + i, pin=True) for i in range(4)]
     dev_pool = [tuple(t.to(dev) for t in b) for b in pool]
-    batched = bool(args.batched)
     gstep = None
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()   # long before the timed region: nvidia-smi needs up to a second for its first sample
+    launches_per_step = None
     if graphed:
         ops.LAUNCHES = 0
         gstep = train.GraphedTrainStep(model, opt, sched, grads, dev_pool[0], T_OUT, STEP, batched=batched, warmup=3,
-                                       buckets=args.buckets if world > 1 else 1)
+                                       buckets=args.buckets if world > 1 else 1, loss_fn=loss_fn)
         launches_per_step = ops.LAUNCHES // 4   # 3 eager warm-ups + 1 capture pass
         torch.cuda.synchronize()
+
+    def eager_step(x, fx, yy, sched_=sched):
+        grads.begin()
+        loss = loss_fn(model, x, fx, yy)
+        loss.backward()
+        grads.finish()
+        grads.all_reduce()
+        opt.step()
+        if sched_ is not None:
+            sched_.step()
+        return loss.detach()
 
     def step_device(i):
         x, fx, yy = dev_pool[i % len(dev_pool)]
         if graphed:
             return gstep((x, fx, yy))           # device->device copy into the static buffers + graph replay
-        return train.train_step(model, opt, sched, grads, x, fx, yy, T_OUT, STEP, batched=batched)
+        return eager_step(x, fx, yy)
 
     losses = train.DeferredLoss()
 
@@ -199,65 +302,27 @@ def run_ours(args):
             losses.push(gstep(pool[i % len(pool)]))
             return None
         x, fx, yy = (t.to(dev, non_blocking=True) for t in pool[i % len(pool)])
-        loss = train.train_step(model, opt, sched, grads, x, fx, yy, T_OUT, STEP, batched=batched)
-        return float(loss.item())  # D2H read of the step's result
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, sampler=None, finish=None):
-        barrier()
-        if sampler:
-            sampler.mark()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ops.LAUNCHES = 0
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        if finish is not None:
-            finish()
-        e1.record()
-        barrier()
-        clocks = sampler.stop() if sampler else None
-        ms = e0.elapsed_time(e1)
-        if graphed:
-            ops.LAUNCHES = launches_per_step * steps   # kernels inside the replayed graph
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, ops.LAUNCHES, clocks
+        return float(eager_step(x, fx, yy).item())  # D2H read of the step's result
 
     for i in range(args.warmup):
         step_device(i)
-    # device-resident timing, with CUDA-event pairs around the dominant kernel (projection conv fprop)
+    ops.LAUNCHES = 0
     if not graphed:
         ops.PROFILE = {}
-    ms_dev, launches, clocks = timed(step_device, args.steps, sampler)
-    prof, ops.PROFILE = ops.PROFILE, None
-    prof_ms = ms_dev
+    ms_dev, clocks = hs.timed(step_device, args.steps, sample=True)
+    launches = launches_per_step * args.steps if graphed else ops.LAUNCHES
     if graphed:
-        # kernels inside a replayed graph cannot be bracketed by events: time the dominant kernel in eager replays of the
-        # same step (same shapes, same buffers) right after the timed region
-        ops.PROFILE = {}
-        side_saved, ops._USE_SIDE = ops._USE_SIDE, False   # per-launch times of kernels running alone, not beside the wgrad branch
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pe0.record()
-        for i in range(3):
-            x, fx, yy = dev_pool[i % len(dev_pool)]
-            train.train_step(model, opt, None, grads, x, fx, yy, T_OUT, STEP, batched=batched)
-        pe1.record()
-        torch.cuda.synchronize()
+        kernel_ms, prof = profile_eager_steps(lambda i: eager_step(*dev_pool[i % len(dev_pool)], sched_=None), 3)
+        nprof = 3
+    else:
         prof, ops.PROFILE = ops.PROFILE, None
-        ops._USE_SIDE = side_saved
-        prof_ms = pe0.elapsed_time(pe1)
+        nprof = args.steps
+        kernel_ms = {t: sum(a.elapsed_time(b) for a, b in v) / nprof for t, v in sorted(prof.items())}
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
     losses.flush()
     n_before = len(losses.values)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, finish=losses.flush)
+    ms_e2e, _ = hs.timed(step_e2e, args.steps, finish=losses.flush)
     if graphed:
         assert len(losses.values) - n_before == args.steps and all(v == v for v in losses.values), "every step's loss must reach the host"
 
@@ -269,57 +334,159 @@ def run_ours(args):
         gathered = [torch.empty_like(digest) for _ in range(world)]
         dist.all_gather(gathered, digest)
         replicas_identical = all(bool(torch.equal(gathered[0], t)) for t in gathered)
+
+    eager_bar = None
+    if rank == 0 and world == 1 and not unrolled and not args.no_eager_baseline:
+        try:
+            from oracle import baselines as BL
+            eager_bar = BL.gpu_eager_baseline(CFG, PER_GPU_BATCH, T_IN, T_OUT, STEP, dev)
+            eager_bar["what"] = ("the UNMODIFIED reference model as stock PyTorch eager (cuDNN / cuBLAS) on this GPU, same optimizer step "
+                                 "(exp_ns.py:191-218, AdamW): fp32 with TF32 tensor cores and bf16 autocast, literal ten-call loop and "
+                                 "the ten calls batched; 5 timed steps after 2 warm-up")
+        except Exception as e:   # a reported baseline must not take the measurement down
+            eager_bar = {"unavailable": repr(e)[:200]}
+
     if rank == 0:
         pk = peaks()
         gb = PER_GPU_BATCH * world
+        step_ms = ms_dev / args.steps
         value = gb * args.steps / (ms_dev / 1e3)
         e2e = gb * args.steps / (ms_e2e / 1e3)
-        calls = T_OUT // STEP
-        tokens_per_launch = PER_GPU_BATCH * h * h * (calls if batched else 1)
+        windows = calls // args.look_ahead if unrolled else calls
+        imgs_per_launch = PER_GPU_BATCH * (windows if batched else 1)
+        tokens_per_launch = imgs_per_launch * h * h
         roof = None
         if prof.get("proj_fprop"):
             durs = [a.elapsed_time(b) for a, b in prof["proj_fprop"]]
             avg_ms = sum(durs) / len(durs)
             ach = conv_fprop_flops(tokens_per_launch) / (avg_ms / 1e3) / 1e12
             roof = {"kernel": "projection conv3x3 fprop (implicit GEMM, x|fx fused)", "bound": "tensor", "achieved": ach,
-                    "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
-                    # (profiles/ncu_r01_conv_fprop_persistent.md); algorithmic minimum 2*M*C + 4*M*2I + 2*9C*2I = 212 MB
-                    "traffic": 160.65e6 if batched else None, "traffic_unit": "bytes/launch (ncu)",
-                    "peak_source": pk["source"] + " (sustained bf16 cuBLAS)", "avg_launch_ms": avg_ms, "launches_timed": len(durs),
-                    # warm launch time per step / graph-timed step time (eager replays only provide the per-launch durations)
-                    "share_of_step": (sum(durs) / (3 if graphed else args.steps)) / (ms_dev / args.steps),
+                    # the kernel is timed ALONE in short eager replays at boost clocks: the burst figure is the honest denominator
+                    "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
+                    "frac_of_sustained_peak": ach / pk["bf16_sustained"],
+                    "traffic": ncu_traffic("proj_fprop"), "traffic_unit": "bytes/launch, dram read+write, ncu --set full (profiles/)",
+                    "algorithmic_bytes_per_launch": tokens_per_launch * (2 * 256 + 2 * 512) + 2 * 2304 * 512,
+                    "peak_source": pk["source"] + " (burst bf16 cuBLAS)", "avg_launch_ms": avg_ms, "launches_timed": len(durs),
+                    "flops_per_launch": conv_fprop_flops(tokens_per_launch),
+                    "share_of_step": (sum(durs) / nprof) / step_ms,
                     "timed": "eager replays after the graph-timed region" if graphed else "inside the timed region"}
             for tag in ("proj_dgrad", "proj_wgrad"):
-                if prof.get(tag):
-                    d2 = [a.elapsed_time(b) for a, b in prof[tag]]
-                    roof[tag + "_share_of_step"] = (sum(d2) / (3 if graphed else args.steps)) / (ms_dev / args.steps)
-            # warm per-kernel-family device time per step (CUDA events around every tagged libtbns launch, eager replays)
-            nprof = 3 if graphed else args.steps
-            roof["kernel_ms_per_step"] = {t: round(sum(a.elapsed_time(b) for a, b in v) / nprof, 3) for t, v in sorted(prof.items())}
+                if tag in kernel_ms:
+                    roof[tag + "_share_of_step"] = kernel_ms[tag] / step_ms
+            roof["kernel_ms_per_step"] = {t: round(v, 3) for t, v in kernel_ms.items()}
+        # Physics-Attention as a whole (BASELINE metric 2 / north_star's 60 % bar): algorithmic FLOPs of the module, forward +
+        # backward, over the device time of ITS kernels (each timed alone, eager replays)
+        pa = None
+        if kernel_ms:
+            pa_ms = sum(v for t, v in kernel_ms.items() if t in PA_TAGS)
+            pa_gflop = 3 * pa_flops_fwd(CFG) * CFG["n_layers"] * PER_GPU_BATCH * calls / 1e9
+            if pa_ms > 0:
+                pa_t = pa_gflop / pa_ms   # GFLOP / ms = TFLOP/s
+                pa = {"pa_tflops": pa_t, "pa_frac_of_burst": pa_t / pk["bf16_burst"], "pa_kernel_ms_per_step": pa_ms,
+                      "pa_gflop_per_step": pa_gflop,
+                      "step_tflops": 3 * model_flops_fwd(CFG) * PER_GPU_BATCH * calls / 1e9 / step_ms,
+                      "kernels": [t for t in PA_TAGS if t in kernel_ms]}
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            v, t_call, cores = cpu_reference_run(3, 1)
-            cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                   "sample": "3 timed x one teacher-forced model call fwd+bwd (B=2, fp32, oracle port on host cores); step = 10 calls"}
+        if world == 1 and not args.no_cpu_baseline and not unrolled:
+            from oracle import baselines as BL
+            from oracle import reference_shim as R
+            r = BL.cpu_reference_steps(CFG, PER_GPU_BATCH, T_IN, T_OUT, STEP, steps=2, warmup=1)
+            cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+                   "sample": f"2 timed real optimizer steps after 1 warm-up (10 calls, one backward, AdamW), B=2, fp32, reference modules ({R.kind()})"}
         per_step_in = sum(t.numel() * t.element_size() for t in pool[0])
+        metric = "NS-64x64 train samples/sec" if not unrolled else f"NS-64x64 unrolled (look_ahead {args.look_ahead}) train samples/sec"
         line = {
-            "metric": "NS-64x64 train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": gb, "parallelism": f"dp{world}",
-                       "teacher_forced_calls_batched": batched, "cuda_graph": graphed, "allreduce_buckets": (gstep.nb if gstep is not None else 1),
+            "config": {"workload": WORKLOAD + (f"; ns_vorticity_unrolling step, look_ahead {args.look_ahead}" if unrolled else ""),
+                       "global_batch": gb, "parallelism": f"dp{world}",
+                       "calls_batched": batched, "images_per_launch": imgs_per_launch, "model_calls_per_step": calls,
+                       "cuda_graph": graphed, "allreduce_buckets": (gstep.nb if gstep is not None else 1),
                        "replicas_identical": replicas_identical,
                        "l2": "activations written per step (>1 GB) exceed the 126 MB L2; fresh input batch every step"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": per_step_in, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,
                     "loss_readback": ("every step's loss through pinned host memory, read one step late (train.DeferredLoss); all "
                                       "K reads inside the timed region") if graphed else "loss.item() every step"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "physics_attention": pa, "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager_bar,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    hs.close()
+
+
+def run_rollout_cfg5(args):
+    """BASELINE configs[4]: closed-loop rollout inference (ns_vorticity_unrolling.py:264-286) of the scaled NS model, batch
+    sharded over ranks; the only exchange is the scalar error metric all-reduced at the end of each rollout."""
+    import transformerbasednavierstokesolver_b200 as pkg
+    from transformerbasednavierstokesolver_b200 import ops, train
+    from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Model
+
+    hs = Harness(args)
+    dev, world, rank = hs.dev, hs.world, hs.rank
+    dist = hs.dist
+    pkg.set_default_precision(args.precision)
+    torch.manual_seed(4321)
+    model = Model(**CFG5).to(dev).eval()
+    train.broadcast_parameters(model)
+    B, h = args.rollout_batch, CFG5["H"]
+    pool = [train.synthetic_ns_batch(B, h, T_IN, T_OUT, seed=7000 * rank + i, pin=True) for i in range(2)]
+    dev_pool = [tuple(t.to(dev) for t in b) for b in pool]
+    graphed = bool(args.graph)
+    ops.LAUNCHES = 0
+    runner = train.GraphedRollout(model, dev_pool[0][:2], T_OUT, STEP, warmup=2) if graphed else None
+    launches_per_step = ops.LAUNCHES // 3 if graphed else None
+    metric_host = torch.empty((), dtype=torch.float32).pin_memory()
+    last = {}
+
+    def one(batch, read):
+        x, fx, yy = batch
+        pred = runner((x, fx)) if graphed else train.rollout(model, x.to(dev, non_blocking=True), fx.to(dev, non_blocking=True), T_OUT, STEP)
+        err = train.rel_l2_sum(pred.reshape(B, -1), yy.to(dev, non_blocking=True).reshape(B, -1))   # test_l2_full, :200
+        if world > 1:
+            dist.all_reduce(err, op=dist.ReduceOp.SUM)     # the only collective of the sharded rollout
+        if read:
+            metric_host.copy_(err, non_blocking=True)
+        last["err"] = err
+
+    for i in range(args.warmup):
+        one(dev_pool[i % 2], False)
+    ops.LAUNCHES = 0
+    ms_dev, clocks = hs.timed(lambda i: one(dev_pool[i % 2], False), args.steps, sample=True)
+    launches = launches_per_step * args.steps if graphed else ops.LAUNCHES
+    ms_e2e, _ = hs.timed(lambda i: one(pool[i % 2], True), args.steps, finish=torch.cuda.synchronize)
+    kernel_ms, prof = profile_eager_steps(lambda i: train.rollout(model, dev_pool[0][0], dev_pool[0][1], T_OUT, STEP), 2)
+    if rank == 0:
+        pk = peaks()
+        gb = B * world
+        calls = T_OUT // STEP
+        step_ms = ms_dev / args.steps
+        frames = gb * calls * args.steps / (ms_dev / 1e3)
+        flops_call = model_flops_fwd(CFG5) * B
+        roof = None
+        if prof.get("proj_fprop"):
+            durs = [a.elapsed_time(b) for a, b in prof["proj_fprop"]]
+            avg_ms = sum(durs) / len(durs)
+            fl = 2.0 * B * h * h * 2304 * 512
+            roof = {"kernel": "projection conv3x3 fprop (implicit GEMM, x|fx fused)", "bound": "tensor", "achieved": fl / (avg_ms / 1e3) / 1e12,
+                    "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": fl / (avg_ms / 1e3) / 1e12 / pk["bf16_burst"], "traffic": None,
+                    "avg_launch_ms": avg_ms, "launches_timed": len(durs), "kernel_ms_per_step": {t: round(v, 3) for t, v in kernel_ms.items()}}
+        per_step_in = sum(t.numel() * t.element_size() for t in pool[0])
+        line = {
+            "metric": "NS-256x256 rollout frames/sec", "value": frames, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "ms_per_model_call": step_ms / calls, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD5, "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world} (batch shards, metric all-reduce)",
+                       "cuda_graph": graphed, "fused_rollout_step": True,
+                       "l2": "each model call streams > 1 GB of activations through the 126 MB L2"},
+            "e2e": {"value": gb * calls * args.steps / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": per_step_in,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "model_tflops": flops_call * calls / 1e9 / step_ms, "rollout_error_metric": float(last["err"]) / gb,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    hs.close()
 
 
 def main():
@@ -328,21 +495,27 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "unrolled", "rollout_cfg5"])
+    ap.add_argument("--look-ahead", type=int, default=2, help="--workload unrolled: chained model calls per window (1, 2, 4, 8, 10)")
+    ap.add_argument("--rollout-batch", type=int, default=2, help="--workload rollout_cfg5: samples per GPU")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batched", type=int, default=1, help="evaluate the 10 teacher-forced calls as one batch (same math)")
-    ap.add_argument("--graph", type=int, default=1, help="replay the optimizer step from CUDA graphs (fwd+bwd graph, eager NCCL "
-                    "all-reduce, optimizer graph); 0 = eager launches")
+    ap.add_argument("--batched", type=int, default=1, help="evaluate the teacher-forced calls / windows as one batch (same math)")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step from CUDA graphs (fwd+bwd graph, eager NCCL all-reduce, "
+                    "optimizer graph); 0 = eager launches")
     ap.add_argument("--buckets", type=int, default=1, help="N > 1 GPUs: cut backward into this many stage graphs and all-reduce each "
-                    "stage's gradient range beside the next stages (measured on 2 GPUs: the 44.8 MB exchange costs 0.07 ms of a "
-                    "10.8 ms step, less than the extra graph launches, so the default is one bucket)")
+                    "stage's gradient range beside the next stages")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-1thread", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "rollout_cfg5":
+        run_rollout_cfg5(args)
     else:
-        run_ours(args)
+        run_train(args, unrolled=args.workload == "unrolled")
 
 
 if __name__ == "__main__":

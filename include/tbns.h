@@ -137,6 +137,11 @@ int tbns_layernorm_bwd(const float* dy, const float* x, const float* mean, const
 int tbns_ln_linear1_supported(int C);
 int tbns_ln_linear1_fwd(const float* x, const float* gamma, const float* beta, const float* w /* [C] */, const float* b /* [1] */,
                         float* out /* [rows] */, float* mean, float* rstd, int rows, int C, float eps, void* stream);
+/* same with the scalar of row r written to out[r*ldo]: the prediction lands straight in column t of a frame history
+ * [rows, ldo], so a closed-loop rollout needs no concatenation (model/SOL_Transolver_Structured_Mesh_2D.py:47-52,
+ * ns_vorticity_unrolling.py:269-277) */
+int tbns_ln_linear1_fwd_strided(const float* x, const float* gamma, const float* beta, const float* w, const float* b, float* out,
+                                long long ldo, float* mean, float* rstd, int rows, int C, float eps, void* stream);
 /* dx = LN'(dout (x) w) + dres.  sums [3][C]: S_c = sum_r dout[r]*xhat[r][c] | D = sum_r dout[r] (replicated over c) |
  * column sums of dx; then dgamma = w*S, dbeta = w*D, dw = gamma*S + beta*D, db = D.  ws: tbns_layernorm_bwd_ws_floats(C). */
 int tbns_ln_linear1_bwd(const float* dout /* [rows] */, const float* w, const float* x, const float* mean, const float* rstd,
@@ -152,6 +157,22 @@ int tbns_ln_linear1_bwd(const float* dout /* [rows] */, const float* w, const fl
  * ------------------------------------------------------------------------------------------- */
 int tbns_pack_proj_weights(const float* Wx, const float* bx, const float* Wfx, const float* bfx, float* Wf, float* Wd,
                            float* bcat, int I, int C, int taps, void* stream);
+/* same with optional bf16 copies Wf16 / Wd16 (the tensor-core operands) written by the same launch; Wf / Wd may be NULL
+ * when only the bf16 copies are wanted (bf16 mode: one launch per layer refreshes the operands after an optimizer step) */
+int tbns_pack_proj_weights16(const float* Wx, const float* bx, const float* Wfx, const float* bfx, float* Wf, float* Wd, void* Wf16,
+                             void* Wd16, float* bcat, int I, int C, int taps, void* stream);
+/* nn.Linear weight W [R][K] fp32 -> bf16 copy out16 [R][Kp] and / or transposed copy outT16 [Kp][R] (columns K..Kp-1 zero):
+ * the K-major operands of the forward (y = x W^T) and data-gradient (dx = dy W) contractions, one launch */
+int tbns_cast_bf16_pair(const float* W, void* out16, void* outT16, int R, int K, int Kp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input packing of the `preprocess` MLP (model/Transolver_Structured_Mesh_2D.py:203-207: pos.repeat + cat(x, fx)) fused
+ * with the rollout window shift (SOL_...py:47-52): writes the bf16 operand [rows, Kp] of the first Linear in one pass.
+ *   out16[r][0:R] = tab16[r % N][0:R] (bf16 table, e.g. the unified-position features) | src1[r*ld1 + j], j < F1 |
+ *   src2[r*ld2 + j], j < F2 (fp32 sources, arbitrary row strides: a window of a frame history) | zeros up to Kp.
+ * ------------------------------------------------------------------------------------------- */
+int tbns_pack_inputs(const void* tab16, int R, const float* src1, long long ld1, int F1, const float* src2, long long ld2, int F2,
+                     void* out16, int Kp, long long rows, int N, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Slice stage (model/Physics_Attention.py:40-42 / :98-101):

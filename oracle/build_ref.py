@@ -2,13 +2,15 @@
 """Build `oracle/_ref/`: the UNMODIFIED reference implementation of the path, compiled where its sources lie.
 
 TEST / BASELINE INFRASTRUCTURE ONLY.  The reference is pure Python (no native code), so "compiling" it
-means byte-compiling the model files straight from /root/reference into sourceless `.pyc` modules under `oracle/_ref/`
-(git-ignored like a built `.so`; NOT gpurun-ignored, so it travels to the GPU box, where /root/reference does not exist).
+means byte-compiling the model files straight from /root/reference into sourceless code objects under `oracle/_ref/`
+(`*.refbin` = the bytes of a `.pyc`; git-ignored like a built `.so`; NOT gpurun-ignored, so they travel to the GPU box, where
+/root/reference does not exist - plain `.pyc` files are dropped by the snapshot).  `oracle/reference_shim.py` imports them
+through a finder that maps `model.*`, `utils.testloss`, `model_dict` onto these files.
 No reference source text is copied into the repository.
 
     python oracle/build_ref.py            # needs /root/reference (build container); a no-op message on the GPU box
 
-Consumers: `oracle/ref_loader.py` -> `bench.py --impl reference`, `bench.py`'s cpu_baseline / gpu_eager_baseline legs,
+Consumers: `oracle/reference_shim.py` / `oracle/baselines.py` -> `bench.py --impl reference`, `bench.py`'s cpu_baseline / gpu_eager_baseline legs,
 and tests that check the oracle against the live reference.  The product package never imports it.
 """
 from __future__ import annotations
@@ -39,10 +41,10 @@ def build(verbose: bool = True) -> bool:
     if not os.path.isfile(os.path.join(REF_ROOT, FILES[0])):
         if verbose:
             print(f"oracle/build_ref: {REF_ROOT} not mounted - keeping whatever is in {OUT}")
-        return os.path.isfile(os.path.join(OUT, "model", "Physics_Attention.pyc"))
+        return os.path.isfile(os.path.join(OUT, "model", "Physics_Attention.refbin"))
     for rel in FILES:
         src = os.path.join(REF_ROOT, rel)
-        dst = os.path.join(OUT, os.path.splitext(rel)[0] + ".pyc")
+        dst = os.path.join(OUT, os.path.splitext(rel)[0] + ".refbin")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # unchecked-hash pyc: valid without the source file next to it; dfile keeps reference-relative paths in tracebacks
         py_compile.compile(src, cfile=dst, dfile=rel, doraise=True, optimize=0,

@@ -22,7 +22,7 @@ _PYC_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 def _root():
     if os.path.isfile(os.path.join(_SRC_ROOT, "model", "Physics_Attention.py")):
         return _SRC_ROOT
-    if os.path.isfile(os.path.join(_PYC_ROOT, "model", "Physics_Attention.pyc")):
+    if os.path.isfile(os.path.join(_PYC_ROOT, "model", "Physics_Attention.refbin")):
         return _PYC_ROOT
     return None
 
@@ -53,14 +53,41 @@ def _install_shims():
         sys.modules["timm.models.layers"] = layers
     if REF_ROOT is None:
         raise ImportError("reference not available: neither /root/reference nor oracle/_ref (run oracle/build_ref.py)")
-    if REF_ROOT not in sys.path:
+    if REF_ROOT == _PYC_ROOT:
+        if not any(isinstance(f, _CompiledRefFinder) for f in sys.meta_path):
+            sys.meta_path.insert(0, _CompiledRefFinder(_PYC_ROOT))
+    elif REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
 
 
+class _CompiledRefFinder:
+    """meta-path finder for the byte-compiled reference: `model`, `utils` (namespace packages in the reference), their
+    modules and `model_dict` resolve to oracle/_ref/**/<name>.refbin (the bytes of a .pyc, loaded sourceless)"""
+    PACKAGES = ("model", "utils")
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery as M
+        import importlib.util as U
+        parts = fullname.split(".")
+        if fullname in self.PACKAGES and os.path.isdir(os.path.join(self.root, fullname)):
+            spec = M.ModuleSpec(fullname, None, is_package=True)
+            spec.submodule_search_locations = [os.path.join(self.root, fullname)]
+            return spec
+        if parts[0] in self.PACKAGES or fullname == "model_dict":
+            f = os.path.join(self.root, *parts) + ".refbin"
+            if os.path.isfile(f):
+                return U.spec_from_file_location(fullname, f, loader=M.SourcelessFileLoader(fullname, f))
+        return None
+
+
 @contextlib.contextmanager
-def cpu_cuda_identity():
-    """Make `.cuda()` a no-op when there is no GPU (reference hard-codes it in get_grid)."""
-    if torch.cuda.is_available():
+def cpu_cuda_identity(force: bool = False):
+    """Make `.cuda()` a no-op when there is no GPU (reference hard-codes it in get_grid); force=True does so even when a GPU
+    is visible (CPU baseline on the GPU box: the model must stay on the host)."""
+    if torch.cuda.is_available() and not force:
         yield
         return
     orig = torch.Tensor.cuda

@@ -5,11 +5,13 @@ Everything is compared with the fp32 CPU oracle (oracle/physics_attention.py, or
 weights and inputs (SURVEY.md §7 hard part 1: both sides then see identical operands and the difference is the CUDA
 path's own intermediate rounding).  Gates (DESIGN.md §5 "bf16-mode gates" justifies each number):
 
-    forward / loss                         2e-3   north_star's per-layer bf16 bound
-    gradients of GEMM weights and biases   1.5e-2 two to three bf16 roundings of O(1e5)-term sums (incoming gradient, saved
-                                                  activation, GELU' product), measured 2e-3 .. 8e-3
-    gradients that are differences of      5e-2   softmax-backward quantities (temperature, slice projection, q/k): sums of
-    large cancelling terms                        signed terms whose magnitude is 10-100x the result
+    forward / loss                         2e-3   north_star's per-layer bf16 bound (measured 3.6e-4 per block)
+    gradients of GEMM weights / biases /   1e-2   two to three bf16 roundings of O(1e5)-term sums (incoming gradient, saved
+    LayerNorm affine                              activation, GELU' product); measured 2e-3 .. 4e-3
+    gradients downstream of the slice-     5e-2   temperature, slice projection, the x-projection (dX = dL.Ws), q / k: sums over
+    softmax backward                              all tokens of dL = w o (dw - sum_g w dw), signed terms that cancel to a
+                                                  small fraction of their magnitude, built from a bf16 deslice gradient;
+                                                  measured 3e-3 .. 3.6e-2 (worst: the logit-bias gradient sum_t dL)
 """
 import copy
 import os
@@ -23,9 +25,10 @@ from oracle import physics_attention as O
 pytestmark = pytest.mark.gpu
 
 OUT_TOL = 2e-3
-GRAD_TOL = 1.5e-2
+GRAD_TOL = 1e-2
 CANCEL_TOL = 5e-2
-CANCEL_KEYS = ("temperature", "in_project_slice.weight", "in_project_slice.bias", "to_q.weight", "to_k.weight")
+CANCEL_KEYS = ("temperature", "in_project_slice.weight", "in_project_slice.bias", "to_q.weight", "to_k.weight",
+               "in_project_x.weight", "in_project_x.bias")
 
 CFG1 = dict(space_dim=2, n_layers=8, n_hidden=256, dropout=0.0, n_head=8, Time_Input=False, mlp_ratio=1, fun_dim=10, out_dim=1,
             slice_num=32, ref=8, unified_pos=1, H=64, W=64)
@@ -234,7 +237,7 @@ def test_tc_conv_multi_tile_persistent(Bimg):
     torch.cuda.synchronize()
     assert O.rel_l2(out.cpu(), ref) < 1e-5
     assert O.rel_l2(dx.cpu(), ref_dx) < 1e-5
-    assert O.rel_l2(torch.cat([dWx, dWfx], 0).cpu(), ref_dW) < 2e-5
+    assert O.rel_l2(torch.cat([dWx, dWfx], 0).cpu(), ref_dW) < 5e-5   # 81920-term sums: the fp32 CPU reference itself carries ~2e-5
 
 
 def test_unrolled_train_step_matches_oracle_loop():
@@ -273,13 +276,14 @@ def test_unrolled_train_step_matches_oracle_loop():
             gref = dict(zip(keys, torch.autograd.grad(loss_ref, [sd[k] for k in keys])))
             sol = sol.to(dev)
             opt = torch.optim.SGD(sol.parameters(), lr=0.0)
-            loss = train.unrolled_train_step(sol, opt, None, None, x.to(dev), fx.to(dev), yy.to(dev), T=T, step=1)
-            assert abs(float(loss) - float(loss_ref)) < 1e-5 * abs(float(loss_ref)), look_ahead
-            for k, p in sol.transolver_model.named_parameters():
-                if k == "placeholder":
-                    continue
-                loose = k.endswith(("temperature", "to_q.weight", "to_k.weight"))
-                assert O.rel_l2(p.grad.cpu(), gref[k]) < (2e-2 if loose else 1e-3), (look_ahead, k)
+            for batched in (False, True):   # literal loop / windows stacked on the batch axis (same math)
+                loss = train.unrolled_train_step(sol, opt, None, None, x.to(dev), fx.to(dev), yy.to(dev), T=T, step=1, batched=batched)
+                assert abs(float(loss) - float(loss_ref)) < 1e-5 * abs(float(loss_ref)), (look_ahead, batched)
+                for k, p in sol.transolver_model.named_parameters():
+                    if k == "placeholder":
+                        continue
+                    loose = k.endswith(("temperature", "to_q.weight", "to_k.weight"))
+                    assert O.rel_l2(p.grad.cpu(), gref[k]) < (2e-2 if loose else 1e-3), (look_ahead, batched, k)
     finally:
         pkg.set_default_precision("bf16")
 
@@ -316,3 +320,46 @@ def test_unrolled_train_step_bf16_cfg1_block_shapes():
     loss = train.unrolled_train_step(sol, opt, None, None, x.to(dev), fx.to(dev), yy.to(dev), T=T, step=1)
     assert abs(float(loss) - float(loss_ref)) < 4e-3 * abs(float(loss_ref))
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for k, p in sol.named_parameters() if not k.endswith("placeholder"))
+
+
+def test_fused_rollout_step_equals_literal_loop():
+    """train.rollout keeps all frames in one history buffer - the window shift is a pointer offset read by the
+    packed preprocess, the last layer writes its prediction into the next column - and must reproduce the reference's
+    literal loop (model call + cat(fx[..., step:], im), exp_ns.py:225-241) bit for bit; the packed preprocess itself is
+    checked against the fp32 oracle forward."""
+    import transformerbasednavierstokesolver_b200 as pkg
+    from transformerbasednavierstokesolver_b200 import train
+    from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Model
+    dev = torch.device("cuda:0")
+    pkg.set_default_precision("bf16")
+    for unified in (1, 0):
+        torch.manual_seed(41)
+        kw = dict(space_dim=2, n_layers=2, n_hidden=256, n_head=8, fun_dim=10, out_dim=1, slice_num=32, ref=8, unified_pos=unified, H=32, W=32)
+        m = Model(**kw)
+        with torch.no_grad():
+            for p in m.parameters():
+                p.copy_(p.bfloat16().float())
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        x, fx, _ = train.synthetic_ns_batch(3, 32, 10, 4, seed=43)
+        x, fx = x.bfloat16().float(), fx.bfloat16().float()
+        with torch.no_grad():
+            ref = OM.model_forward(x, fx, sd, 2, 8, grid=(32, 32), unified_pos=bool(unified), ref=8)
+        m = m.to(dev)
+        assert m._packed_preprocess_ok(x.to(dev), fx.to(dev))
+        xd, fd = x.to(dev), fx.to(dev)
+        with torch.no_grad():
+            first = m(xd, fx=fd)
+            assert O.rel_l2(first.cpu(), ref) < 3 * OUT_TOL      # preprocess + two blocks, read through the C -> 1 head
+            preds, w = [], fd
+            for _ in range(4):
+                im = m(xd, fx=w)
+                preds.append(im)
+                w = torch.cat((w[..., 1:], im), -1)
+            literal = torch.cat(preds, -1)
+        fused = train.rollout(m, xd, fd, T=4, step=1)
+        assert fused.shape == literal.shape == (3, 1024, 4)
+        assert torch.equal(fused, literal)
+        # gradient wrt the input window flows through the packed preprocess (SOL unrolled training)
+        f2 = fd.clone().requires_grad_(True)
+        m(xd, fx=f2).square().sum().backward()
+        assert f2.grad is not None and bool(torch.isfinite(f2.grad).all()) and float(f2.grad.abs().max()) > 0

@@ -320,10 +320,11 @@ def test_pa_baseline_config_sizes(dev, cfg, precision):
     out.backward(dout.to(dev))
     rdx, rg = O.pa_backward(dout, sd, sv)
     # ALL 13 gradients (SURVEY §8 a-bwd), both modes.  bf16 mode: GEMM weights / biases see two to three bf16 operand roundings
-    # of long sums (gate 1.5e-2); the softmax-backward quantities (temperature, slice projection, q/k) are sums of large
-    # cancelling terms (gate 5e-2); fp32 mode: 2e-4 / 5e-3.
-    cancel = ("temperature", "in_project_slice.weight", "in_project_slice.bias", "to_q.weight", "to_k.weight")
-    assert O.rel_l2(xd.grad.cpu(), rdx) < (2e-4 if precision == "fp32" else 1.5e-2)
+    # of long sums (gate 1e-2); everything downstream of the slice-softmax backward is a sum of large cancelling terms
+    # (gate 5e-2; tests/test_gpu_bench_path.py states the measured values); fp32 mode: 2e-4 / 5e-3.
+    cancel = ("temperature", "in_project_slice.weight", "in_project_slice.bias", "to_q.weight", "to_k.weight",
+              "in_project_x.weight", "in_project_x.bias")   # everything downstream of the slice-softmax backward
+    assert O.rel_l2(xd.grad.cpu(), rdx) < (2e-4 if precision == "fp32" else 1e-2)
     got = dict(m.named_parameters())
     assert set(got) == set(rg)
     errs = {k: O.rel_l2(got[k].grad.cpu(), rg[k]) for k in rg}
@@ -332,7 +333,7 @@ def test_pa_baseline_config_sizes(dev, cfg, precision):
         if precision == "fp32":
             assert e < (5e-3 if k in cancel else 2e-4), (k, e)   # oracle itself runs in fp32 here
         else:
-            assert e < (5e-2 if k in cancel else 1.5e-2), (k, e)
+            assert e < (5e-2 if k in cancel else 1e-2), (k, e)
 
 
 def test_slice_weights_partition_of_unity_full_size(dev):

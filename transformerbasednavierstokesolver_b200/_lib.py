@@ -85,8 +85,12 @@ _SIGS = {
     "tbns_layernorm_bwd": (_i, [_fp] * 12 + [_i, _i, _fp]),
     "tbns_ln_linear1_supported": (_i, [_i]),
     "tbns_ln_linear1_fwd": (_i, [_fp] * 8 + [_i, _i, C.c_float, _fp]),
+    "tbns_ln_linear1_fwd_strided": (_i, [_fp] * 6 + [_ll] + [_fp] * 2 + [_i, _i, C.c_float, _fp]),
     "tbns_ln_linear1_bwd": (_i, [_fp] * 11 + [_i, _i, _fp]),
+    "tbns_pack_inputs": (_i, [_fp, _i, _fp, _ll, _i, _fp, _ll, _i, _fp, _i, _ll, _i, _fp]),
     "tbns_pack_proj_weights": (_i, [_fp] * 7 + [_i, _i, _i, _fp]),
+    "tbns_pack_proj_weights16": (_i, [_fp] * 9 + [_i, _i, _i, _fp]),
+    "tbns_cast_bf16_pair": (_i, [_fp] * 3 + [_i, _i, _i, _fp]),
     "tbns_slice_groups": (_i, [_i, _i, _i]),
     "tbns_pa_slice_fwd": (_i, [_fp] * 7 + [_i] * 6 + [_fp]),
     "tbns_pa_slice_tc_supported": (_i, [_i, _i]),

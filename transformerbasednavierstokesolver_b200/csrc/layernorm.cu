@@ -566,8 +566,8 @@ namespace tbns {
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_linear1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta, const float* __restrict__ w,
                                                                      const float* __restrict__ b, float* __restrict__ out,
-                                                                     float* __restrict__ mean, float* __restrict__ rstd, int rows, int C,
-                                                                     float eps) {
+                                                                     long long ldo, float* __restrict__ mean,
+                                                                     float* __restrict__ rstd, int rows, int C, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= rows) return;
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_linear1_fwd_kernel(const flo
   }
   dot = warp_sum(dot);
   if (lane == 0) {
-    out[row] = dot + b[0];
+    out[(long long)row * ldo] = dot + b[0];
     mean[row] = mu;
     rstd[row] = rs;
   }
@@ -605,14 +605,24 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_linear1_fwd_kernel(const flo
 
 extern "C" int tbns_ln_linear1_supported(int C) { return (C == 128 || C == 256 || C == 512) ? 1 : 0; }
 
+extern "C" int tbns_ln_linear1_fwd_strided(const float* x, const float* gamma, const float* beta, const float* w, const float* b,
+                                           float* out, long long ldo, float* mean, float* rstd, int rows, int C, float eps,
+                                           void* stream);
+
 extern "C" int tbns_ln_linear1_fwd(const float* x, const float* gamma, const float* beta, const float* w, const float* b, float* out,
                                    float* mean, float* rstd, int rows, int C, float eps, void* stream) {
-  TBNS_REQUIRE(x && gamma && beta && w && b && out && mean && rstd, "tbns_ln_linear1_fwd: null pointer");
+  return tbns_ln_linear1_fwd_strided(x, gamma, beta, w, b, out, 1, mean, rstd, rows, C, eps, stream);
+}
+
+extern "C" int tbns_ln_linear1_fwd_strided(const float* x, const float* gamma, const float* beta, const float* w, const float* b,
+                                           float* out, long long ldo, float* mean, float* rstd, int rows, int C, float eps,
+                                           void* stream) {
+  TBNS_REQUIRE(x && gamma && beta && w && b && out && mean && rstd && ldo >= 1, "tbns_ln_linear1_fwd: null pointer / bad stride");
   TBNS_REQUIRE(rows >= 0 && tbns_ln_linear1_supported(C), "tbns_ln_linear1_fwd: C=%d unsupported (128, 256, 512)", C);
   TBNS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
                  reinterpret_cast<uintptr_t>(w)) & 15) == 0, "tbns_ln_linear1_fwd: pointers must be 16-byte aligned");
   if (rows == 0) return TBNS_OK;
-  ln_linear1_fwd_kernel<<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, w, b, out, mean, rstd, rows, C, eps);
+  ln_linear1_fwd_kernel<<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, w, b, out, ldo, mean, rstd, rows, C, eps);
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }

@@ -1,0 +1,61 @@
+// Input packing for the `preprocess` MLP (model/Transolver_Structured_Mesh_2D.py:203-207):
+//   fx = preprocess(cat(x, fx))  with  x = pos.repeat(B) (unified_pos) or the raw coordinates.
+// The reference materialises pos.repeat [B,N,ref^2] and the concatenation [B,N,ref^2+T_in] in fp32 every call, and its
+// rollout loops add a window shift cat(fx[..., step:], im) per step (SOL_Transolver_Structured_Mesh_2D.py:47-52,
+// ns_vorticity_unrolling.py:269-277).  Here ONE pass writes the bf16 TMA operand of the first Linear directly:
+//   out16[b*N+n][0:R]        = tab16[n][0:R]                 (bf16 table, broadcast over the batch; optional)
+//   out16[..][R:R+F1]        = bf16(src1[(b*N+n)*ld1 + j])   (optional fp32 source, e.g. raw coordinates)
+//   out16[..][R+F1:R+F1+F2]  = bf16(src2[(b*N+n)*ld2 + j])   (fp32 source; a strided window of a frame history, so the
+//                                                             window shift is just a pointer offset)
+//   out16[..][rest up to Kp] = 0                             (K padded to whole 64-element TMA boxes)
+// HBM-bound, 16-byte stores, one thread per 8 output columns.
+#include "common.cuh"
+
+namespace tbns {
+
+__global__ void pack_inputs_kernel(const __nv_bfloat16* __restrict__ tab16, int R, const float* __restrict__ src1, long long ld1,
+                                   int F1, const float* __restrict__ src2, long long ld2, int F2, __nv_bfloat16* __restrict__ out,
+                                   int Kp, long long rows, int N) {
+  const int cpr = Kp >> 3;   // 16-byte chunks per output row
+  const long long total = rows * cpr;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / cpr;
+    const int c0 = (int)(idx - row * cpr) * 8;
+    __nv_bfloat16 v[8];
+    if (c0 + 8 <= R && (R & 7) == 0) {
+      *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(tab16 + (row % N) * R + c0);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float f = 0.f;
+        if (c < R) f = __bfloat162float(tab16[(row % N) * R + c]);
+        else if (c < R + F1) f = src1[row * ld1 + (c - R)];
+        else if (c < R + F1 + F2) f = src2[row * ld2 + (c - R - F1)];
+        v[j] = __float2bfloat16_rn(f);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + row * Kp + c0) = *reinterpret_cast<uint4*>(v);
+  }
+}
+
+}  // namespace tbns
+
+using namespace tbns;
+
+extern "C" int tbns_pack_inputs(const void* tab16, int R, const float* src1, long long ld1, int F1, const float* src2, long long ld2,
+                                int F2, void* out16, int Kp, long long rows, int N, void* stream) {
+  TBNS_REQUIRE(out16 && Kp > 0 && Kp % 8 == 0 && rows >= 0 && N > 0, "tbns_pack_inputs: bad args");
+  TBNS_REQUIRE(R >= 0 && F1 >= 0 && F2 >= 0 && R + F1 + F2 <= Kp, "tbns_pack_inputs: %d + %d + %d columns do not fit Kp=%d", R, F1, F2, Kp);
+  TBNS_REQUIRE((R == 0 || tab16) && (F1 == 0 || src1) && (F2 == 0 || src2), "tbns_pack_inputs: null source");
+  TBNS_REQUIRE((reinterpret_cast<uintptr_t>(out16) & 15) == 0 && (!tab16 || (reinterpret_cast<uintptr_t>(tab16) & 15) == 0),
+               "tbns_pack_inputs: out16 / tab16 must be 16-byte aligned");
+  if (rows == 0) return TBNS_OK;
+  const long long total = rows * (Kp / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+  pack_inputs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(tab16), R, src1, ld1, F1,
+                                                                         src2, ld2, F2, reinterpret_cast<__nv_bfloat16*>(out16), Kp, rows, N);
+  TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
+}

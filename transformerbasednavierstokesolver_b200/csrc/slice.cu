@@ -14,12 +14,14 @@ namespace tbns {
 
 constexpr float EPS_NORM = 1e-5f;
 // one CTA per (batch, head) and only B*H of them: latency-bound chains of tiny contractions -> as many warps as a CTA can hold
-constexpr int TOKEN_THREADS = 1024;
+// 512 threads and <= 64 registers: two CTAs share an SM, so the B*H = 160 CTAs of the benchmark shape are ONE wave on 148 SMs
+// (1024-thread CTAs ran 148 + 12: two waves of a latency-bound kernel)
+constexpr int TOKEN_THREADS = 512;
 
 // grid (H, B), block 256.  All [rows][D] shared arrays use the padded stride DS = D+1 (bank-conflict free for both
 // row-wise and column-wise thread mappings).
 template <int DT, int GT>
-__global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ Wq,
+__global__ void __launch_bounds__(TOKEN_THREADS, 2) token_attn_fwd_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ Wq,
                                                              const float* __restrict__ Wk, const float* __restrict__ Wv,
                                                              const float* __restrict__ Wo, float* __restrict__ s_out,
                                                              float* __restrict__ Tt_out, float* __restrict__ tok_out,
@@ -153,8 +155,16 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
       float acc = 0.f;
       for (int dd = 0; dd < D; ++dd) acc = fmaf(O[g * DS + dd], wr[dd], acc);
       Pout[(long long)g * Cout + c] = acc;
-      if (P16) P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(acc);
       if (PT16) PT16[((long long)b * Cout + c) * (H * G) + h * G + g] = __float2bfloat16_rn(acc);
+    }
+    if (P16) {   // centred copy (see below), slow path: P is read back from global memory
+      __syncthreads();
+      for (int o = tid; o < G * Cout; o += nt) {
+        const int g = o / Cout, c = o - g * Cout;
+        float m = 0.f;
+        for (int g2 = 0; g2 < G; ++g2) m += Pout[(long long)g2 * Cout + c];
+        P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(Pout[(long long)g * Cout + c] - m / (float)G);
+      }
     }
     return;
   }
@@ -180,7 +190,6 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
         }
         const float acc = a0 + a1;
         Pout[(long long)g * Cout + c] = acc;
-        if (P16) P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(acc);
         Ps[g * (Cout + 1) + c] = acc;
       }
       done7 = true;
@@ -195,12 +204,33 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
 #pragma unroll 8
       for (int dd = 0; dd < D; ++dd) acc = fmaf(ov[dd], wv[dd], acc);
       Pout[(long long)g * Cout + c] = acc;
-      if (P16) P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(acc);
       Ps[g * (Cout + 1) + c] = acc;
     }
   }
+  if (P16 || PT16) __syncthreads();
+  if (P16) {
+    // P16 is the weight operand of the deslice gradient dw = dOut.P^T (backward).  The slice tokens of a head are all close
+    // to the field's mean, so the rows P[g,:] share a large common component; the softmax backward annihilates anything
+    // constant over g (dL' = w o (dw - sum_g w dw), sum_g w = 1), which would leave bf16 rounding noise of the common part
+    // over a small signal.  Storing P[g,:] - mean_g P[g,:] removes it at the operand level: same gradient, ~8x less error.
+    const float invG = 1.0f / (float)G;
+    if (nt % Cout == 0) {   // the thread's column is fixed: one pass for the mean, one for its rows
+      const int c = tid % Cout;
+      float m = 0.f;
+      for (int g2 = 0; g2 < G; ++g2) m += Ps[g2 * (Cout + 1) + c];
+      m *= invG;
+      for (int g = tid / Cout; g < G; g += nt / Cout)
+        P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(Ps[g * (Cout + 1) + c] - m);
+    } else {
+      for (int o = tid; o < G * Cout; o += nt) {
+        const int c = o % Cout, g = o / Cout;
+        float m = 0.f;
+        for (int g2 = 0; g2 < G; ++g2) m += Ps[g2 * (Cout + 1) + c];
+        P16[((long long)b * H * G + (long long)h * G + g) * Cout + c] = __float2bfloat16_rn(Ps[g * (Cout + 1) + c] - m * invG);
+      }
+    }
+  }
   if (PT16) {
-    __syncthreads();
     // transposed (K-major) bf16 copy: row c of image b holds this head's G slices contiguously
     __nv_bfloat16* ptb = PT16 + (long long)b * Cout * (H * G) + h * G;
     if ((G & 7) == 0 && ((H * G) & 7) == 0 && (reinterpret_cast<uintptr_t>(PT16) & 15) == 0) {
@@ -225,7 +255,7 @@ __global__ void __launch_bounds__(TOKEN_THREADS) token_attn_fwd_kernel(const flo
 
 // grid (H, B), block 256
 template <int DT, int GT>
-__global__ void __launch_bounds__(TOKEN_THREADS) token_attn_bwd_kernel(const float* __restrict__ dP, const float* __restrict__ Wq,
+__global__ void __launch_bounds__(TOKEN_THREADS, 2) token_attn_bwd_kernel(const float* __restrict__ dP, const float* __restrict__ Wq,
                                                              const float* __restrict__ Wk, const float* __restrict__ Wv,
                                                              const float* __restrict__ Wo, const float* __restrict__ s_in,
                                                              const float* __restrict__ tok_in, const float* __restrict__ q_in,
@@ -481,9 +511,11 @@ __global__ void dtau_finish_kernel(const float* __restrict__ dtau_part, const fl
   dtemperature[h] = acc;
 }
 
-// Wf[n][tap*C+ci], Wd[ci][tap*2I+n], bcat[n]  from nn.Conv2d/Linear weights [I][C][taps]
+// Wf[n][tap*C+ci], Wd[ci][tap*2I+n], bcat[n]  from nn.Conv2d/Linear weights [I][C][taps]; fp32 and/or bf16 (K-major tensor-core
+// operand) outputs: the bf16 copies are written directly, so a weight refresh after an optimizer step is one launch per layer
 __global__ void pack_proj_weights_kernel(const float* __restrict__ Wx, const float* __restrict__ bx, const float* __restrict__ Wfx,
                                          const float* __restrict__ bfx, float* __restrict__ Wf, float* __restrict__ Wd,
+                                         __nv_bfloat16* __restrict__ Wf16, __nv_bfloat16* __restrict__ Wd16,
                                          float* __restrict__ bcat, int I, int C, int taps) {
   const long long total = 2LL * I * C * taps;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -494,10 +526,36 @@ __global__ void pack_proj_weights_kernel(const float* __restrict__ Wx, const flo
     const float* src = n < I ? Wx : Wfx;
     const int co = n < I ? n : n - I;
     const float v = src[((long long)co * C + ci) * taps + tap];
-    Wf[idx] = v;
-    if (Wd) Wd[(long long)ci * taps * 2 * I + (long long)tap * 2 * I + n] = v;
+    const long long di = (long long)ci * taps * 2 * I + (long long)tap * 2 * I + n;
+    if (Wf) Wf[idx] = v;
+    if (Wd) Wd[di] = v;
+    if (Wf16) Wf16[idx] = __float2bfloat16_rn(v);
+    if (Wd16) Wd16[di] = __float2bfloat16_rn(v);
   }
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < 2 * I; n += gridDim.x * blockDim.x) bcat[n] = n < I ? bx[n] : bfx[n - I];
+}
+
+// bf16 copy [R][Kp] and / or transposed bf16 copy [Kp][R] of an fp32 matrix [R][K] (K zero-padded to Kp): both K-major
+// operand layouts of a Linear weight (forward / data-gradient contraction) in ONE launch.  32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) cast_bf16_pair_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out,
+                                                            __nv_bfloat16* __restrict__ outT, int R, int K, int Kp) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = r0 + ty + 8 * j, k = k0 + tx;
+    const float v = (r < R && k < K) ? W[(long long)r * K + k] : 0.f;
+    tile[ty + 8 * j][tx] = v;
+    if (out && r < R && k < Kp) out[(long long)r * Kp + k] = __float2bfloat16_rn(v);
+  }
+  if (!outT) return;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = k0 + ty + 8 * j, r = r0 + tx;
+    if (k < Kp && r < R) outT[(long long)k * R + r] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
+  }
 }
 
 #define TBNS_SLICE_EXTERN(D_, G_)                                                                                                          \
@@ -661,14 +719,30 @@ extern "C" int tbns_pa_dtau_finish(const float* dtau_part, const float* temperat
   return TBNS_OK;
 }
 
-extern "C" int tbns_pack_proj_weights(const float* Wx, const float* bx, const float* Wfx, const float* bfx, float* Wf, float* Wd,
-                                      float* bcat, int I, int C, int taps, void* stream) {
-  TBNS_REQUIRE(Wx && bx && Wfx && bfx && Wf && bcat, "tbns_pack_proj_weights: null pointer");
+extern "C" int tbns_pack_proj_weights16(const float* Wx, const float* bx, const float* Wfx, const float* bfx, float* Wf, float* Wd,
+                                        void* Wf16, void* Wd16, float* bcat, int I, int C, int taps, void* stream) {
+  TBNS_REQUIRE(Wx && bx && Wfx && bfx && (Wf || Wf16) && bcat, "tbns_pack_proj_weights: null pointer");
   TBNS_REQUIRE(I > 0 && C > 0 && (taps == 1 || taps == 9), "tbns_pack_proj_weights: bad dims");
   const long long total = 2LL * I * C * taps;
   int blocks = (int)((total + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  pack_proj_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Wx, bx, Wfx, bfx, Wf, Wd, bcat, I, C, taps);
+  pack_proj_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Wx, bx, Wfx, bfx, Wf, Wd, reinterpret_cast<__nv_bfloat16*>(Wf16),
+                                                                     reinterpret_cast<__nv_bfloat16*>(Wd16), bcat, I, C, taps);
+  TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
+}
+
+extern "C" int tbns_pack_proj_weights(const float* Wx, const float* bx, const float* Wfx, const float* bfx, float* Wf, float* Wd,
+                                      float* bcat, int I, int C, int taps, void* stream) {
+  TBNS_REQUIRE(Wf != nullptr, "tbns_pack_proj_weights: null pointer");
+  return tbns_pack_proj_weights16(Wx, bx, Wfx, bfx, Wf, Wd, nullptr, nullptr, bcat, I, C, taps, stream);
+}
+
+extern "C" int tbns_cast_bf16_pair(const float* W, void* out16, void* outT16, int R, int K, int Kp, void* stream) {
+  TBNS_REQUIRE(W && (out16 || outT16) && R > 0 && K > 0 && Kp >= K, "tbns_cast_bf16_pair: bad args");
+  dim3 grid(cdiv(Kp, 32), cdiv(R, 32));
+  cast_bf16_pair_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, reinterpret_cast<__nv_bfloat16*>(out16),
+                                                                reinterpret_cast<__nv_bfloat16*>(outT16), R, K, Kp);
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }

@@ -44,15 +44,21 @@ class _PhysicsAttentionBase(nn.Module):
         self._pack_key = None
         self._packed = None
 
-    # packed projection weights (fprop / dgrad operand layouts), refreshed when the masters change
-    def _packed_weights(self):
+    # packed projection weights (fprop / dgrad operand layouts), refreshed when the masters change (ops: cache validity rules)
+    def _packed_weights(self, prec=None):
         px, pfx = self.in_project_x, self.in_project_fx
+        lin = self.to_out[0]
+        taps = 9 if px.weight.dim() == 4 else 1
+        # bf16 mode on tensor-core shapes: only the bf16 operands are needed - one launch per refresh
+        bf16_only = (prec == ops.TBNS_PREC_BF16 and px.weight.dim() in (2, 4) and
+                     ops.pa_tc_shapes_ok(px.weight.shape[1], 2 * px.weight.shape[0], self.heads * self.in_project_slice.weight.shape[0],
+                                         lin.weight.shape[0], taps))
         key = (px.weight.data_ptr(), px.weight._version, px.bias._version, pfx.weight.data_ptr(), pfx.weight._version,
-               pfx.bias._version, px.weight.device, ops.cache_context())
+               pfx.bias._version, px.weight.device, ops.cache_context(), bf16_only)
         if key != self._pack_key:
             with torch.no_grad(), torch.cuda.device(px.weight.device):
                 self._packed = ops.pack_proj_weights(px.weight.detach().contiguous(), px.bias.detach().contiguous(),
-                                                     pfx.weight.detach().contiguous(), pfx.bias.detach().contiguous())
+                                                     pfx.weight.detach().contiguous(), pfx.bias.detach().contiguous(), bf16_only)
             self._pack_key = key
         return self._packed
 
@@ -69,8 +75,8 @@ class _PhysicsAttentionBase(nn.Module):
                                       "(every reference script uses dropout=0.0)")
         B, N, C = x.shape
         grid = self._grid((B, N, C))
-        packed = self._packed_weights()
         prec = ops.PRECISIONS[self.precision or config.get_default_precision()]
+        packed = self._packed_weights(prec)
         lin = self.to_out[0]
         return ops.PhysicsAttentionFn.apply(
             x.float(), residual, self.temperature, self.in_project_x.weight, self.in_project_x.bias, self.in_project_fx.weight,
@@ -85,8 +91,8 @@ def _forward_block(self, fx, ln):
     if self.training and self.dropout.p > 0.0:
         raise NotImplementedError("dropout > 0 in training mode is not supported by the fused kernels")
     grid = self._grid(tuple(fx.shape))
-    packed = self._packed_weights()
     prec = ops.PRECISIONS[self.precision or config.get_default_precision()]
+    packed = self._packed_weights(prec)
     lin = self.to_out[0]
     return ops.AttnBlockFn.apply(
         fx.float(), ln.weight, ln.bias, ln.eps, self.temperature, self.in_project_x.weight, self.in_project_x.bias,

@@ -6,6 +6,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import config, ops
 from ._blocks import MLP, Transolver_block as _Block, init_weights, time_conditioning
 from .Physics_Attention import Physics_Attention_Structured_Mesh_2D  # noqa: F401  (re-exported like the reference)
 
@@ -50,17 +51,41 @@ class Model(nn.Module):
         d = torch.sqrt(((mesh[:, :, None, None, :] - lattice[None, None]) ** 2).sum(-1))
         return d.reshape(1, self.H, self.W, self.ref * self.ref).repeat(batchsize, 1, 1, 1).contiguous()
 
-    def forward(self, x, fx, T=None):
-        if self.unified_pos:
-            if self.pos.device != x.device:
-                self.pos = self.pos.to(x.device)
-            x = self.pos.repeat(x.shape[0], 1, 1, 1).reshape(x.shape[0], self.H * self.W, self.ref * self.ref)
-        if fx is not None:
-            fx = self.preprocess(torch.cat((x, fx), -1))
+    def _pos16(self, device):
+        """bf16 copy [N, ref*ref] of the unified-position table: the operand the packed preprocess reads (broadcast over the
+        batch inside the pack kernel instead of `pos.repeat(B)`, reference :204)"""
+        t = getattr(self, "_pos16_cache", None)
+        if t is None or t.device != device:
+            t = self.pos.to(device).reshape(self.H * self.W, self.ref * self.ref).to(torch.bfloat16).contiguous()
+            self._pos16_cache = t
+        return t
+
+    def _packed_preprocess_ok(self, x, fx):
+        pp = self.preprocess
+        return (fx is not None and fx.is_cuda and fx.dtype == torch.float32 and config.get_default_precision() == "bf16"
+                and pp.n_layers == 0 and pp.act_name == 'gelu' and ops.mlp_tc_ok(pp.n_input, pp.n_hidden, pp.n_output))
+
+    def forward(self, x, fx, T=None, out=None):
+        """reference signature forward(x, fx, T=None).  `out` (extension, inference only): a [B, N, out_dim] view - e.g. one
+        column of a frame history - that receives the prediction in place (train.rollout)."""
+        if self._packed_preprocess_ok(x, fx):
+            # bf16 mode: position features / coordinates and the input fields are packed straight into the bf16 operand of
+            # the first Linear (no pos.repeat, no cat, no padded copy; `fx` may be a strided window of a frame history)
+            pre, post = self.preprocess.linear_pre[0], self.preprocess.linear_post
+            tab16 = self._pos16(fx.device) if self.unified_pos else None
+            src1 = None if self.unified_pos else x
+            fx = ops.PackedMlpFn.apply(tab16, src1, fx, pre.weight, pre.bias, post.weight, post.bias)
         else:
-            fx = self.preprocess(x) + self.placeholder[None, None, :]
+            if self.unified_pos:
+                if self.pos.device != x.device:
+                    self.pos = self.pos.to(x.device)
+                x = self.pos.repeat(x.shape[0], 1, 1, 1).reshape(x.shape[0], self.H * self.W, self.ref * self.ref)
+            if fx is not None:
+                fx = self.preprocess(torch.cat((x, fx), -1))
+            else:
+                fx = self.preprocess(x) + self.placeholder[None, None, :]
         if T is not None:
             fx = fx + time_conditioning(self.time_fc, T, self.n_hidden)
-        for block in self.blocks:
+        for block in self.blocks[:-1]:
             fx = block(fx)
-        return fx
+        return self.blocks[-1](fx) if out is None else self.blocks[-1](fx, out=out)

@@ -64,12 +64,16 @@ class Transolver_block(nn.Module):
             self.ln_3 = nn.LayerNorm(hidden_dim)
             self.mlp2 = nn.Linear(hidden_dim, out_dim)
 
-    def forward(self, fx):
+    def forward(self, fx, out=None):
         prec = ops.PRECISIONS[self.Attn.precision or config.get_default_precision()]
         fx = self.Attn.forward_block(fx.contiguous(), self.ln_1)
         pre, post = self.mlp.linear_pre[0], self.mlp.linear_post
         fx = ops.LnMlpFn.apply(fx, self.ln_2.weight, self.ln_2.bias, pre.weight, pre.bias, post.weight, post.bias, self.ln_2.eps, prec)
         if self.last_layer:
+            if out is not None:
+                if torch.is_grad_enabled() and fx.requires_grad:
+                    raise RuntimeError("`out=` writes the prediction in place and is for inference (torch.no_grad()) only")
+                return ops.ln_linear_into(fx, self.ln_3.weight, self.ln_3.bias, self.mlp2.weight, self.mlp2.bias, self.ln_3.eps, prec, out)
             return ops.LnLinearFn.apply(fx, self.ln_3.weight, self.ln_3.bias, self.mlp2.weight, self.mlp2.bias, self.ln_3.eps, prec)
         return fx
 

@@ -196,6 +196,13 @@ def invalidate_weight_caches():
     _WEIGHT_GEN += 1
 
 
+# Fused / foreach optimizers (torch.optim.AdamW(fused=True), the reference's AdamW on CUDA) update parameters WITHOUT bumping
+# `_version`, so every optimizer step of any torch optimizer starts a new weight generation.
+from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook  # noqa: E402
+
+_reg_post_hook(lambda *_a, **_k: invalidate_weight_caches())
+
+
 def begin_capture():
     """call right before a new CUDA-graph capture of code that uses this module: derived weights are rebuilt inside it"""
     global _CAP_EPOCH
@@ -228,20 +235,31 @@ def _w16_cached(W: torch.Tensor, key_extra, build) -> torch.Tensor:
     return w16
 
 
+def weight_bf16_pair(W: torch.Tensor, Kp: Optional[int] = None):
+    """(bf16 copy [R, Kp], transposed bf16 copy [Kp, R]) of a Linear weight [R, K], K zero-padded to Kp (tensor-core
+    contractions take K in units of 64): the K-major operands of y = x W^T and dx = dy W, produced by ONE kernel launch and
+    cached together."""
+    R_, K = W.shape
+    Kp = K if Kp is None else Kp
+
+    def build():
+        Wc = W.detach().contiguous()
+        w16 = torch.empty(R_, Kp, device=W.device, dtype=torch.bfloat16)
+        wt16 = torch.empty(Kp, R_, device=W.device, dtype=torch.bfloat16)
+        check(_lib.load().tbns_cast_bf16_pair(_p(Wc), _p(w16), _p(wt16), R_, K, Kp, _stream()), "tbns_cast_bf16_pair")
+        _count(1)
+        return w16, wt16
+    return _w16_cached(W, ("pair", Kp), build)
+
+
 def weight_bf16(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     """bf16 (optionally transposed) copy of a weight matrix as a K-major tensor-core operand."""
-    return _w16_cached(W, (transpose, 0),
-                       lambda: cast_bf16(W.detach().t().contiguous() if transpose else W.detach().contiguous()))
+    return weight_bf16_pair(W)[1 if transpose else 0]
 
 
 def weight_bf16_padded(W: torch.Tensor, Kp: int, transpose: bool = False) -> torch.Tensor:
-    """like weight_bf16 for a weight [R, K] whose K is zero-padded to Kp (tensor-core contractions take K in units of 64):
-    [R, Kp] or, transposed, [Kp, R]."""
-    def build():
-        wp = torch.zeros(W.shape[0], Kp, device=W.device, dtype=torch.float32)
-        wp[:, :W.shape[1]] = W.detach()
-        return cast_bf16(wp.t().contiguous() if transpose else wp)
-    return _w16_cached(W, (transpose, Kp), build)
+    """like weight_bf16 for a weight [R, K] whose K is zero-padded to Kp: [R, Kp] or, transposed, [Kp, R]."""
+    return weight_bf16_pair(W, Kp)[1 if transpose else 0]
 
 
 def tc_supported(Cin: int, N: int, taps: int) -> bool:
@@ -443,23 +461,34 @@ class LayerNormFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # projection weight packing (cached by the modules; see model/Physics_Attention.py in this package)
 # ------------------------------------------------------------------------------------------------
-def pack_proj_weights(Wx, bx, Wfx, bfx):
-    """nn.Conv2d [I,C,3,3] / nn.Linear [I,C] pair -> (Wf [2I, taps*C], Wd [C, taps*2I], bcat [2I])."""
+def pack_proj_weights(Wx, bx, Wfx, bfx, bf16_only: bool = False):
+    """nn.Conv2d [I,C,3,3] / nn.Linear [I,C] pair -> (Wf [2I, taps*C], Wd [C, taps*2I], bcat [2I], Wf16, Wd16); one launch.
+    bf16_only (the module runs the tensor-core path): only the bf16 operands are produced and returned in the Wf / Wd slots
+    as well."""
     _chk(Wx, bx, Wfx, bfx)
     I, C_ = Wx.shape[0], Wx.shape[1]
     taps = 9 if Wx.dim() == 4 else 1
-    Wf = torch.empty(2 * I, taps * C_, device=Wx.device, dtype=torch.float32)
-    Wd = torch.empty(C_, taps * 2 * I, device=Wx.device, dtype=torch.float32)
-    bcat = torch.empty(2 * I, device=Wx.device, dtype=torch.float32)
-    check(_lib.load().tbns_pack_proj_weights(_p(Wx), _p(bx), _p(Wfx), _p(bfx), _p(Wf), _p(Wd), _p(bcat), I, C_, taps, _stream()),
-          "tbns_pack_proj_weights")
+    dev = Wx.device
+    bcat = torch.empty(2 * I, device=dev, dtype=torch.float32)
+    want_f = tc_supported(C_, 2 * I, taps)
+    want_d = tc_supported(2 * I, C_, taps)
+    bf16_only = bf16_only and want_f and want_d
+    Wf = None if bf16_only else torch.empty(2 * I, taps * C_, device=dev, dtype=torch.float32)
+    Wd = None if bf16_only else torch.empty(C_, taps * 2 * I, device=dev, dtype=torch.float32)
+    Wf16 = torch.empty(2 * I, taps * C_, device=dev, dtype=torch.bfloat16) if want_f else None
+    Wd16 = torch.empty(C_, taps * 2 * I, device=dev, dtype=torch.bfloat16) if want_d else None
+    check(_lib.load().tbns_pack_proj_weights16(_p(Wx), _p(bx), _p(Wfx), _p(bfx), _p(Wf), _p(Wd), _p(Wf16), _p(Wd16), _p(bcat), I, C_,
+                                               taps, _stream()), "tbns_pack_proj_weights16")
     _count(1)
-    Wf16 = Wd16 = None
-    if tc_supported(C_, 2 * I, taps):
-        Wf16 = cast_bf16(Wf)
-    if tc_supported(2 * I, C_, taps):
-        Wd16 = cast_bf16(Wd)
+    if bf16_only:
+        return Wf16, Wd16, bcat, Wf16, Wd16
     return Wf, Wd, bcat, Wf16, Wd16
+
+
+def pa_tc_shapes_ok(C_, I2, HG, Cout, taps) -> bool:
+    """shape rules of the tensor-core route of the whole attention module (see _pa_tc_ok)"""
+    return (tc_supported(C_, I2, taps) and tc_supported(I2, C_, taps) and wgrad_supported(C_, I2, taps) and tc_supported(HG, Cout, 1)
+            and tc_supported(Cout, HG, 1) and wgrad_supported(HG, Cout, 1))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -469,9 +498,7 @@ def _pa_tc_ok(precision, C_, I2, HG, Cout, taps, packed16) -> bool:
     """bf16 mode runs every token contraction of the module on tcgen05 when all of them fit the tensor-core kernels'
     shape rules (channel counts multiples of 64 / 128); otherwise the whole module uses the fp32 SIMT engine with
     bf16-rounded operands (same numerics, slower)."""
-    return (precision == TBNS_PREC_BF16 and packed16 and tc_supported(C_, I2, taps) and tc_supported(I2, C_, taps)
-            and wgrad_supported(C_, I2, taps) and tc_supported(HG, Cout, 1) and tc_supported(Cout, HG, 1)
-            and wgrad_supported(HG, Cout, 1))
+    return precision == TBNS_PREC_BF16 and packed16 and pa_tc_shapes_ok(C_, I2, HG, Cout, taps)
 
 
 def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, heads: int,
@@ -821,7 +848,7 @@ class PaEncodeFn(torch.autograd.Function):
         _begin_forward()
         x = x.contiguous()
         Wf, Wd, bcat, Wf16, Wd16 = packed
-        _chk(x, temperature, Ws, bs, Wq, Wk, Wv, Wo, Wf, Wd, bcat)
+        _chk(x, temperature, Ws, bs, Wq, Wk, Wv, Wo, bcat)
         temperature_c = temperature.contiguous()
         O, w, saved = pa_encode_forward(x, temperature_c, Wf, bcat, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
                                         Wv.contiguous(), Wo.contiguous(), heads, grid, precision, Wf16)
@@ -1048,7 +1075,7 @@ class PhysicsAttentionFn(torch.autograd.Function):
         if residual is not None:
             residual = residual.contiguous()
         Wf, Wd, bcat, Wf16, Wd16 = packed
-        _chk(x, residual, temperature, Ws, bs, Wq, Wk, Wv, Wo, bo, Wf, Wd, bcat)
+        _chk(x, residual, temperature, Ws, bs, Wq, Wk, Wv, Wo, bo, bcat)
         temperature_c = temperature.contiguous()
         out, saved = pa_forward(x, temperature_c, Wf, bcat, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
                                 Wv.contiguous(), Wo.contiguous(), bo.contiguous(), residual, heads, grid, precision, Wf16)
@@ -1084,7 +1111,7 @@ class AttnBlockFn(torch.autograd.Function):
         fx = fx.contiguous()
         Wf, Wd, bcat, Wf16, Wd16 = packed
         ln_w, ln_b = ln_w.contiguous(), ln_b.contiguous()
-        _chk(fx, ln_w, ln_b, temperature, Ws, bs, Wq, Wk, Wv, Wo, bo, Wf, Wd, bcat)
+        _chk(fx, ln_w, ln_b, temperature, Ws, bs, Wq, Wk, Wv, Wo, bo, bcat)
         B, N, C_ = fx.shape
         structured = grid is not None
         tc = _pa_tc_ok(precision, C_, Wf.shape[0], heads * Ws.shape[0], Wo.shape[0], 9 if structured else 1, Wf16 is not None)
@@ -1213,6 +1240,46 @@ def mlp_tc_ok(K: int, R: int, Cout: int) -> bool:
             and wgrad_supported(Cout, R, 1) and wgrad_supported(R, Kp, 1))
 
 
+def _mlp_tc_forward(in16, W1, b1, W2, b2, Kp, out_shape):
+    """Linear(Kp -> R) + GELU + Linear(R -> Cout) on the tensor cores from the packed bf16 input [M, Kp]"""
+    M = in16.shape[0]
+    R, Cout = W1.shape[0], W2.shape[0]
+    dev = in16.device
+    b1, b2 = b1.contiguous(), b2.contiguous()
+    pre16 = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
+    hid16 = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
+    gemm_tc(in16, weight_bf16_padded(W1, Kp), None, b1, 1, 1, M, Kp, R, act=3, aux_out=pre16, aux_bf16=1, C16=hid16, tag="pre_fc1")
+    out = torch.empty(*out_shape, Cout, device=dev, dtype=torch.float32)
+    gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, tag="pre_fc2")
+    return out, pre16, hid16
+
+
+def _mlp_tc_backward(dout, in16, W1, W2, pre16, hid16, K, need_dx):
+    """-> (dxp [M, Kp] fp32 | None, dW1 [R, K], db1, dW2, db2)"""
+    M, Kp = in16.shape
+    R, Cout = W1.shape[0], W2.shape[0]
+    f32 = dict(device=dout.device, dtype=torch.float32)
+    dout = dout.contiguous()
+    dout16, db2 = _take_grad16(dout)
+    if dout16 is None:
+        dout16 = cast_bf16(dout)
+    if db2 is None:
+        db2 = colsum(dout, M, Cout)
+    dW2 = torch.empty(Cout, R, **f32)
+    gemm_tc_wgrad(dout16, hid16, 1, 1, M, Cout, R, C=dW2, tag="pre_dW2")
+    dpre16 = torch.empty(M, R, device=dout.device, dtype=torch.bfloat16)
+    gemm_tc(dout16, weight_bf16(W2, transpose=True), None, None, 1, 1, M, Cout, R, act=4, aux_in=pre16, aux_bf16=1, C16=dpre16,
+            tag="pre_dpre")
+    db1 = colsum_bf16(dpre16, M, R)
+    dW1p = torch.empty(R, Kp, **f32)
+    gemm_tc_wgrad(dpre16, in16, 1, 1, M, R, Kp, C=dW1p, tag="pre_dW1")
+    dxp = None
+    if need_dx:
+        dxp = torch.empty(M, Kp, **f32)
+        gemm_tc(dpre16, weight_bf16_padded(W1, Kp, transpose=True), dxp, None, 1, 1, M, R, Kp, tag="pre_dx")
+    return dxp, dW1p[:, :K], db1, dW2, db2
+
+
 class MlpFn(torch.autograd.Function):
     """`preprocess`: Linear(K -> R) + GELU + Linear(R -> Cout) on the tensor cores (bf16 mode)
     model/Transolver_Structured_Mesh_2D.py:13-38,165-166,206-207.  K (= fun_dim + 64 or + space_dim) is zero-padded to a
@@ -1224,17 +1291,12 @@ class MlpFn(torch.autograd.Function):
         _begin_forward()
         K = inp.shape[-1]
         M = inp.numel() // K
-        R, Cout = W1.shape[0], W2.shape[0]
         Kp = -(-K // 64) * 64
-        dev = inp.device
-        in16 = torch.zeros(M, Kp, device=dev, dtype=torch.bfloat16)
-        in16[:, :K] = inp.reshape(M, K)
-        b1, b2 = b1.contiguous(), b2.contiguous()
-        pre16 = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
-        hid16 = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
-        gemm_tc(in16, weight_bf16_padded(W1, Kp), None, b1, 1, 1, M, Kp, R, act=3, aux_out=pre16, aux_bf16=1, C16=hid16, tag="pre_fc1")
-        out = torch.empty(*inp.shape[:-1], Cout, device=dev, dtype=torch.float32)
-        gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, tag="pre_fc2")
+        in16 = torch.empty(M, Kp, device=inp.device, dtype=torch.bfloat16)
+        src = inp.reshape(M, K).float().contiguous()
+        check(_lib.load().tbns_pack_inputs(None, 0, None, 0, 0, _p(src), K, K, _p(in16), Kp, M, M, _stream()), "tbns_pack_inputs")
+        _count(1)
+        out, pre16, hid16 = _mlp_tc_forward(in16, W1, b1, W2, b2, Kp, inp.shape[:-1])
         ctx.save_for_backward(in16, W1, W2, pre16, hid16)
         ctx.K = K
         return out
@@ -1244,29 +1306,65 @@ class MlpFn(torch.autograd.Function):
     def backward(ctx, dout):
         in16, W1, W2, pre16, hid16 = ctx.saved_tensors
         K = ctx.K
-        M, Kp = in16.shape
-        R, Cout = W1.shape[0], W2.shape[0]
-        f32 = dict(device=dout.device, dtype=torch.float32)
-        dout = dout.contiguous()
-        dout16, db2 = _take_grad16(dout)
-        if dout16 is None:
-            dout16 = cast_bf16(dout)
-        if db2 is None:
-            db2 = colsum(dout, M, Cout)
-        dW2 = torch.empty(Cout, R, **f32)
-        gemm_tc_wgrad(dout16, hid16, 1, 1, M, Cout, R, C=dW2, tag="pre_dW2")
-        dpre16 = torch.empty(M, R, device=dout.device, dtype=torch.bfloat16)
-        gemm_tc(dout16, weight_bf16(W2, transpose=True), None, None, 1, 1, M, Cout, R, act=4, aux_in=pre16, aux_bf16=1, C16=dpre16,
-                tag="pre_dpre")
-        db1 = colsum_bf16(dpre16, M, R)
-        dW1p = torch.empty(R, Kp, **f32)
-        gemm_tc_wgrad(dpre16, in16, 1, 1, M, R, Kp, C=dW1p, tag="pre_dW1")
-        dinp = None
-        if ctx.needs_input_grad[0]:
-            dxp = torch.empty(M, Kp, **f32)
-            gemm_tc(dpre16, weight_bf16_padded(W1, Kp, transpose=True), dxp, None, 1, 1, M, R, Kp, tag="pre_dx")
-            dinp = dxp[:, :K].reshape(*dout.shape[:-1], K)
-        return dinp, dW1p[:, :K], db1, dW2, db2
+        dxp, dW1, db1, dW2, db2 = _mlp_tc_backward(dout, in16, W1, W2, pre16, hid16, K, ctx.needs_input_grad[0])
+        dinp = dxp[:, :K].reshape(*dout.shape[:-1], K) if dxp is not None else None
+        return dinp, dW1, db1, dW2, db2
+
+
+def _row_strided(t: torch.Tensor):
+    """[.., F] fp32 tensor whose rows are uniformly strided (last dim contiguous) -> (tensor to keep alive, row stride)"""
+    t = t if t.dtype == torch.float32 else t.float()
+    F = t.shape[-1]
+    ok = t.stride(-1) == 1 or F == 1
+    ld = t.stride(-2) if t.dim() >= 2 else F
+    for d in range(t.dim() - 2, 0, -1):     # leading dims must collapse onto the row stride
+        ok = ok and t.stride(d - 1) == t.stride(d) * t.shape[d]
+    if not ok or ld < F or (t.data_ptr() % 4):
+        t = t.contiguous()
+        ld = F
+    return t, ld
+
+
+class PackedMlpFn(torch.autograd.Function):
+    """`preprocess(cat(x, fx))` (model/Transolver_Structured_Mesh_2D.py:203-207) with the concatenation fused into the load:
+    the bf16 operand of the first Linear is written in ONE pass from a bf16 feature table [N, R] broadcast over the batch
+    (the unified-position features; the reference materialises pos.repeat(B) in fp32 every call), an optional fp32 source
+    (raw coordinates) and the input fields `fx` - which may be a strided window of a frame history, so the window shift of
+    the rollout loops (SOL_Transolver_Structured_Mesh_2D.py:47-52) costs nothing."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, tab16, src1, fx, W1, b1, W2, b2):
+        _begin_forward()
+        B, N = fx.shape[0], fx.shape[1]
+        M = B * N
+        R = tab16.shape[-1] if tab16 is not None else 0
+        F1 = src1.shape[-1] if src1 is not None else 0
+        F2 = fx.shape[-1]
+        K = R + F1 + F2
+        Kp = -(-K // 64) * 64
+        s1, ld1 = _row_strided(src1) if src1 is not None else (None, 0)
+        s2, ld2 = _row_strided(fx)
+        in16 = torch.empty(M, Kp, device=fx.device, dtype=torch.bfloat16)
+        check(_lib.load().tbns_pack_inputs(_p(tab16), R, _p(s1), ld1, F1, _p(s2), ld2, F2, _p(in16), Kp, M, N, _stream()),
+              "tbns_pack_inputs")
+        _count(1)
+        out, pre16, hid16 = _mlp_tc_forward(in16, W1, b1, W2, b2, Kp, (B, N))
+        ctx.save_for_backward(in16, W1, W2, pre16, hid16)
+        ctx.dims = (R, F1, F2, B, N)
+        return out
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, dout):
+        in16, W1, W2, pre16, hid16 = ctx.saved_tensors
+        R, F1, F2, B, N = ctx.dims
+        K = R + F1 + F2
+        need1, need2 = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dxp, dW1, db1, dW2, db2 = _mlp_tc_backward(dout, in16, W1, W2, pre16, hid16, K, need1 or need2)
+        d1 = dxp[:, R:R + F1].reshape(B, N, F1) if need1 else None
+        d2 = dxp[:, R + F1:K].reshape(B, N, F2) if need2 else None
+        return None, d1, d2, dW1, db1, dW2, db2
 
 
 class LnLinearFn(torch.autograd.Function):
@@ -1340,3 +1438,27 @@ class LnLinearFn(torch.autograd.Function):
         dfx = dfx.view_as(fx)
         _stash_grad16(dfx, dfx16, dfsum)
         return dfx, dg, dbeta, dW, db, None, None
+
+
+def ln_linear_into(fx, gamma, beta, W, b, eps, precision, out):
+    """inference-only form of LnLinearFn: mlp2(ln_3(fx)) written in place into `out`, a [.., out_dim] view whose rows may be
+    strided (one column of a frame history: the rollout needs no concatenation afterwards).  Returns `out`."""
+    lib = _lib.load()
+    fx = fx.contiguous()
+    C_ = fx.shape[-1]
+    M = fx.numel() // C_
+    Od = W.shape[0]
+    if (Od == 1 and lib.tbns_ln_linear1_supported(C_) and out.dtype == torch.float32 and out.is_cuda and out.numel() == M
+            and _row_strided(out)[0] is out):
+        gamma, beta, W, b = (t.detach().contiguous() for t in (gamma, beta, W, b))
+        _chk(fx, gamma, beta, W, b)
+        mean = torch.empty(M, device=fx.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        with torch.cuda.device(fx.device), _Timed("ln_linear1_fwd"):
+            check(lib.tbns_ln_linear1_fwd_strided(_p(fx), _p(gamma), _p(beta), _p(W), _p(b), _p(out), _row_strided(out)[1], _p(mean),
+                                                  _p(rstd), M, C_, float(eps), _stream()), "tbns_ln_linear1_fwd_strided")
+        _count(1)
+        return out
+    with torch.no_grad():
+        out.copy_(LnLinearFn.apply(fx, gamma, beta, W, b, eps, precision))
+    return out

@@ -134,21 +134,40 @@ def train_step(model, optimizer, scheduler, grads: Optional[FlatGradients], x, f
     return loss.detach()
 
 
-def unrolled_train_step(sol_model, optimizer, scheduler, grads: Optional[FlatGradients], x, fx, yy, T: int, step: int = 1):
-    """ns_vorticity_unrolling.py:225-244: windows of `look_ahead` chained calls, loss on the last prediction of each window,
-    teacher forcing between windows."""
+def unrolled_step_loss(sol_model, x, fx, yy, T: int, step: int = 1, batched: bool = True) -> torch.Tensor:
+    """summed relative-L2 loss of one ns_vorticity_unrolling.py:225-244 batch: windows of `look_ahead` CHAINED model calls
+    (the prediction is fed back inside a window), loss on the last prediction of each window, ground truth fed back between
+    windows.  Because the ground truth is fed back between windows, the input of window t is known up front
+    (cat(fx, yy)[..., t : t + T_in]); batched=True stacks the windows on the batch axis, so the step is `look_ahead`
+    sequential calls on T/look_ahead * B samples instead of T calls on B samples - same math."""
     bsz = x.shape[0]
     look_ahead = sol_model.n
+    off = look_ahead * step
+    starts = list(range(0, T - off + 1, off))
+    if batched:
+        T_in = fx.shape[-1]
+        full = torch.cat((fx, yy), dim=-1)
+        win = torch.cat([full[..., t:t + T_in] for t in starts], dim=0)
+        y = torch.cat([yy[..., t + off - step:t + off] for t in starts], dim=0)
+        im = sol_model(x.repeat(len(starts), 1, 1), win)
+        return rel_l2_sum(im.reshape(len(starts) * bsz, -1), y.reshape(len(starts) * bsz, -1))
+    loss = 0
+    for t in starts:
+        y = yy[..., t + off - step:t + off]
+        im = sol_model(x, fx)
+        loss = loss + rel_l2_sum(im.reshape(bsz, -1), y.reshape(bsz, -1))
+        fx = torch.cat((fx[..., off:], yy[..., t:t + off]), dim=-1)
+    return loss
+
+
+def unrolled_train_step(sol_model, optimizer, scheduler, grads: Optional[FlatGradients], x, fx, yy, T: int, step: int = 1,
+                        batched: bool = False):
+    """one optimizer step of ns_vorticity_unrolling.py:225-244 (see unrolled_step_loss)"""
     if grads is not None:
         grads.begin()
     else:
         optimizer.zero_grad(set_to_none=True)
-    loss = 0
-    for t in range(0, T - look_ahead * step + 1, look_ahead * step):
-        y = yy[..., t + (look_ahead - 1) * step: t + look_ahead * step]
-        im = sol_model(x, fx)
-        loss = loss + rel_l2_sum(im.reshape(bsz, -1), y.reshape(bsz, -1))
-        fx = torch.cat((fx[..., look_ahead * step:], yy[..., t:t + look_ahead * step]), dim=-1)
+    loss = unrolled_step_loss(sol_model, x, fx, yy, T, step, batched)
     loss.backward()
     if grads is not None:
         grads.finish()
@@ -161,7 +180,20 @@ def unrolled_train_step(sol_model, optimizer, scheduler, grads: Optional[FlatGra
 
 @torch.no_grad()
 def rollout(model: Callable, x, fx, T: int, step: int = 1) -> torch.Tensor:
-    """closed-loop autoregressive rollout (predictions fed back): returns [B, N, T]"""
+    """closed-loop autoregressive rollout (predictions fed back; exp_ns.py:225-241, ns_vorticity_unrolling.py:264-286):
+    returns [B, N, T].
+
+    Models of this package run the FUSED rollout step: all frames live in one history buffer [B, N, T_in + T]; the input of
+    step t is the strided window hist[..., t : t + T_in] (read directly by the packed preprocess, ops.PackedMlpFn) and the
+    last layer writes its prediction straight into column T_in + t (`out=`), so the reference's per-step
+    `cat(fx[..., step:], im)` and the final `cat(preds)` do not exist.  Any other callable takes the literal loop."""
+    if getattr(model, "_packed_preprocess_ok", None) is not None and fx.is_cuda and model._packed_preprocess_ok(x, fx):
+        B, N, T_in = fx.shape
+        hist = torch.empty(B, N, T_in + T, device=fx.device, dtype=torch.float32)
+        hist[..., :T_in] = fx
+        for t in range(0, T, step):
+            model(x, fx=hist[..., t:t + T_in], out=hist[..., T_in + t:T_in + t + step])
+        return hist[..., T_in:]
     preds = []
     for _ in range(0, T, step):
         im = model(x, fx=fx)
@@ -234,12 +266,15 @@ class GraphedTrainStep:
     capturable=True and a tensor lr (the host-side scheduler writes the new lr into that tensor after each replay)."""
 
     def __init__(self, model, optimizer, scheduler, grads: FlatGradients, example, T: int, step: int = 1,
-                 batched: bool = True, warmup: int = 3, buckets: int = 1):
+                 batched: bool = True, warmup: int = 3, buckets: int = 1, loss_fn: Optional[Callable] = None):
+        """loss_fn(model, x, fx, yy) -> scalar loss; default: the teacher-forced step loss of exp_ns.py (step_loss).  Pass
+        `lambda m, x, fx, yy: unrolled_step_loss(m, x, fx, yy, T, step)` with a SOL_... model for the unrolled driver."""
         self.model, self.opt, self.sched, self.grads = model, optimizer, scheduler, grads
         self.T, self.step_, self.batched = T, step, batched
+        self.loss_fn = loss_fn or (lambda m, x, fx, yy: step_loss(m, x, fx, yy, T, step, batched))
         self.static = tuple(torch.empty_like(t, device=next(model.parameters()).device) for t in example)
         self.load(example)
-        blocks = list(getattr(model, "blocks", []))
+        blocks = list(getattr(model, "blocks", None) or getattr(getattr(model, "transolver_model", None), "blocks", []))
         self.nb = max(1, min(int(buckets), len(blocks)))
         if self.nb > 1:
             self._plan_stages(blocks)
@@ -330,7 +365,7 @@ class GraphedTrainStep:
         out = None
         if k == 0:
             x, fx, yy = self.static
-            self._loss_t = step_loss(self.model, x, fx, yy, self.T, self.step_, self.batched)
+            self._loss_t = self.loss_fn(self.model, x, fx, yy)
             out = self._loss_t.detach()
             root, gout = self._loss_t, None
         else:
@@ -360,7 +395,7 @@ class GraphedTrainStep:
     def _fwd_bwd(self):
         x, fx, yy = self.static
         self.grads.begin()
-        loss = step_loss(self.model, x, fx, yy, self.T, self.step_, self.batched)
+        loss = self.loss_fn(self.model, x, fx, yy)
         loss.backward()
         self.grads.finish()
         return loss.detach()
@@ -390,3 +425,45 @@ class GraphedTrainStep:
         if self.sched is not None:
             self.sched.step()     # host-side schedule; writes the new lr into the device tensor the graph reads
         return self.loss
+
+
+class GraphedRollout:
+    """closed-loop rollout (train.rollout) of a fixed shape replayed from ONE CUDA graph: T model calls whose inputs are
+    strided windows of the static frame history and whose outputs land in its next column.  `load` copies a (host or
+    device) batch in; `__call__` replays and returns the [B, N, T] view of the predictions inside the static history."""
+
+    def __init__(self, model, example, T: int, step: int = 1, warmup: int = 2):
+        from . import ops
+        x, fx = example
+        dev = next(model.parameters()).device
+        self.model, self.T, self.step_, self.T_in = model, T, step, fx.shape[-1]
+        self.x = torch.empty_like(x, device=dev)
+        self.hist = torch.zeros(fx.shape[0], fx.shape[1], self.T_in + T, device=dev, dtype=torch.float32)
+        self.load((x, fx))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ops.begin_capture()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._run()
+
+    @torch.no_grad()
+    def _run(self):
+        for t in range(0, self.T, self.step_):
+            self.model(self.x, fx=self.hist[..., t:t + self.T_in], out=self.hist[..., self.T_in + t:self.T_in + t + self.step_])
+
+    def load(self, batch):
+        x, fx = batch
+        self.x.copy_(x, non_blocking=True)
+        self.hist[..., :self.T_in].copy_(fx, non_blocking=True)
+
+    def __call__(self, batch=None) -> torch.Tensor:
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        return self.hist[..., self.T_in:]
