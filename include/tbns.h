@@ -132,6 +132,12 @@ int tbns_layernorm_bwd(const float* dy, const float* x, const float* mean, const
                        float* dsum /* optional [C]: column sums of dx = bias gradient of the layer that produced this stream */,
                        float* ws, int rows, int C, void* stream);
 
+/* same for a bf16 incoming gradient dy16 (written bf16-only by the data-gradient GEMM in bf16 mode); C in {128, 256, 512};
+ * sums [3][C] = dgamma | dbeta | column sums of dx */
+int tbns_layernorm_bwd_supported16(int C);
+int tbns_layernorm_bwd16(const void* dy16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                         const float* dres, float* dx, void* dx16, float* sums, float* ws, int rows, int C, void* stream);
+
 /* Last layer with out_dim = 1: out = mlp2(ln_3(x)) = LN(x) . w + b in one pass over x
  * (model/Transolver_Structured_Mesh_2D.py:66-67,72-73).  C in {128, 256, 512}. */
 int tbns_ln_linear1_supported(int C);

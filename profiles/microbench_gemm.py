@@ -22,12 +22,14 @@ hid16 = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
 res = torch.randn(M, C, generator=g).to(dev)
 out = torch.empty(M, C, device=dev)
 dXF16 = torch.randn(M, I2, generator=g).to(dev).bfloat16()
+Wd16 = (torch.randn(C, 9 * I2, generator=g) / 68).to(dev).bfloat16()
 dWx = torch.empty(C, C, 3, 3, device=dev)
 dWfx = torch.empty(C, C, 3, 3, device=dev)
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
 cases = {
     "conv_fprop 81920x2304x512": (lambda: ops.gemm_tc(x16, Wf16, XF, bias, B, Hg, Wg, C, I2, 9, 0), 2.0 * M * 9 * C * I2),
+    "conv_dgrad 81920x4608x256": (lambda: ops.gemm_tc(dXF16, Wd16, out, None, B, Hg, Wg, I2, C, 9, 1), 2.0 * M * 9 * C * I2),
     "fc1 81920x256x256 +bias+gelu+pre16+bf16": (lambda: ops.gemm_tc(x16, W1, None, b1, 1, 1, M, C, C, act=1, aux_out=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
     "dpre 81920x256x256 gelu'(pre16)+bf16": (lambda: ops.gemm_tc(x16, W1, None, None, 1, 1, M, C, C, act=2, aux_in=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
     "fc1d 81920x256x256 +bias+gelu+gelu'16+bf16 (act 3)": (lambda: ops.gemm_tc(x16, W1, None, b1, 1, 1, M, C, C, act=3, aux_out=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),

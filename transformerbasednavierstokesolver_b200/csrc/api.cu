@@ -1,7 +1,10 @@
 // Library-level plumbing of libtbns: thread-local error string, version, device probe.
 #include <stdarg.h>
 
-#include "common.cuh"
+#include <mutex>
+#include <unordered_map>
+
+#include "tc_common.cuh"
 
 namespace tbns {
 static thread_local char g_err[512] = "";
@@ -10,6 +13,38 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+int encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  k.v[0] = reinterpret_cast<uint64_t>(ptr);
+  k.v[1] = ((uint64_t)dt << 32) | ((uint64_t)rank << 8) | (uint64_t)(dev & 0xff);
+  for (int i = 0; i < rank; ++i) {
+    k.v[2 + i] = dims[i];
+    k.v[10 + i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) k.v[6 + i] = strides_bytes[i];
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(k);
+    if (it != cache.end()) {
+      *m = it->second;
+      return TBNS_OK;
+    }
+  }
+  const int rc = encode_tmap_uncached(m, dt, ptr, rank, dims, strides_bytes, box);
+  if (rc == TBNS_OK) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(k, *m);
+  }
+  return rc;
 }
 }  // namespace tbns
 

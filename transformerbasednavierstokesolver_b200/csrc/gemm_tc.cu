@@ -8,12 +8,11 @@
 // in_project_x | in_project_fx as ONE GEMM (N = 2*inner_dim) — zero padding comes for free from TMA out-of-bounds
 // fill; flip = 1 gives the transposed convolution of the backward pass (dgrad); taps = 1 is a plain Linear.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0   : TMA producer  — cp.async.bulk.tensor 4D (A, one shifted box per tap) + 2D (W) into a STAGES-deep
-//              128B-swizzled shared-memory ring, completion on mbarriers (expect_tx)
-//   warp 1   : allocates TMEM, one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
-//              tcgen05.commit releases ring slots / publishes the accumulator
-//   warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns per warp), + bias, fp32 stores
+// Kernels in this file (all warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// the remaining warps = epilogue):
+//   gemm_tc_persistent_kernel  one CTA per SM loops over 128 x BN tiles, TMEM accumulator double-buffered (short-K contractions)
+//   gemm_tc_2cta_kernel        CTA pairs on 256 x 256 tiles, tcgen05.mma.cta_group::2 (the long-K projection conv / dgrad)
+//   gemm_tc_wgrad_kernel       token contraction (weight gradients), MN-major operands, split-K
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -97,152 +96,6 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base, int warp) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// TN kernel: C[token, n] = sum_k A[shift(token), k] W[n, k]   (both operands K-major)
-// ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using S = TcSmem<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t bar_full = base + S::BAR_OFF;
-  const uint32_t bar_empty = bar_full + STAGES * 8;
-  const uint32_t bar_acc = bar_empty + STAGES * 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR_OFF + (2 * STAGES + 1) * 8);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  const int mt = blockIdx.x;
-  const int tw = mt % p.tiles_w;
-  const int th = (mt / p.tiles_w) % p.tiles_h;
-  const int bimg = mt / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.BW, h0 = th * p.BH;
-  const int n0 = blockIdx.y * BN;
-  const int kc_per_tap = p.Cin / TC_BK;
-  const int nkb = p.taps * kc_per_tap;
-
-  const uint32_t tmem_base = tc_prologue<BN, STAGES>(bar_full, bar_empty, bar_acc, tmem_slot, &tmA, &tmB, warp, lane);
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      const int wb = p.w_batched ? bimg : 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(bar_empty + s * 8, ph ^ 1);
-        const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
-        int dy = 0, dx = 0;
-        if (p.taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
-          if (p.flip) { dy = -dy; dx = -dx; }
-        }
-        const uint32_t sa = base + s * S::STAGE_BYTES;
-        const uint32_t sb = sa + S::A_BYTES;
-        mbar_expect_tx(bar_full + s * 8, S::STAGE_BYTES);
-        tma_load_4d(sa, &tmA, bar_full + s * 8, kc * TC_BK, w0 + dx, h0 + dy, bimg);
-        tma_load_3d(sb, &tmB, bar_full + s * 8, kb * TC_BK, n0, wb);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_bf16(BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(bar_full + s * 8, ph);
-        tc_fence_after();
-        const uint32_t sa = base + s * S::STAGE_BYTES;
-        const uint32_t sb = sa + S::A_BYTES;
-#pragma unroll
-        for (int k = 0; k < TC_BK / TC_UK; ++k) {
-          const uint64_t ad = umma_desc_kmajor_sw128(sa + k * TC_UK * 2);
-          const uint64_t bd = umma_desc_kmajor_sw128(sb + k * TC_UK * 2);
-          umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(bar_empty + s * 8);  // slot free once these MMAs have read it
-      }
-      umma_commit(bar_acc);              // accumulator complete
-    }
-  } else {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;                 // tile row == TMEM lane
-    const int hh = r / p.BW, ww = r - hh * p.BW;
-    const int h = h0 + hh, w = w0 + ww;
-    const bool valid = (h < p.Hg) && (w < p.Wg);
-    const long long grow = ((long long)bimg * p.Hg + h) * p.Wg + w;
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (valid) {
-        const int n = n0 + c0;
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (p.act == 1) {
-          if (p.aux_out) {
-            float* ao = p.aux_out + grow * p.ldaux + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ao + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (p.act == 2) {
-          const float* ai = p.aux_in + grow * p.ldaux + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 a = *reinterpret_cast<const float4*>(ai + j);
-            v[j] *= gelu_erf_grad(a.x); v[j + 1] *= gelu_erf_grad(a.y); v[j + 2] *= gelu_erf_grad(a.z); v[j + 3] *= gelu_erf_grad(a.w);
-          }
-        }
-        if (p.residual) {
-          const float* rr = p.residual + grow * p.ldr + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 a = *reinterpret_cast<const float4*>(rr + j);
-            v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
-          }
-        }
-        if (p.round_tf32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            uint32_t u;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j]));
-            v[j] = __uint_as_float(u);
-          }
-        }
-        if (p.C) {
-          float* cr = p.C + grow * p.ldc + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        if (p.C16) {
-          __nv_bfloat16* cr = p.C16 + grow * p.ldc16 + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __nv_bfloat162 o[4] = {__floats2bfloat162_rn(v[j], v[j + 1]), __floats2bfloat162_rn(v[j + 2], v[j + 3]),
-                                   __floats2bfloat162_rn(v[j + 4], v[j + 5]), __floats2bfloat162_rn(v[j + 6], v[j + 7])};
-            *reinterpret_cast<uint4*>(cr + j) = *reinterpret_cast<uint4*>(o);
-          }
-        }
-      }
-    }
-  }
-  tc_teardown<BN>(tmem_base, warp);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Persistent TN kernel: one CTA per SM loops over output tiles; the fp32 accumulator is double-buffered in TMEM
 // (2 x BN columns) so the fused epilogue of tile i (8 warps: tcgen05.ld -> bias / GELU / GELU' / residual -> fp32 / bf16
 // stores) overlaps the TMA + tcgen05.mma main loop of tile i+1.  Roles: warp 0 TMA producer, warp 1 TMEM allocator +
@@ -275,63 +128,6 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   float c, d;
   gelu_parts(x, c, d);
   return fmaf(x, d, c);
-}
-
-// fused epilogue of one accumulator row segment: 32 consecutive columns starting at n of global row `grow`
-__device__ __forceinline__ void tc_epi_store(const TcParams& p, float (&v)[32], long long grow, int n) {
-  if (p.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-    }
-  }
-  if (p.act == 1) {
-    if (p.aux_out) {
-      float* ao = p.aux_out + grow * p.ldaux + n;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ao + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-  } else if (p.act == 2) {
-    const float* ai = p.aux_in + grow * p.ldaux + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 a = *reinterpret_cast<const float4*>(ai + j);
-      v[j] *= gelu_grad_fast(a.x); v[j + 1] *= gelu_grad_fast(a.y); v[j + 2] *= gelu_grad_fast(a.z); v[j + 3] *= gelu_grad_fast(a.w);
-    }
-  }
-  if (p.residual) {
-    const float* rr = p.residual + grow * p.ldr + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 a = *reinterpret_cast<const float4*>(rr + j);
-      v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
-    }
-  }
-  if (p.round_tf32) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      uint32_t u;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j]));
-      v[j] = __uint_as_float(u);
-    }
-  }
-  if (p.C) {
-    float* cr = p.C + grow * p.ldc + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-  }
-  if (p.C16) {
-    __nv_bfloat16* cr = p.C16 + grow * p.ldc16 + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      __nv_bfloat162 o[4] = {__floats2bfloat162_rn(v[j], v[j + 1]), __floats2bfloat162_rn(v[j + 2], v[j + 3]),
-                             __floats2bfloat162_rn(v[j + 4], v[j + 5]), __floats2bfloat162_rn(v[j + 6], v[j + 7])};
-      *reinterpret_cast<uint4*>(cr + j) = *reinterpret_cast<uint4*>(o);
-    }
-  }
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -630,6 +426,182 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the persistent TN kernel (long-K contractions: the 3x3 projection conv and its dgrad).
+// Two CTAs of a cluster (one TPC) own a 256 x 256 output tile: each CTA stages ITS 128 token rows of A and HALF of the
+// weight tile (128 of the 256 output channels) per k-block, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which
+// reads both halves of B from the two shared memories, and each CTA finds its 128 x 256 accumulator rows in its own TMEM.
+// Per CTA and k-block that is 32 KB of TMA traffic and 8 KB of operand reads per MMA instead of 48 KB / 12 KB, and the
+// ring gets 6 stages instead of 4 in the same shared memory - the single-CTA kernel's tensor pipe sat at 77 % waiting for
+// operands.  Protocol (CUTLASS sm100 2-SM pipelines): both producers signal the LEADER's full barrier (its expect_tx covers
+// both CTAs' bytes); tcgen05.commit multicasts the slot-free / accumulator-ready arrivals to both CTAs; the epilogue warps of
+// both CTAs hand the accumulator buffer back on the leader's barrier (remote arrive); cluster barriers fence set-up and
+// teardown.
+// ------------------------------------------------------------------------------------------------
+constexpr int TC2_BN = 256;
+constexpr int TC2_STAGES = 6;
+struct Tc2Smem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;            // this CTA's 128 rows
+  static constexpr int B_BYTES = (TC2_BN / 2) * TC_BK * 2;     // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = TC2_STAGES * STAGE_BYTES;
+  static constexpr int NBAR = 2 * TC2_STAGES + 4;
+  static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCP_THREADS, 1)
+gemm_tc_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
+                    int total_pair_tiles, int m_tiles) {
+  using S = Tc2Smem;
+  constexpr int BN = TC2_BN, STAGES = TC2_STAGES;
+  constexpr int TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bar_full = base + S::BAR_OFF;        // used in the leader CTA only
+  const uint32_t bar_empty = bar_full + STAGES * 8;   // per CTA (multicast commit)
+  const uint32_t bar_accf = bar_empty + STAGES * 8;   // [2] per CTA (multicast commit)
+  const uint32_t bar_acce = bar_accf + 16;            // [2] used in the leader CTA only (both CTAs' epilogue warps arrive)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR_OFF + S::NBAR * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_tiles = p.N / BN;
+  const int kc_per_tap = p.Cin / TC_BK;
+  const int nkb = p.taps * kc_per_tap;
+  const int first = (int)cluster_id_x(), stride = (int)cluster_count_x();
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_accf + a * 8, 1);
+      mbar_init(bar_acce + a * 8, 2 * TCP_EPI_WARPS);   // one arrival per epilogue warp of each CTA
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own A rows + own half of B; bytes are counted on the leader's full barrier =====
+      uint32_t it = 0;
+      for (int tile = first; tile < total_pair_tiles; tile += stride) {
+        const int nt = tile % n_tiles, mt = 2 * (tile / n_tiles) + (int)rank;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, bimg = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH, n0 = nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(bar_empty + s * 8, ph ^ 1);
+          const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
+          int dy = 0, dx = 0;
+          if (p.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+            if (p.flip) { dy = -dy; dx = -dx; }
+          }
+          const uint32_t sa = base + s * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
+          const uint32_t full_leader = mapa_shared(bar_full + s * 8, 0);
+          if (rank == 0) mbar_expect_tx(bar_full + s * 8, 2 * S::STAGE_BYTES);
+          // an M tile past the end (odd tile count) has bimg == Bimg: the box is out of bounds and TMA fills zeros
+          tma_load_4d_2sm(sa, &tmA, full_leader, kc * TC_BK, w0 + dx, h0 + dy, bimg);
+          tma_load_3d_2sm(sb, &tmB, full_leader, kb * TC_BK, n0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = umma_idesc_bf16_2sm(BN);
+      uint32_t it = 0, j = 0;
+      for (int tile = first; tile < total_pair_tiles; tile += stride, ++j) {
+        const uint32_t as = j & 1;
+        mbar_wait(bar_acce + as * 8, ((j >> 1) & 1) ^ 1);   // both CTAs' epilogues have drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t dtmem = tmem_base + as * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(bar_full + s * 8, ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UK; ++k) {
+            const uint64_t ad = umma_desc_kmajor_sw128(sa + k * TC_UK * 2);
+            const uint64_t bd = umma_desc_kmajor_sw128(sb + k * TC_UK * 2);
+            umma_bf16_2sm(dtmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(bar_empty + s * 8, 3);   // the slot is free in both CTAs
+        }
+        umma_commit_2sm(bar_accf + as * 8, 3);     // accumulator complete: both CTAs' epilogues
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..17 of both CTAs, each on its own 128 accumulator rows =====
+    const int q = warp & 3;
+    const int slot = (warp - 2) >> 2;
+    const uint32_t acce_leader = mapa_shared(bar_acce, 0);
+    uint32_t j = 0;
+    for (int tile = first; tile < total_pair_tiles; tile += stride, ++j) {
+      const int nt = tile % n_tiles, mt = 2 * (tile / n_tiles) + (int)rank;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, bimg = mt / (p.tiles_w * p.tiles_h);
+      const int n0 = nt * BN;
+      long long grow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = q * 32 + (lane >> 2) + 8 * k;
+        const int hh = r / p.BW, ww = r - hh * p.BW;
+        const int h = th * p.BH + hh, w = tw * p.BW + ww;
+        grow[k] = (mt < m_tiles && h < p.Hg && w < p.Wg) ? ((long long)bimg * p.Hg + h) * p.Wg + w : -1;
+      }
+      const uint32_t as = j & 1;
+      mbar_wait(bar_accf + as * 8, (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = slot * 32; c0 < BN; c0 += 32 * (TCP_EPI_WARPS / 4)) {
+        float v[2][16];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0);
+        tmem_ld_16x256b_x4(ta, v[0]);
+        tmem_ld_16x256b_x4(ta + (16u << 16), v[1]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 * (TCP_EPI_WARPS / 4) >= BN) {
+          // last TMEM read of this tile by this warp: hand the buffer back to the leader's MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acce_leader + as * 8);
+        }
+        tc_epi_frag2<EPI>(p, v, grow, n0 + c0, lane);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal or read it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // NT ("wgrad") kernel: D[(tap, a), n] = sum_token A[shift(token, tap), a] * B[token, n]
 // Both operands are token-major in HBM, i.e. MN-major for the MMA: the SAME TMA boxes as above ([tokens][64 feat],
 // 128B swizzle) are consumed through MN-major UMMA descriptors, so no transposed copy of activations is ever made.
@@ -780,16 +752,6 @@ static int pick_bw(int Hg, int Wg, int tokens) {
   return best;
 }
 
-template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES>;
-  TBNS_SMEM_OPT_IN((gemm_tc_kernel<BN, STAGES>), S::TOTAL);
-  dim3 grid(m_tiles, p.N / BN);
-  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(tmA, tmB, p);
-  TBNS_LAUNCH_CHECK();
-  return TBNS_OK;
-}
-
 template <int BN, int STAGES, int EPI>
 static int launch_tcp_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
   using S = TcpSmem<BN, STAGES>;
@@ -824,6 +786,31 @@ static int launch_tcp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPa
     }
   }
   return launch_tcp_epi<BN, STAGES, -1>(tmA, tmB, p, m_tiles, st);
+}
+
+template <int EPI>
+static int launch_tc2_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st) {
+  TBNS_SMEM_OPT_IN((gemm_tc_2cta_kernel<EPI>), Tc2Smem::TOTAL);
+  const int pairs = (m_tiles + 1) / 2 * (p.N / TC2_BN);
+  int clusters = sm_count() / 2;
+  if (pairs < clusters) clusters = pairs;
+  gemm_tc_2cta_kernel<EPI><<<2 * clusters, TCP_THREADS, Tc2Smem::TOTAL, st>>>(tmA, tmB, p, pairs, m_tiles);
+  TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
+}
+
+// CTA-pair kernel: the long-K option sets only (projection fprop / dgrad); everything else stays on the single-CTA kernel
+static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles, cudaStream_t st, bool* handled) {
+  *handled = true;
+  switch (epi_code(p)) {
+    case (EPI_C): return launch_tc2_epi<EPI_C>(tmA, tmB, p, m_tiles, st);
+    case (EPI_C16): return launch_tc2_epi<EPI_C16>(tmA, tmB, p, m_tiles, st);
+    case (EPI_BIAS | EPI_C): return launch_tc2_epi<EPI_BIAS | EPI_C>(tmA, tmB, p, m_tiles, st);
+    case (EPI_BIAS | EPI_ROUND | EPI_C): return launch_tc2_epi<EPI_BIAS | EPI_ROUND | EPI_C>(tmA, tmB, p, m_tiles, st);
+    default: break;
+  }
+  *handled = false;
+  return TBNS_OK;
 }
 
 template <int BN, int STAGES>
@@ -883,46 +870,33 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
   int rc = encode_act(&tmA, d.A16, d.Bimg, d.Hg, d.Wg, d.Cin, p.BW, p.BH);
   if (rc) return rc;
   const int N = d.N;
-  // short K (<= 8 k-blocks: Linear / deslice / MLP contractions): the fused epilogue (GELU, residual, 1-3 output streams)
-  // outweighs the main loop, so run 128-wide tiles with a 3-stage ring (~99 KB) and let TWO CTAs share an SM: one CTA's
-  // epilogue overlaps the other's TMA/MMA phase and twice as many epilogue warps are resident.
-  const bool short_k = (d.taps * d.Cin) / TC_BK <= 8 && N % 128 == 0;
-  const int BN = short_k ? 128 : ((N % 256 == 0 && m_tiles * (N / 256) >= sm_count()) ? 256 : (N % 128 == 0 ? 128 : 64));
-  {
-    const cuuint64_t K = (cuuint64_t)d.taps * d.Cin;
+  const cuuint64_t K = (cuuint64_t)d.taps * d.Cin;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto encode_w = [&](CUtensorMap* m, int rows_per_box) {
     cuuint64_t dims[3] = {K, (cuuint64_t)N, (cuuint64_t)(d.w_batched ? d.Bimg : 1)};
     cuuint64_t str[2] = {K * 2, K * 2 * (cuuint64_t)N};
-    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, 1u};
-    rc = encode_bf16(&tmB, d.W16, 3, dims, str, box);
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)rows_per_box, 1u};
+    return encode_bf16(m, d.W16, 3, dims, str, box);
+  };
+  static const bool two_cta = [] { const char* e = getenv("TBNS_TC_2CTA"); return !e || atoi(e) != 0; }();
+  if (two_cta && N % TC2_BN == 0 && !d.w_batched && K / TC_BK >= 16 && m_tiles >= 2) {
+    // long K (the 3x3 projections and their dgrad): CTA pairs, tcgen05.mma.cta_group::2; each CTA loads half of the weight tile
+    rc = encode_w(&tmB, TC2_BN / 2);
     if (rc) return rc;
+    bool handled = false;
+    rc = launch_tc2(tmA, tmB, p, (int)m_tiles, st, &handled);
+    if (handled) return rc;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  static int persist = -1;
-  if (persist < 0) {
-    const char* e = getenv("TBNS_TC_PERSIST");
-    persist = e ? atoi(e) : 1;
-  }
-  if (persist) {
-    // persistent kernel: one CTA per SM, double-buffered TMEM accumulator, 8 epilogue warps
-    const char* e128 = getenv("TBNS_TC_SHORTK_BN128");
-    const bool bn128 = short_k && (e128 ? atoi(e128) != 0 : false);
-    const int BNp = (N % 256 == 0 && !bn128) ? 256 : (N % 128 == 0 ? 128 : 64);
-    if (BNp != BN) {
-      const cuuint64_t K = (cuuint64_t)d.taps * d.Cin;
-      cuuint64_t dims[3] = {K, (cuuint64_t)N, (cuuint64_t)(d.w_batched ? d.Bimg : 1)};
-      cuuint64_t str[2] = {K * 2, K * 2 * (cuuint64_t)N};
-      cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BNp, 1u};
-      rc = encode_bf16(&tmB, d.W16, 3, dims, str, box);
-      if (rc) return rc;
-    }
-    if (BNp == 256) return launch_tcp<256, 4>(tmA, tmB, p, (int)m_tiles, st);
-    if (BNp == 128) return launch_tcp<128, 6>(tmA, tmB, p, (int)m_tiles, st);
-    return launch_tcp<64, 8>(tmA, tmB, p, (int)m_tiles, st);
-  }
-  TBNS_REQUIRE(!d.aux_bf16 && d.act <= 2, "tbns_gemm_tc: bf16 aux buffers / act 3, 4 need the persistent kernel");
-  if (BN == 256) return launch_tc<256, 4>(tmA, tmB, p, (int)m_tiles, st);
-  if (BN == 128) return short_k ? launch_tc<128, 3>(tmA, tmB, p, (int)m_tiles, st) : launch_tc<128, 6>(tmA, tmB, p, (int)m_tiles, st);
-  return launch_tc<64, 8>(tmA, tmB, p, (int)m_tiles, st);
+  // persistent single-CTA kernel: one CTA per SM, double-buffered TMEM accumulator, 16 epilogue warps.  Short-K contractions
+  // (Linear / deslice / MLP: the fused epilogue outweighs the main loop) may run 128-wide tiles (TBNS_TC_SHORTK_BN128=1).
+  static const bool bn128 = [] { const char* e = getenv("TBNS_TC_SHORTK_BN128"); return e && atoi(e) != 0; }();
+  const bool short_k = K / TC_BK <= 8 && N % 128 == 0;
+  const int BN = (N % 256 == 0 && !(short_k && bn128)) ? 256 : (N % 128 == 0 ? 128 : 64);
+  rc = encode_w(&tmB, BN);
+  if (rc) return rc;
+  if (BN == 256) return launch_tcp<256, 4>(tmA, tmB, p, (int)m_tiles, st);
+  if (BN == 128) return launch_tcp<128, 6>(tmA, tmB, p, (int)m_tiles, st);
+  return launch_tcp<64, 8>(tmA, tmB, p, (int)m_tiles, st);
 }
 
 extern "C" int tbns_gemm_tc_wgrad_supported(int Ma, int Nb, int taps) {

@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
 // R1 (rank-one dy, the model's last layer mlp2 = Linear(C -> 1) after ln_3): dy[row][c] = dy[row] * wvec[c] is formed on the
 // fly from the [rows] gradient of the scalar output, and the first two accumulators hold S_c = sum_r dy[r]*xhat[r][c] and
 // D = sum_r dy[r] instead, from which dgamma = w*S, dbeta = w*D, dW = gamma*S + beta*D, db = D.
-template <int NV, bool R1>
+// DY16: dy arrives as bf16 (the data-gradient GEMM that produced it wrote bf16 only: 84 MB less traffic per launch at the
+// benchmark shape; the residual gradient stream `dres` stays fp32).
+template <int NV, bool R1, bool DY16 = false>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_reg_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                         const float* __restrict__ gamma, const float* __restrict__ dres,
@@ -262,6 +264,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_reg_kernel(const 
       if (R1) {
         const float4 w = w4[R1 ? k : 0];
         d4[k] = make_float4(dsc * w.x, dsc * w.y, dsc * w.z, dsc * w.w);
+      } else if (DY16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + off + k * 128);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        d4[k] = make_float4(a.x, a.y, b.x, b.y);
       } else {
         d4[k] = *reinterpret_cast<const float4*>(dy + off + k * 128);
       }
@@ -428,6 +435,30 @@ extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long
     if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     reduce_rows_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(in, out, rows, cols, cols);
   }
+  TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
+}
+
+extern "C" int tbns_layernorm_bwd_supported16(int C) { return (C == 128 || C == 256 || C == 512) ? 1 : 0; }
+
+extern "C" int tbns_layernorm_bwd16(const void* dy16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                    const float* dres, float* dx, void* dx16, float* sums /* [3][C] */, float* ws, int rows, int C,
+                                    void* stream) {
+  TBNS_REQUIRE(dy16 && x && mean && rstd && gamma && dx && sums && ws, "tbns_layernorm_bwd16: null pointer");
+  TBNS_REQUIRE(rows > 0 && tbns_layernorm_bwd_supported16(C), "tbns_layernorm_bwd16: C=%d unsupported (128, 256, 512)", C);
+  TBNS_REQUIRE(((reinterpret_cast<uintptr_t>(dy16) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+                 reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(dx16)) & 15) == 0,
+               "tbns_layernorm_bwd16: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(dx16);
+  const float* dy = reinterpret_cast<const float*>(dy16);
+  int ctas = cdiv(rows, LN_WARPS * 2);
+  if (ctas > LN_BWD_CTAS) ctas = LN_BWD_CTAS;
+  if (C == 128) layernorm_bwd_reg_kernel<1, false, true><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
+  else if (C == 256) layernorm_bwd_reg_kernel<2, false, true><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
+  else layernorm_bwd_reg_kernel<4, false, true><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
+  TBNS_LAUNCH_CHECK();
+  reduce_rows_par_kernel<<<cdiv(3 * C, 32), 1024, 0, st>>>(ws, sums, ctas, 3 * C, 3LL * C);
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }

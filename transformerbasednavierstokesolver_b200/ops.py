@@ -343,6 +343,23 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5, want32: bool 
     return y, y16, mean, rstd
 
 
+def layernorm_bwd16(dy16, x, mean, rstd, gamma, dres=None, want16: bool = True):
+    """layernorm_bwd for a bf16 incoming gradient -> (dx, dx16 | None, dgamma, dbeta, colsum(dx))"""
+    _chk(x, mean, rstd, gamma, dres)
+    lib = _lib.load()
+    C_ = x.shape[-1]
+    rows = x.numel() // C_
+    dx = torch.empty_like(x)
+    dx16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want16 else None
+    out3 = torch.empty(3, C_, device=x.device, dtype=torch.float32)
+    ws = torch.empty(lib.tbns_layernorm_bwd_ws_floats(C_), device=x.device, dtype=torch.float32)
+    with _Timed("layernorm_bwd"):
+        check(lib.tbns_layernorm_bwd16(_p(dy16), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), _p(out3), _p(ws),
+                                       rows, C_, _stream()), "tbns_layernorm_bwd16")
+    _count(2)
+    return dx, dx16, out3[0], out3[1], out3[2]
+
+
 def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, want16: bool = False, want_sum: bool = False):
     """returns (dx, dx16 | None, dgamma, dbeta[, colsum(dx)]); dx = LN'(dy) + dres"""
     _chk(dy, x, mean, rstd, gamma, dres)
@@ -570,7 +587,7 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
 
 
 def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, saved, heads: int,
-                grid: Optional[Tuple[int, int]], precision: int, Wd16=None, dout16=None, dbo=None):
+                grid: Optional[Tuple[int, int]], precision: int, Wd16=None, dout16=None, dbo=None, dx_bf16: bool = False):
     """returns dx and the parameter gradients in reference (state_dict) layouts.  `saved` is pa_forward's tuple; its last
     entry is the module input (fp32 in SIMT mode, its bf16 copy in tensor-core mode)."""
     lib = _lib.load()
@@ -654,13 +671,18 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
         check(lib.tbns_pa_dtau_finish(_p(dtau_part), _p(temperature), _p(dtemp), B, H, groups, int(structured), _stream()),
               "tbns_pa_dtau_finish")
     # (1a') projections: dgrad, wgrad (scattered straight into Conv2d / Linear weight layout)
-    dx = torch.empty(B, N, C_, **f32)
+    # dx_bf16 (tensor-core route, caller feeds a LayerNorm backward): the data gradient is written in bf16 only
+    dx_bf16 = dx_bf16 and tc
+    dx = torch.empty(B, N, C_, device=dev, dtype=torch.bfloat16) if dx_bf16 else torch.empty(B, N, C_, **f32)
     if tc:
         with _OnSide():
             dWx = torch.empty(Wx_shape, **f32)
             dWfx = torch.empty(Wx_shape, **f32)
             gemm_tc_wgrad(xs, dXF16, B, Hg, Wg, C_, I2, taps=taps, scatter=(dWx, dWfx), I=I, tag="proj_wgrad")
-        gemm_tc(dXF16, Wd16, dx, None, B, Hg, Wg, I2, C_, taps, 1, tag="proj_dgrad")
+        if dx_bf16:
+            gemm_tc(dXF16, Wd16, None, None, B, Hg, Wg, I2, C_, taps, 1, C16=dx, tag="proj_dgrad")
+        else:
+            gemm_tc(dXF16, Wd16, dx, None, B, Hg, Wg, I2, C_, taps, 1, tag="proj_dgrad")
         keep = (dXF16, xs, dWs_part, dtau_part, dWqkv_part, dWo_part, dTt, s, dw16, dP)
         return dx, dict(temperature=dtemp.view(1, H, 1, 1), Wx=dWx, bx=dbx, Wfx=dWfx, bfx=dbfx, Ws=dWs, bs=dbs,
                         Wq=dWqkv[0], Wk=dWqkv[1], Wv=dWqkv[2], Wo=dWo, bo=dbo, _keep=keep)
@@ -1131,11 +1153,15 @@ class AttnBlockFn(torch.autograd.Function):
         fx, ln_w, mean, rstd, temperature, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved = ctx.saved_tensors
         dout = dout.contiguous()
         dout16, dsum = _take_grad16(dout)
+        ln16 = bool(_lib.load().tbns_layernorm_bwd_supported16(fx.shape[-1]))
         dx1, g = pa_backward(dout, xshape, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
                              Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16, dout16=dout16,
-                             dbo=dsum)
-        dfx, dfx16, dlw, dlb, dfsum = layernorm_bwd(dx1, fx, mean, rstd, ln_w, dres=dout, want16=precision == TBNS_PREC_BF16,
-                                                    want_sum=True)
+                             dbo=dsum, dx_bf16=ln16)
+        if dx1.dtype == torch.bfloat16:
+            dfx, dfx16, dlw, dlb, dfsum = layernorm_bwd16(dx1, fx, mean, rstd, ln_w, dres=dout)
+        else:
+            dfx, dfx16, dlw, dlb, dfsum = layernorm_bwd(dx1, fx, mean, rstd, ln_w, dres=dout, want16=precision == TBNS_PREC_BF16,
+                                                        want_sum=True)
         _join_side()                        # weight-gradient work of pa_backward overlapped the LayerNorm backward above
         g.pop("_keep", None)
         _stash_grad16(dfx, dfx16, dfsum)   # column sums of dfx = to-be bias gradient of the previous block's mlp.linear_post
@@ -1210,9 +1236,14 @@ class LnMlpFn(torch.autograd.Function):
                 db1 = colsum_bf16(dpre16, M, R)
                 dW1 = torch.empty(R, C_, **f32)
                 gemm_tc_wgrad(dpre16, x2, 1, 1, M, R, C_, C=dW1, tag="mlp_dW1")
-            dx2 = torch.empty(M, C_, **f32)
-            gemm_tc(dpre16, W1t16, dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
-            dfx, dfx16, dg, db, dfsum = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout, want16=True, want_sum=True)
+            if _lib.load().tbns_layernorm_bwd_supported16(C_):
+                dx2 = torch.empty(M, C_, device=fx.device, dtype=torch.bfloat16)   # feeds the LayerNorm backward only: bf16
+                gemm_tc(dpre16, W1t16, None, None, 1, 1, M, R, C_, C16=dx2, tag="mlp_dx2")
+                dfx, dfx16, dg, db, dfsum = layernorm_bwd16(dx2, fx, mean, rstd, gamma, dres=dout)
+            else:
+                dx2 = torch.empty(M, C_, **f32)
+                gemm_tc(dpre16, W1t16, dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
+                dfx, dfx16, dg, db, dfsum = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout, want16=True, want_sum=True)
             _join_side()
             dfx = dfx.view_as(fx)
             _stash_grad16(dfx, dfx16, dfsum)   # the attention stage's backward consumes dfx next: bf16 copy + to_out bias gradient
