@@ -718,6 +718,157 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_teardown<BN>(tmem_base, warp);
 }
 
+// CTA-pair variant of the token-contraction kernel: a cluster of two CTAs owns a 256 (a) x 256 (n) output tile of one tap.
+// Each CTA stages its 128 a-features of A and its 128 n-features of B per 64-token k-block (32 KB instead of 48 KB, 6 ring
+// stages instead of 4); the leader issues tcgen05.mma.cta_group::2 with MN-major descriptors; each CTA drains its own 128
+// accumulator rows.  Same barrier protocol as gemm_tc_2cta_kernel, one tile per cluster (no accumulator hand-back).
+constexpr int WG2_STAGES = 6;
+struct Wg2Smem {
+  static constexpr int A_BYTES = 2 * WG_BKT * 128;          // 2 panels [64 tok][64 a]
+  static constexpr int B_BYTES = 2 * WG_BKT * 128;          // 2 panels [64 tok][64 n] (this CTA's half of the 256-wide tile)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = WG2_STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * WG2_STAGES + 1) * 8 + 16 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgParams p) {
+  using S = Wg2Smem;
+  constexpr int STAGES = WG2_STAGES, BN = 256;
+  constexpr uint32_t PANEL = WG_BKT * 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bar_full = base + S::BAR_OFF;       // leader only
+  const uint32_t bar_empty = bar_full + STAGES * 8;  // per CTA
+  const uint32_t bar_acc = bar_empty + STAGES * 8;   // per CTA
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR_OFF + (2 * STAGES + 1) * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  // grid.x = 2 * pair tiles (cluster = consecutive CTA pair), grid.y = batch * split_k
+  const int tile = blockIdx.x >> 1;
+  const int ni = tile % p.n_chunks;                  // 256-wide n chunk
+  const int mi = (tile / p.n_chunks) % p.m_chunks;   // 256-tall a chunk (pair)
+  const int tap = tile / (p.n_chunks * p.m_chunks);
+  const int kbpi = p.tiles_w * p.tiles_h;
+  int e0, e1, bidx, split;
+  if (p.batched) {
+    bidx = blockIdx.y / p.split_k;
+    split = blockIdx.y - bidx * p.split_k;
+    const int per = (kbpi + p.split_k - 1) / p.split_k;
+    e0 = bidx * kbpi + min(kbpi, split * per);
+    e1 = bidx * kbpi + min(kbpi, (split + 1) * per);
+  } else {
+    bidx = 0;
+    split = blockIdx.y;
+    const int total = p.Bimg * kbpi;
+    const int per = (total + p.split_k - 1) / p.split_k;
+    e0 = min(total, split * per);
+    e1 = min(total, (split + 1) * per);
+  }
+  const int nkb = e1 - e0;
+  int dy = 0, dx = 0;
+  if (p.taps == 9) {
+    dy = tap / 3 - 1;
+    dx = tap % 3 - 1;
+  }
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int a0 = mi * 256 + (int)rank * 128, nn0 = ni * BN + (int)rank * 128;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(bar_empty + s * 8, ph ^ 1);
+        const int e = e0 + i;
+        const int b = e / kbpi, rem = e - b * kbpi;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        const int h0 = th * p.BH, w0 = tw * p.BW;
+        const uint32_t sa = base + s * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+        const uint32_t full_leader = mapa_shared(bar_full + s * 8, 0);
+        if (rank == 0) mbar_expect_tx(bar_full + s * 8, 2 * S::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_4d_2sm(sa + j * PANEL, &tmA, full_leader, a0 + j * 64, w0 + dx, h0 + dy, b);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_4d_2sm(sb + j * PANEL, &tmB, full_leader, nn0 + j * 64, w0, h0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_2sm(BN) | (1u << 15) | (1u << 16);   // both operands MN-major
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(bar_full + s * 8, ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_BKT / TC_UK; ++k) {
+          const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * TC_UK * 128, PANEL);
+          const uint64_t bd = umma_desc_mnmajor_sw128(sb + k * TC_UK * 128, PANEL);
+          umma_bf16_2sm(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_2sm(bar_empty + s * 8, 3);
+      }
+      if (nkb > 0) umma_commit_2sm(bar_acc, 3);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int batch = p.batched ? p.Bimg : 1;
+    float* orow = p.ws + (((long long)split * batch + bidx) * p.Mtot + (long long)tap * p.Ma + mi * 256 + (int)rank * 128 + r) * p.Nb + ni * BN;
+    if (nkb > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      if (nkb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
 // fp32 -> bf16 (round to nearest even), 8 elements per thread
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
@@ -917,7 +1068,9 @@ extern "C" int tbns_gemm_tc_wgrad(const tbns_tc_wgrad_desc* dp, void* stream) {
   p.BW = pick_bw(d.Hg, d.Wg, WG_BKT); p.BH = WG_BKT / p.BW;
   p.tiles_w = cdiv(d.Wg, p.BW); p.tiles_h = cdiv(d.Hg, p.BH);
   const int BN = d.Nb % 256 == 0 ? 256 : (d.Nb % 128 == 0 ? 128 : 64);
-  p.m_chunks = d.Ma / TC_BM; p.n_chunks = d.Nb / BN;
+  static const bool two_cta = [] { const char* e = getenv("TBNS_TC_2CTA"); return !e || atoi(e) != 0; }();
+  const bool pair = two_cta && BN == 256 && d.Ma % 256 == 0;   // CTA pairs on 256 x 256 tiles
+  p.m_chunks = d.Ma / (pair ? 256 : TC_BM); p.n_chunks = d.Nb / BN;
   p.batched = d.batched; p.split_k = d.split_k;
   const int batch = d.batched ? d.Bimg : 1;
   const int tiles = d.taps * p.m_chunks * p.n_chunks;
@@ -929,7 +1082,13 @@ extern "C" int tbns_gemm_tc_wgrad(const tbns_tc_wgrad_desc* dp, void* stream) {
   rc = encode_act(&tmB, d.B16, d.Bimg, d.Hg, d.Wg, d.Nb, p.BW, p.BH);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 256) rc = launch_wg<256, 4>(tmA, tmB, p, tiles, gy, st);
+  if (pair) {
+    TBNS_SMEM_OPT_IN((gemm_tc_wgrad2_kernel), Wg2Smem::TOTAL);
+    dim3 grid(2 * tiles, gy);
+    gemm_tc_wgrad2_kernel<<<grid, TC_THREADS, Wg2Smem::TOTAL, st>>>(tmA, tmB, p);
+    rc = cudaGetLastError() == cudaSuccess ? TBNS_OK : TBNS_ERR_CUDA;
+    if (rc) set_error("gemm_tc_wgrad2_kernel launch failed");
+  } else if (BN == 256) rc = launch_wg<256, 4>(tmA, tmB, p, tiles, gy, st);
   else if (BN == 128) rc = launch_wg<128, 6>(tmA, tmB, p, tiles, gy, st);
   else rc = launch_wg<64, 8>(tmA, tmB, p, tiles, gy, st);
   if (rc) return rc;
