@@ -93,6 +93,11 @@ typedef struct tbns_tc_desc {
   void* C16; long long ldc16;   /* bf16 output or NULL (operand of the next tensor-core contraction)    */
   int round_tf32;               /* 1: round the fp32 output to TF32 (RNA): it feeds kind::tf32 MMAs downstream */
   int aux_bf16;                 /* 1: aux_out / aux_in point to bf16 buffers (halves the GELU side-stream traffic)   */
+  /* Fused LayerNorm of the OUTPUT rows (ln_gamma != NULL; N in {128, 256} so that one tile holds whole rows; needs C with
+   * ldc == N): ln_out16[m, :] = bf16(LayerNorm(C[m, :]) * ln_gamma + ln_beta), ln_mean / ln_rstd [rows] for the backward.
+   * This is the NEXT stage's nn.LayerNorm (model/Transolver_Structured_Mesh_2D.py:70-71: ln_1 / ln_2 read the residual
+   * stream the contraction has just produced) - it costs no extra pass over HBM.                                          */
+  const float* ln_gamma; const float* ln_beta; void* ln_out16; float* ln_mean; float* ln_rstd; float ln_eps;
 } tbns_tc_desc;
 int tbns_gemm_tc_supported(int Cin, int N, int taps);
 int tbns_gemm_tc(const tbns_tc_desc* d, void* stream);

@@ -106,12 +106,13 @@ def test_block_b20_bf16_graph_sidestream_all_gradients():
             fwd_bwd()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    hits0 = ops.HANDOFF_HITS
+    hits0, ln0 = ops.HANDOFF_HITS, ops.LN_FUSED_HITS
     graph = torch.cuda.CUDAGraph()
     ops.begin_capture()
     with torch.cuda.graph(graph):
         out, grads = fwd_bwd()
     assert ops.HANDOFF_HITS > hits0, "the fused backward chain must hand its bf16 gradient copies on (ops._take_grad16)"
+    assert ops.LN_FUSED_HITS == ln0 + 1, "ln_2 must come out of the attention output GEMM's epilogue (ops._take_ln)"
     for t in (out,) + tuple(grads):
         t.fill_(float("nan"))
     graph.replay()
@@ -156,8 +157,10 @@ def test_cfg1_model_b20_bf16_graphed_train_step_all_gradients():
     grads = train.FlatGradients(m.parameters())
     opt = torch.optim.AdamW(m.parameters(), lr=torch.tensor(1e-3, device=dev), weight_decay=1e-5, fused=True, capturable=True)
     batch = tuple(t.to(dev) for t in (x, fx, yy))
+    ln0 = ops.LN_FUSED_HITS
     gs = train.GraphedTrainStep(m, opt, None, grads, batch, T=10, step=1, batched=True, warmup=2)
     assert ops._USE_SIDE
+    assert ops.LN_FUSED_HITS == ln0 + 3 * 16, "all 8 ln_1 and 8 ln_2 are computed in GEMM epilogues (2 warm-up steps + capture)"
     # warm-up and capture moved the weights: restart from the conditioned state, then replay forward+backward only
     m.load_state_dict(state0)
     ops.invalidate_weight_caches()

@@ -50,6 +50,7 @@ class TcDesc(C.Structure):
         ("C", _fp), ("ldc", _ll),
         ("C16", _fp), ("ldc16", _ll),
         ("round_tf32", _i), ("aux_bf16", _i),
+        ("ln_gamma", _fp), ("ln_beta", _fp), ("ln_out16", _fp), ("ln_mean", _fp), ("ln_rstd", _fp), ("ln_eps", C.c_float),
     ]
 
 

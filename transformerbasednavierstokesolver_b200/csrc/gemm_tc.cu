@@ -39,6 +39,13 @@ struct TcParams {
   int tiles_w, tiles_h;
   int N, w_batched;
   int round_tf32;           // round the fp32 output to TF32 (round-to-nearest): it is the operand of tf32 MMAs downstream
+  // fused LayerNorm of the OUTPUT rows (N == BN: a tile holds whole rows): the consumer's LayerNorm runs in this epilogue
+  const float* ln_gamma;    // [N] or nullptr
+  const float* ln_beta;     // [N]
+  __nv_bfloat16* ln_out16;  // [rows, N] bf16: LN(C) - the TMA operand of the next contraction
+  float* ln_mean;           // [rows]
+  float* ln_rstd;           // [rows]
+  float ln_eps;
 };
 
 struct WgParams {
@@ -153,16 +160,18 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
 // EPI < 0: every option is a runtime test on TcParams.  EPI >= 0: a bit set of EPI_* flags fixed at compile time, so the
 // short-K contractions (whose time is all epilogue) run straight-line code for exactly the options they use.
 enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_DGELU = 4, EPI_RES = 8, EPI_ROUND = 16, EPI_C = 32, EPI_C16 = 64, EPI_AUX16 = 128,
-             EPI_AUXOUT = 256, EPI_DERIV = 512 /* the aux stream holds GELU'(pre) instead of pre (act 3 / 4) */ };
+             EPI_AUXOUT = 256, EPI_DERIV = 512 /* the aux stream holds GELU'(pre) instead of pre (act 3 / 4) */,
+             EPI_LN = 1024 /* LayerNorm of the output rows fused in (persistent kernel, N == BN) */ };
 static int epi_code(const TcParams& p) {
   const bool gelu = p.act == 1 || p.act == 3, mul = p.act == 2 || p.act == 4;
   return (p.bias ? EPI_BIAS : 0) | (gelu ? EPI_GELU : 0) | (mul ? EPI_DGELU : 0) | (p.act >= 3 ? EPI_DERIV : 0) |
          (p.residual ? EPI_RES : 0) | (p.round_tf32 ? EPI_ROUND : 0) | (p.C ? EPI_C : 0) | (p.C16 ? EPI_C16 : 0) |
-         (p.aux_bf16 ? EPI_AUX16 : 0) | (gelu && p.aux_out ? EPI_AUXOUT : 0);
+         (p.aux_bf16 ? EPI_AUX16 : 0) | (gelu && p.aux_out ? EPI_AUXOUT : 0) | (p.ln_gamma ? EPI_LN : 0);
 }
 
 template <int EPI>
-__device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][16], const long long (&grow)[4], int n, int t) {
+__device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][16], const long long (&grow)[4], int n, int t,
+                                             float* st1 = nullptr, float* st2 = nullptr) {
   // compile-time view of the options (constant-folded when EPI >= 0)
   struct {
     const float* bias; int act; float* aux_out; const float* aux_in; long long ldaux; const float* residual; long long ldr;
@@ -247,6 +256,10 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
         x1 = __uint_as_float(u1);
       }
       if (ok && (K_C || (GEN && p.C))) *reinterpret_cast<float2*>(p.C + gr * p.ldc + c) = make_float2(x0, x1);
+      if (EPI >= 0 && (EPI & EPI_LN)) {   // row statistics of the values just written (fused LayerNorm, pass 1)
+        st1[k] += x0 + x1;
+        st2[k] = fmaf(x0, x0, fmaf(x1, x1, st2[k]));
+      }
       if (K_C16 || (GEN && p.C16)) {
         // bf16 pairs are only 4 bytes: trade pairs with the neighbouring lane so that every thread owns 4 consecutive columns
         // (8 bytes) of column group j or j+1 and four threads fill one 32-byte sector of the row
@@ -266,6 +279,46 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
   }
 }
 
+// fused LayerNorm, pass 2: re-read this thread's own fp32 outputs of one 32-column chunk (L2 hits), normalise, bf16 store
+// (same lane-pair exchange as the C16 path: four threads fill one 32-byte sector of a row)
+__device__ __forceinline__ void tc_epi_ln_store(const TcParams& p, const long long (&grow)[4], const float (&mu)[4], const float (&rs)[4],
+                                                int n, int t) {
+  const int cb = n + 2 * (t & 3);
+  float2 g[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    g[j] = *reinterpret_cast<const float2*>(p.ln_gamma + cb + 8 * j);
+    b[j] = *reinterpret_cast<const float2*>(p.ln_beta + cb + 8 * j);
+  }
+  float2 x[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      x[k][j] = grow[k] >= 0 ? *reinterpret_cast<const float2*>(p.C + grow[k] * p.ldc + cb + 8 * j) : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool ok = grow[k] >= 0;
+    uint32_t mine[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y0 = fmaf((x[k][j].x - mu[k]) * rs[k], g[j].x, b[j].x), y1 = fmaf((x[k][j].y - mu[k]) * rs[k], g[j].y, b[j].y);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+      mine[j & 1] = *reinterpret_cast<uint32_t*>(&h2);
+      if (j & 1) {
+        const bool even = (t & 1) == 0;
+        const uint32_t got = __shfl_xor_sync(0xffffffffu, even ? mine[1] : mine[0], 1);
+        uint2 o;
+        o.x = even ? mine[0] : got;
+        o.y = even ? got : mine[1];
+        const int c = cb + 8 * j;
+        const int cc = even ? (c - 8) : (c - 2);
+        if (ok) *reinterpret_cast<uint2*>(p.ln_out16 + grow[k] * (long long)p.N + cc) = o;
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 struct TcpSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
@@ -273,7 +326,9 @@ struct TcpSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int NBAR = 2 * STAGES + 4;  // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
-  static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static constexpr int LN_OFF = BAR_OFF + NBAR * 8 + 16;        // fused LayerNorm: [2 tile parities][4 column slots][128 rows] float2
+  static constexpr int LN_BYTES = 2 * 4 * TC_BM * 8;
+  static constexpr int TOTAL = LN_OFF + LN_BYTES + 1024;
 };
 
 template <int BN, int STAGES, int EPI>
@@ -399,6 +454,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       mbar_wait(bar_accf + as * 8, (j >> 1) & 1);
       tc_fence_after();
       bool handed_back = false;
+      constexpr bool LN = EPI >= 0 && (EPI & EPI_LN);
+      float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c0 = slot * 32; c0 < BN; c0 += 32 * (TCP_EPI_WARPS / 4)) {
         float v[2][16];
@@ -412,9 +469,45 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           mbar_arrive(bar_acce + as * 8);
           handed_back = true;
         }
-        tc_epi_frag2<EPI>(p, v, grow, n0 + c0, lane);
+        tc_epi_frag2<EPI>(p, v, grow, n0 + c0, lane, st1, st2);
       }
       if (!handed_back) mbar_arrive(bar_acce + as * 8);   // narrow tiles: this warp's column slot does not exist
+      if (LN) {
+        // fused LayerNorm of the output rows (the tile holds whole rows: N == BN).  Pass 1 above accumulated sum / sum of
+        // squares of this thread's columns; combine the four lanes that share a row, then the four column-slot warps through
+        // shared memory (double-buffered by tile parity: one named barrier per tile), then normalise the values just written.
+        float2* red = reinterpret_cast<float2*>(gen + S::LN_OFF) + (j & 1) * (4 * TC_BM);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          st1[k] += __shfl_xor_sync(0xffffffffu, st1[k], 1);
+          st2[k] += __shfl_xor_sync(0xffffffffu, st2[k], 1);
+          st1[k] += __shfl_xor_sync(0xffffffffu, st1[k], 2);
+          st2[k] += __shfl_xor_sync(0xffffffffu, st2[k], 2);
+          if ((lane & 3) == 0) red[slot * TC_BM + q * 32 + (lane >> 2) + 8 * k] = make_float2(st1[k], st2[k]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TCP_THREADS - 64) : "memory");
+        float mu[4], rs[4];
+        const float invN = 1.0f / (float)BN;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = q * 32 + (lane >> 2) + 8 * k;
+          float a = 0.f, b2 = 0.f;
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {   // fixed order: identical in all four slot warps
+            const float2 pr = red[sl * TC_BM + r];
+            a += pr.x;
+            b2 += pr.y;
+          }
+          mu[k] = a * invN;
+          rs[k] = rsqrtf(fmaxf(b2 * invN - mu[k] * mu[k], 0.f) + p.ln_eps);
+          if (slot == 0 && (lane & 3) == 0 && grow[k] >= 0) {
+            p.ln_mean[grow[k]] = mu[k];
+            p.ln_rstd[grow[k]] = rs[k];
+          }
+        }
+#pragma unroll 1
+        for (int c0 = slot * 32; c0 < BN; c0 += 32 * (TCP_EPI_WARPS / 4)) tc_epi_ln_store(p, grow, mu, rs, n0 + c0, lane);
+      }
     }
   }
   tc_fence_before();
@@ -926,6 +1019,8 @@ static int launch_tcp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPa
       TBNS_EPI_CASE(EPI_BIAS | EPI_C)                                               // projection fprop
       TBNS_EPI_CASE(EPI_BIAS | EPI_ROUND | EPI_C)                                   // projection fprop feeding the tf32 slice stage
       TBNS_EPI_CASE(EPI_BIAS | EPI_RES | EPI_C)                                     // deslice (+) to_out + residual, fc2 + residual
+      TBNS_EPI_CASE(EPI_BIAS | EPI_RES | EPI_C | EPI_LN)                            // ... + the next stage's LayerNorm
+      TBNS_EPI_CASE(EPI_BIAS | EPI_C | EPI_LN)                                      // preprocess fc2 + the first block's ln_1
       TBNS_EPI_CASE(EPI_C | EPI_C16)                                                // dw (fp32 + bf16)
       TBNS_EPI_CASE(EPI_C16)                                                        // dw (bf16 only)
       TBNS_EPI_CASE(EPI_BIAS | EPI_GELU | EPI_AUXOUT | EPI_AUX16 | EPI_C16)         // fc1: pre (bf16) + gelu (bf16)
@@ -935,6 +1030,10 @@ static int launch_tcp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPa
 #undef TBNS_EPI_CASE
       default: break;
     }
+  }
+  if (p.ln_gamma) {
+    set_error("tbns_gemm_tc: the fused LayerNorm exists for the option sets bias(+residual)+fp32 output only");
+    return TBNS_ERR_UNSUPPORTED;
   }
   return launch_tcp_epi<BN, STAGES, -1>(tmA, tmB, p, m_tiles, st);
 }
@@ -1014,6 +1113,13 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
   p.BW = pick_bw(d.Hg, d.Wg, TC_BM); p.BH = TC_BM / p.BW;
   p.tiles_w = cdiv(d.Wg, p.BW); p.tiles_h = cdiv(d.Hg, p.BH);
   p.N = d.N; p.w_batched = d.w_batched; p.round_tf32 = d.round_tf32;
+  p.ln_gamma = d.ln_gamma; p.ln_beta = d.ln_beta; p.ln_out16 = reinterpret_cast<__nv_bfloat16*>(d.ln_out16);
+  p.ln_mean = d.ln_mean; p.ln_rstd = d.ln_rstd; p.ln_eps = d.ln_eps;
+  if (d.ln_gamma) {
+    TBNS_REQUIRE((d.N == 128 || d.N == 256) && d.C && d.ldc == d.N && d.ln_beta && d.ln_out16 && d.ln_mean && d.ln_rstd &&
+                     al16p(d.ln_out16) && al16p(d.ln_gamma) && al16p(d.ln_beta),
+                 "tbns_gemm_tc: fused LayerNorm needs N in {128, 256} (a tile holds whole rows), a dense fp32 output and all ln_* buffers");
+  }
   const long long m_tiles = (long long)d.Bimg * p.tiles_w * p.tiles_h;
   TBNS_REQUIRE(m_tiles <= 0x7fffffffLL, "tbns_gemm_tc: too many tiles");
 

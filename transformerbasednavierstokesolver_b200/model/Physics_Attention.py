@@ -84,8 +84,9 @@ class _PhysicsAttentionBase(nn.Module):
             self.to_v.weight, lin.weight, lin.bias, packed, self.heads, grid, prec)
 
 
-def _forward_block(self, fx, ln):
-    """fx + self(ln(fx)) as ONE fused autograd stage (used by Transolver_block): LayerNorm, attention, residual."""
+def _forward_block(self, fx, ln, next_ln=None):
+    """fx + self(ln(fx)) as ONE fused autograd stage (used by Transolver_block): LayerNorm, attention, residual.
+    next_ln: the nn.LayerNorm that consumes the result (the block's ln_2) - computed in the output GEMM's epilogue."""
     if not fx.is_cuda:
         raise RuntimeError("Physics-Attention (B200) has no CPU path: move the module and its input to a CUDA device")
     if self.training and self.dropout.p > 0.0:
@@ -97,7 +98,8 @@ def _forward_block(self, fx, ln):
     return ops.AttnBlockFn.apply(
         fx.float(), ln.weight, ln.bias, ln.eps, self.temperature, self.in_project_x.weight, self.in_project_x.bias,
         self.in_project_fx.weight, self.in_project_fx.bias, self.in_project_slice.weight, self.in_project_slice.bias,
-        self.to_q.weight, self.to_k.weight, self.to_v.weight, lin.weight, lin.bias, packed, self.heads, grid, prec)
+        self.to_q.weight, self.to_k.weight, self.to_v.weight, lin.weight, lin.bias, packed, self.heads, grid, prec,
+        *((next_ln.weight, next_ln.bias, next_ln.eps) if next_ln is not None else (None, None, 1e-5)))
 
 
 _PhysicsAttentionBase.forward_block = _forward_block

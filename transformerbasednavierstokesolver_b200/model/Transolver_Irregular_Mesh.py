@@ -5,7 +5,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._blocks import MLP, Transolver_block as _Block, init_weights, time_conditioning
+from ._blocks import MLP, Transolver_block as _Block, init_weights, link_blocks, time_conditioning
 from .Physics_Attention import Physics_Attention_Irregular_Mesh  # noqa: F401
 
 
@@ -29,6 +29,7 @@ class Model(nn.Module):
         self.blocks = nn.ModuleList([
             Transolver_block(num_heads=n_head, hidden_dim=n_hidden, dropout=dropout, act=act, mlp_ratio=mlp_ratio, out_dim=out_dim,
                              slice_num=slice_num, last_layer=(i == n_layers - 1)) for i in range(n_layers)])
+        link_blocks(self.blocks)
         self.initialize_weights()
         self.placeholder = nn.Parameter((1 / n_hidden) * torch.rand(n_hidden, dtype=torch.float))
 

@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import config, ops
-from ._blocks import MLP, Transolver_block as _Block, init_weights, time_conditioning
+from ._blocks import MLP, Transolver_block as _Block, init_weights, link_blocks, time_conditioning
 from .Physics_Attention import Physics_Attention_Structured_Mesh_2D  # noqa: F401  (re-exported like the reference)
 
 
@@ -34,6 +34,7 @@ class Model(nn.Module):
         self.blocks = nn.ModuleList([
             Transolver_block(num_heads=n_head, hidden_dim=n_hidden, dropout=dropout, act=act, mlp_ratio=mlp_ratio, out_dim=out_dim,
                              slice_num=slice_num, H=H, W=W, last_layer=(i == n_layers - 1)) for i in range(n_layers)])
+        link_blocks(self.blocks)
         self.initialize_weights()
         self.placeholder = nn.Parameter((1 / n_hidden) * torch.rand(n_hidden, dtype=torch.float))
 
@@ -74,7 +75,9 @@ class Model(nn.Module):
             pre, post = self.preprocess.linear_pre[0], self.preprocess.linear_post
             tab16 = self._pos16(fx.device) if self.unified_pos else None
             src1 = None if self.unified_pos else x
-            fx = ops.PackedMlpFn.apply(tab16, src1, fx, pre.weight, pre.bias, post.weight, post.bias)
+            ln1 = self.blocks[0].ln_1 if (T is None and isinstance(self.blocks[0], _Block)) else None   # computed by the second Linear
+            fx = ops.PackedMlpFn.apply(tab16, src1, fx, pre.weight, pre.bias, post.weight, post.bias,
+                                       *((ln1.weight, ln1.bias, ln1.eps) if ln1 is not None else (None, None, 1e-5)))
         else:
             if self.unified_pos:
                 if self.pos.device != x.device:

@@ -63,12 +63,17 @@ class Transolver_block(nn.Module):
         if last_layer:
             self.ln_3 = nn.LayerNorm(hidden_dim)
             self.mlp2 = nn.Linear(hidden_dim, out_dim)
+        self._next_ln = ()   # (ln_1 of the following block,): set by link_blocks; a tuple so that it is not a registered submodule
 
     def forward(self, fx, out=None):
         prec = ops.PRECISIONS[self.Attn.precision or config.get_default_precision()]
-        fx = self.Attn.forward_block(fx.contiguous(), self.ln_1)
+        # each LayerNorm is computed by the GEMM that produces its input (bf16 mode): ln_2 in the attention's output
+        # projection, the next block's ln_1 in this block's second MLP Linear
+        fx = self.Attn.forward_block(fx.contiguous(), self.ln_1, self.ln_2)
         pre, post = self.mlp.linear_pre[0], self.mlp.linear_post
-        fx = ops.LnMlpFn.apply(fx, self.ln_2.weight, self.ln_2.bias, pre.weight, pre.bias, post.weight, post.bias, self.ln_2.eps, prec)
+        nxt = self._next_ln[0] if (self._next_ln and not self.last_layer) else None
+        fx = ops.LnMlpFn.apply(fx, self.ln_2.weight, self.ln_2.bias, pre.weight, pre.bias, post.weight, post.bias, self.ln_2.eps, prec,
+                               *((nxt.weight, nxt.bias, nxt.eps) if nxt is not None else (None, None, 1e-5)))
         if self.last_layer:
             if out is not None:
                 if torch.is_grad_enabled() and fx.requires_grad:
@@ -76,6 +81,14 @@ class Transolver_block(nn.Module):
                 return ops.ln_linear_into(fx, self.ln_3.weight, self.ln_3.bias, self.mlp2.weight, self.mlp2.bias, self.ln_3.eps, prec, out)
             return ops.LnLinearFn.apply(fx, self.ln_3.weight, self.ln_3.bias, self.mlp2.weight, self.mlp2.bias, self.ln_3.eps, prec)
         return fx
+
+
+def link_blocks(blocks):
+    """tell every block which LayerNorm consumes its output (the next block's ln_1), so that its last GEMM can compute it"""
+    blocks = list(blocks)
+    for a, b in zip(blocks[:-1], blocks[1:]):
+        if isinstance(a, Transolver_block) and isinstance(b, Transolver_block):
+            a._next_ln = (b.ln_1,)
 
 
 def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:

@@ -266,10 +266,25 @@ def tc_supported(Cin: int, N: int, taps: int) -> bool:
     return bool(_lib.load().tbns_gemm_tc_supported(Cin, N, taps))
 
 
+def ln_fusable(N: int) -> bool:
+    """the producer GEMM can run the consumer's LayerNorm in its epilogue when one output tile holds whole rows"""
+    return N in (128, 256)
+
+
 def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps=1, flip=0, tag=None, *, C16=None, w_batched=0, act=0, aux_out=None,
-            aux_in=None, residual=None, round_tf32=0, aux_bf16=0):
-    """tcgen05 implicit GEMM, K-major operands (include/tbns.h: tbns_gemm_tc).  C fp32 and/or C16 bf16 outputs [.., N]."""
+            aux_in=None, residual=None, round_tf32=0, aux_bf16=0, ln=None):
+    """tcgen05 implicit GEMM, K-major operands (include/tbns.h: tbns_gemm_tc).  C fp32 and/or C16 bf16 outputs [.., N].
+    ln = (gamma, beta, eps): also run LayerNorm over the output rows in the epilogue -> returns (y16, mean, rstd)."""
     d = _lib.TcDesc()
+    ln_out = None
+    if ln is not None:
+        rows = Bimg * Hg * Wg
+        y16 = torch.empty(rows, N, device=C.device, dtype=torch.bfloat16)
+        mean = torch.empty(rows, device=C.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=C.device, dtype=torch.float32)
+        g_, b_ = ln[0].detach().contiguous(), ln[1].detach().contiguous()
+        d.ln_gamma, d.ln_beta, d.ln_out16, d.ln_mean, d.ln_rstd, d.ln_eps = _p(g_), _p(b_), _p(y16), _p(mean), _p(rstd), float(ln[2])
+        ln_out = (y16, mean, rstd)
     d.A16, d.Bimg, d.Hg, d.Wg, d.Cin, d.taps, d.flip = _p(A16), Bimg, Hg, Wg, Cin, taps, flip
     d.W16, d.N, d.w_batched = _p(W16), N, w_batched
     d.bias, d.act = _p(bias), act
@@ -282,6 +297,7 @@ def gemm_tc(A16, W16, C, bias, Bimg, Hg, Wg, Cin, N, taps=1, flip=0, tag=None, *
     with _Timed(tag):
         check(_lib.load().tbns_gemm_tc(ct.byref(d), _stream()), "tbns_gemm_tc")
     _count(1)
+    return ln_out
 
 
 def _wgrad_split(tiles: int, kblocks: int) -> int:
@@ -456,6 +472,29 @@ def _take_grad16(t: torch.Tensor):
     return None, None
 
 
+# The LayerNorm a stage starts with may already have been computed by the producer of its input (fused into that GEMM's
+# epilogue, gemm_tc(ln=...)): the result travels as an attribute of the producer's output tensor and is used only when it was
+# computed with exactly this stage's affine parameters.
+LN_FUSED_HITS = 0
+
+
+def _attach_ln(t: torch.Tensor, ln_out, gamma, beta, eps):
+    if ln_out is not None:
+        t._tbns_ln = (ln_out, gamma.data_ptr(), gamma._version, beta.data_ptr(), beta._version, float(eps), t._version, _WEIGHT_GEN)
+    return t
+
+
+def _take_ln(t: torch.Tensor, gamma, beta, eps):
+    """-> (y16 [rows, C] bf16, mean, rstd) computed by the producer of `t` with these LayerNorm parameters, or None"""
+    global LN_FUSED_HITS
+    side = getattr(t, "_tbns_ln", None)
+    if side is not None and side[1:] == (gamma.data_ptr(), gamma._version, beta.data_ptr(), beta._version, float(eps), t._version,
+                                         _WEIGHT_GEN):
+        LN_FUSED_HITS += 1
+        return side[0]
+    return None
+
+
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
     @_on_device
@@ -519,8 +558,10 @@ def _pa_tc_ok(precision, C_, I2, HG, Cout, taps, packed16) -> bool:
 
 
 def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, heads: int,
-               grid: Optional[Tuple[int, int]], precision: int, Wf16=None, x16=None):
-    """returns (out, saved tuple). x [B,N,C]; Wf/bcat packed projections; residual [B,N,Cout] or None."""
+               grid: Optional[Tuple[int, int]], precision: int, Wf16=None, x16=None, ln_next=None):
+    """returns (out, saved tuple). x [B,N,C]; Wf/bcat packed projections; residual [B,N,Cout] or None.
+    ln_next = (gamma, beta, eps) of the LayerNorm that consumes `out` (tensor-core route): computed in the epilogue of the
+    output GEMM and attached to `out` (see _attach_ln)."""
     lib = _lib.load()
     B, N, C_ = (x if x is not None else x16).shape
     I2 = Wf.shape[0]
@@ -579,7 +620,11 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
     # (3) deslice (+) to_out (+ bias, + residual)   :116-119 / :55-57
     out = torch.empty(B, N, Cout, **f32)
     if tc:
-        gemm_tc(w16, PT16, out, bo, B, 1, N, HG, Cout, w_batched=1, residual=residual, tag="deslice_out")
+        fuse = ln_next is not None and ln_fusable(Cout)
+        ln_out = gemm_tc(w16, PT16, out, bo, B, 1, N, HG, Cout, w_batched=1, residual=residual, tag="deslice_out",
+                         ln=(ln_next if fuse else None))
+        if fuse:
+            _attach_ln(out, ln_out, *ln_next)
         return out, (XF, w16, s, tok, q, k, v, A, O, P16, x16)
     gemm(M=N, N=Cout, K=HG, A=w, lda=HG, a_kind=0, B=P, ldb=Cout, b_kind=1, C=out, ldc=Cout, batch=B, sA=N * HG,
          sB=HG * Cout, sC=N * Cout, sR=N * Cout, bias=bo, residual=residual, ldr=Cout, precision=precision, tag="deslice_out")
@@ -1128,19 +1173,25 @@ class AttnBlockFn(torch.autograd.Function):
 
     @staticmethod
     @_on_device
-    def forward(ctx, fx, ln_w, ln_b, eps, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, packed, heads, grid, precision):
+    def forward(ctx, fx, ln_w, ln_b, eps, temperature, Wx, bx, Wfx, bfx, Ws, bs, Wq, Wk, Wv, Wo, bo, packed, heads, grid, precision,
+                nln_w=None, nln_b=None, nln_eps=1e-5):
         _begin_forward()
         fx = fx.contiguous()
         Wf, Wd, bcat, Wf16, Wd16 = packed
-        ln_w, ln_b = ln_w.contiguous(), ln_b.contiguous()
         _chk(fx, ln_w, ln_b, temperature, Ws, bs, Wq, Wk, Wv, Wo, bo, bcat)
         B, N, C_ = fx.shape
         structured = grid is not None
         tc = _pa_tc_ok(precision, C_, Wf.shape[0], heads * Ws.shape[0], Wo.shape[0], 9 if structured else 1, Wf16 is not None)
-        x1, x1_16, mean, rstd = layernorm_fwd(fx, ln_w, ln_b, eps, want32=not tc, want16=tc)
+        pre = _take_ln(fx, ln_w, ln_b, eps) if tc else None
+        if pre is not None:      # ln_1 was computed by the producer of fx (previous block's fc2 / the preprocess MLP)
+            x1, (x1_16, mean, rstd) = None, pre
+            x1_16 = x1_16.view(B, N, C_)
+        else:
+            x1, x1_16, mean, rstd = layernorm_fwd(fx, ln_w.contiguous(), ln_b.contiguous(), eps, want32=not tc, want16=tc)
         temperature_c = temperature.contiguous()
         out, saved = pa_forward(x1, temperature_c, Wf, bcat, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
-                                Wv.contiguous(), Wo.contiguous(), bo.contiguous(), fx, heads, grid, precision, Wf16, x16=x1_16)
+                                Wv.contiguous(), Wo.contiguous(), bo.contiguous(), fx, heads, grid, precision, Wf16, x16=x1_16,
+                                ln_next=((nln_w, nln_b, nln_eps) if (tc and nln_w is not None) else None))
         ctx.save_for_backward(fx, ln_w, mean, rstd, temperature_c, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved)
         ctx.Wd16 = Wd16
         ctx.cfg = (heads, grid, precision, tuple(Wx.shape), tuple(fx.shape))
@@ -1166,7 +1217,7 @@ class AttnBlockFn(torch.autograd.Function):
         g.pop("_keep", None)
         _stash_grad16(dfx, dfx16, dfsum)   # column sums of dfx = to-be bias gradient of the previous block's mlp.linear_post
         return (dfx, dlw, dlb, None, g["temperature"], g["Wx"], g["bx"], g["Wfx"], g["bfx"], g["Ws"], g["bs"], g["Wq"], g["Wk"],
-                g["Wv"], g["Wo"], g["bo"], None, None, None, None)
+                g["Wv"], g["Wo"], g["bo"], None, None, None, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1175,10 +1226,9 @@ class AttnBlockFn(torch.autograd.Function):
 class LnMlpFn(torch.autograd.Function):
     @staticmethod
     @_on_device
-    def forward(ctx, fx, gamma, beta, W1, b1, W2, b2, eps, precision):
+    def forward(ctx, fx, gamma, beta, W1, b1, W2, b2, eps, precision, nln_w=None, nln_b=None, nln_eps=1e-5):
         _begin_forward()
         fx = fx.contiguous()
-        gamma, beta, W1, b1, W2, b2 = (t.contiguous() for t in (gamma, beta, W1, b1, W2, b2))
         _chk(fx, gamma, beta, W1, b1, W2, b2)
         C_ = fx.shape[-1]
         M = fx.numel() // C_
@@ -1186,7 +1236,12 @@ class LnMlpFn(torch.autograd.Function):
         Cout = W2.shape[0]
         use_tc = (precision == TBNS_PREC_BF16 and Cout == C_ and tc_supported(C_, R, 1) and tc_supported(R, Cout, 1)
                   and wgrad_supported(Cout, R, 1) and wgrad_supported(R, C_, 1))
-        x2, x2_16, mean, rstd = layernorm_fwd(fx, gamma, beta, eps, want32=not use_tc, want16=use_tc)
+        got = _take_ln(fx, gamma, beta, eps) if use_tc else None
+        gamma, beta, W1, b1, W2, b2 = (t.contiguous() for t in (gamma, beta, W1, b1, W2, b2))
+        if got is not None:      # ln_2 was computed in the epilogue of the attention's output GEMM
+            x2, (x2_16, mean, rstd) = None, got
+        else:
+            x2, x2_16, mean, rstd = layernorm_fwd(fx, gamma, beta, eps, want32=not use_tc, want16=use_tc)
         pre = torch.empty(M, R, device=fx.device, dtype=torch.float32)
         if use_tc:
             # tensor-core MLP: bf16 operands; LN output and hidden activation only ever exist in bf16 (+ fp32 pre-activation
@@ -1195,7 +1250,11 @@ class LnMlpFn(torch.autograd.Function):
             pre = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)   # GELU'(pre-activation), written by fc1's epilogue (act 3)
             gemm_tc(x2_16, weight_bf16(W1), None, b1, 1, 1, M, C_, R, act=3, aux_out=pre, aux_bf16=1, C16=hid16, tag="mlp_fc1")
             out = torch.empty(*fx.shape[:-1], Cout, device=fx.device, dtype=torch.float32)
-            gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, residual=fx, tag="mlp_fc2")
+            fuse = nln_w is not None and ln_fusable(Cout)
+            ln_out = gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, residual=fx, tag="mlp_fc2",
+                             ln=((nln_w, nln_b, nln_eps) if fuse else None))   # + the next block's ln_1
+            if fuse:
+                _attach_ln(out, ln_out, nln_w, nln_b, nln_eps)
             ctx.save_for_backward(fx, gamma, W1, W2, x2_16, mean, rstd, pre, hid16)
             ctx.precision = precision
             return out
@@ -1247,7 +1306,7 @@ class LnMlpFn(torch.autograd.Function):
             _join_side()
             dfx = dfx.view_as(fx)
             _stash_grad16(dfx, dfx16, dfsum)   # the attention stage's backward consumes dfx next: bf16 copy + to_out bias gradient
-            return dfx, dg, db, dW1, db1, dW2, db2, None, None
+            return dfx, dg, db, dW1, db1, dW2, db2, None, None, None, None, None
         gemm(M=Cout, N=R, K=M, A=dout, lda=Cout, a_kind=1, B=hid, ldb=R, b_kind=1, C=dW2, ldc=R, precision=precision,
              split_k=_split_k(Cout, R, M))
         dpre = torch.empty(M, R, **f32)
@@ -1262,7 +1321,7 @@ class LnMlpFn(torch.autograd.Function):
         dfx, _, dg, db = layernorm_bwd(dx2, fx, mean, rstd, gamma, dres=dout)  # + residual branch
         dfx = dfx.view_as(fx)
         _stash_grad16(dfx)
-        return dfx, dg, db, dW1, db1, dW2, db2, None, None
+        return dfx, dg, db, dW1, db1, dW2, db2, None, None, None, None, None
 
 
 def mlp_tc_ok(K: int, R: int, Cout: int) -> bool:
@@ -1271,7 +1330,7 @@ def mlp_tc_ok(K: int, R: int, Cout: int) -> bool:
             and wgrad_supported(Cout, R, 1) and wgrad_supported(R, Kp, 1))
 
 
-def _mlp_tc_forward(in16, W1, b1, W2, b2, Kp, out_shape):
+def _mlp_tc_forward(in16, W1, b1, W2, b2, Kp, out_shape, ln_next=None):
     """Linear(Kp -> R) + GELU + Linear(R -> Cout) on the tensor cores from the packed bf16 input [M, Kp]"""
     M = in16.shape[0]
     R, Cout = W1.shape[0], W2.shape[0]
@@ -1281,7 +1340,10 @@ def _mlp_tc_forward(in16, W1, b1, W2, b2, Kp, out_shape):
     hid16 = torch.empty(M, R, device=dev, dtype=torch.bfloat16)
     gemm_tc(in16, weight_bf16_padded(W1, Kp), None, b1, 1, 1, M, Kp, R, act=3, aux_out=pre16, aux_bf16=1, C16=hid16, tag="pre_fc1")
     out = torch.empty(*out_shape, Cout, device=dev, dtype=torch.float32)
-    gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, tag="pre_fc2")
+    fuse = ln_next is not None and ln_next[0] is not None and ln_fusable(Cout)
+    ln_out = gemm_tc(hid16, weight_bf16(W2), out, b2, 1, 1, M, R, Cout, tag="pre_fc2", ln=(ln_next if fuse else None))
+    if fuse:
+        _attach_ln(out, ln_out, *ln_next)   # the first block's ln_1
     return out, pre16, hid16
 
 
@@ -1365,7 +1427,7 @@ class PackedMlpFn(torch.autograd.Function):
 
     @staticmethod
     @_on_device
-    def forward(ctx, tab16, src1, fx, W1, b1, W2, b2):
+    def forward(ctx, tab16, src1, fx, W1, b1, W2, b2, nln_w=None, nln_b=None, nln_eps=1e-5):
         _begin_forward()
         B, N = fx.shape[0], fx.shape[1]
         M = B * N
@@ -1380,7 +1442,7 @@ class PackedMlpFn(torch.autograd.Function):
         check(_lib.load().tbns_pack_inputs(_p(tab16), R, _p(s1), ld1, F1, _p(s2), ld2, F2, _p(in16), Kp, M, N, _stream()),
               "tbns_pack_inputs")
         _count(1)
-        out, pre16, hid16 = _mlp_tc_forward(in16, W1, b1, W2, b2, Kp, (B, N))
+        out, pre16, hid16 = _mlp_tc_forward(in16, W1, b1, W2, b2, Kp, (B, N), (nln_w, nln_b, nln_eps))
         ctx.save_for_backward(in16, W1, W2, pre16, hid16)
         ctx.dims = (R, F1, F2, B, N)
         return out
@@ -1395,7 +1457,7 @@ class PackedMlpFn(torch.autograd.Function):
         dxp, dW1, db1, dW2, db2 = _mlp_tc_backward(dout, in16, W1, W2, pre16, hid16, K, need1 or need2)
         d1 = dxp[:, R:R + F1].reshape(B, N, F1) if need1 else None
         d2 = dxp[:, R + F1:K].reshape(B, N, F2) if need2 else None
-        return None, d1, d2, dW1, db1, dW2, db2
+        return None, d1, d2, dW1, db1, dW2, db2, None, None, None
 
 
 class LnLinearFn(torch.autograd.Function):
