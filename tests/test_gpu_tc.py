@@ -262,3 +262,61 @@ def test_preprocess_mlp_tc(M, K, R, Cout, need_dx):
         assert a.shape == b.shape
         # output: one bf16 rounding (hidden activation); gradients: two more (incoming gradient, GELU' product)
         assert O.rel_l2(a.detach().cpu().double(), b) < (2e-3 if i == 0 else 5e-3)
+
+
+@pytest.mark.parametrize("B,H,G,Cout,nchunk", [(3, 2, 32, 128, 5), (2, 4, 64, 256, 19), (20, 8, 32, 256, 11)])
+def test_token_stage_mma_kernels_match_oracle(B, H, G, Cout, nchunk):
+    """token stage on warp-level MMAs (dim_head 32; 3xTF32): forward outputs (s, tok, q, k, v, A, O, P, the bf16 operand
+    copies) and every backward output against the fp64 oracle (model/Physics_Attention.py:102-111, SURVEY §8 a-bwd) at fp32
+    accuracy."""
+    from transformerbasednavierstokesolver_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    D = 32
+    I = H * D
+    g = torch.Generator().manual_seed(B * 100 + G + Cout)
+    part = torch.rand(B, H, nchunk, G, D + 1, generator=g) * 2 - 0.7
+    part[..., D] = torch.rand(B, H, nchunk, G, generator=g) * 30 + 0.5          # slice norms are positive
+    Wq, Wk, Wv = (torch.randn(D, D, generator=g) * 0.3 for _ in range(3))
+    Wo = torch.randn(Cout, I, generator=g) * 0.1
+    dP = torch.randn(B, H * G, Cout, generator=g)
+    p64 = part.double().sum(2)
+    s_ref, Tt_ref = p64[..., D], p64[..., :D]
+    st = O.token_attn_fwd(s_ref, Tt_ref, Wq.double(), Wk.double(), Wv.double(), Wo.double())
+    rdTt, rds, rdWq, rdWk, rdWv, rdWo = O.token_attn_bwd(dP.double(), s_ref, Tt_ref, st, Wq.double(), Wk.double(), Wv.double(), Wo.double())
+
+    f32 = dict(device=dev, dtype=torch.float32)
+    s = torch.empty(B, H, G, **f32)
+    Tt, tok, q, k, v, Oo = (torch.full((B, H, G, D), float("nan"), **f32) for _ in range(6))
+    A = torch.full((B, H, G, G), float("nan"), **f32)
+    P = torch.full((B, H * G, Cout), float("nan"), **f32)
+    P16 = torch.empty(B, H * G, Cout, device=dev, dtype=torch.bfloat16)
+    PT16 = torch.empty(B, Cout, H * G, device=dev, dtype=torch.bfloat16)
+    dd = lambda t: t.to(dev).contiguous()
+    partd, Wqd, Wkd, Wvd, Wod, dPd = dd(part), dd(Wq), dd(Wk), dd(Wv), dd(Wo), dd(dP)
+    stream = torch.cuda.current_stream().cuda_stream
+    p_ = lambda t: t.data_ptr()
+    _lib.check(lib.tbns_pa_token_attn_fwd(p_(partd), nchunk, p_(Wqd), p_(Wkd), p_(Wvd), p_(Wod), p_(s), p_(Tt), p_(tok), p_(q), p_(k), p_(v),
+                                          p_(A), p_(Oo), p_(P), p_(P16), p_(PT16), B, H, D, G, Cout, stream), "token fwd")
+    torch.cuda.synchronize()
+    tol = 2e-6
+    assert O.rel_l2(s.cpu(), s_ref) < tol and O.rel_l2(Tt.cpu(), Tt_ref) < tol
+    for name, got in (("tok", tok), ("q", q), ("k", k), ("v", v), ("A", A), ("O", Oo)):
+        assert O.rel_l2(got.cpu(), st[name]) < tol, name
+    assert O.rel_l2(P.cpu(), st["P"]) < tol
+    assert O.rel_l2(PT16.float().cpu(), st["P"].transpose(1, 2)) < 4e-3                     # bf16 storage
+    Pc = st["P"].reshape(B, H, G, Cout)
+    Pc = (Pc - Pc.mean(2, keepdim=True)).reshape(B, H * G, Cout)                          # centred over the slices of a head
+    assert O.rel_l2(P16.float().cpu(), Pc) < 8e-3   # bf16 storage of fp32 differences (cancellation noise of the centring itself)
+    dTt = torch.full((B, H, G, D), float("nan"), **f32)
+    ds = torch.full((B, H, G), float("nan"), **f32)
+    dWqkv = torch.full((B * H, 3 * D * D), float("nan"), **f32)
+    dWo = torch.full((B, Cout * I), float("nan"), **f32)
+    _lib.check(lib.tbns_pa_token_attn_bwd(p_(dPd), p_(Wqd), p_(Wkd), p_(Wvd), p_(Wod), p_(s), p_(tok), p_(q), p_(k), p_(v), p_(A), p_(Oo),
+                                          p_(dTt), p_(ds), p_(dWqkv), p_(dWo), B, H, D, G, Cout, stream), "token bwd")
+    torch.cuda.synchronize()
+    gtol = 1e-5
+    assert O.rel_l2(dTt.cpu(), rdTt) < gtol and O.rel_l2(ds.cpu(), rds) < gtol
+    got = dWqkv.double().sum(0).view(3, D, D).cpu()
+    assert O.rel_l2(got[0], rdWq) < gtol and O.rel_l2(got[1], rdWk) < gtol and O.rel_l2(got[2], rdWv) < gtol
+    assert O.rel_l2(dWo.double().sum(0).view(Cout, I).cpu(), rdWo) < gtol

@@ -626,7 +626,10 @@ extern "C" int tbns_pa_slice_fwd(const float* XF, const float* Ws, const float* 
   return TBNS_ERR_UNSUPPORTED;
 }
 
-extern "C" int tbns_pa_token_attn_fwd(const float* part, int nchunk, const float* Wq, const float* Wk, const float* Wv,
+// SIMT token kernels: any (dim_head, slice_num); the extern "C" entry points live in token.cu, which takes the warp-MMA
+// kernels for dim_head 32 and falls back to these
+namespace tbns {
+int token_attn_fwd_simt(const float* part, int nchunk, const float* Wq, const float* Wk, const float* Wv,
                                       const float* Wo, float* s, float* Tt, float* tok, float* q, float* k, float* v, float* A,
                                       float* O, float* P, void* P16, void* PT16, int B, int H, int D, int G, int Cout,
                                       void* stream) {
@@ -659,7 +662,7 @@ extern "C" int tbns_pa_token_attn_fwd(const float* part, int nchunk, const float
   return TBNS_OK;
 }
 
-extern "C" int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const float* Wk, const float* Wv, const float* Wo,
+int token_attn_bwd_simt(const float* dP, const float* Wq, const float* Wk, const float* Wv, const float* Wo,
                                       const float* s, const float* tok, const float* q, const float* k, const float* v,
                                       const float* A, const float* O, float* dTt, float* ds, float* dWqkv_part, float* dWo_part,
                                       int B, int H, int D, int G, int Cout, void* stream) {
@@ -691,6 +694,7 @@ extern "C" int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const fl
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
+}  // namespace tbns
 
 extern "C" int tbns_pa_slice_bwd(const float* XF, const float* Ws, const float* bs, const float* temperature, const float* dw,
                                  const float* dTt, const float* ds, float* dXF, void* dXF16, float* dWs_part, float* dtau_part,

@@ -127,42 +127,65 @@ __global__ void __launch_bounds__(TK_THREADS) token_attn_fwd_mma_kernel(
   const long long bh = (long long)b * H + h;
   const int I = H * D, HG = H * G;
 
-  // this head's slice of to_out.weight and the shared q/k/v weights (128-byte rows, coalesced)
-  for (int idx = tid; idx < Cout * (D / 4); idx += TK_THREADS) {
-    const int c = idx >> 3, d4 = (idx & 7) * 4;
-    const float4 w4 = *reinterpret_cast<const float4*>(Wo + (long long)c * I + h * D + d4);
-    *reinterpret_cast<float4*>(Wos + c * LD + d4) = w4;
-  }
+  // shared q/k/v weights (128-byte rows, coalesced)
   for (int idx = tid; idx < D * (D / 4); idx += TK_THREADS) {
     const int r = idx >> 3, d4 = (idx & 7) * 4;
     *reinterpret_cast<float4*>(Wqs + r * LD + d4) = *reinterpret_cast<const float4*>(Wq + r * D + d4);
     *reinterpret_cast<float4*>(Wks + r * LD + d4) = *reinterpret_cast<const float4*>(Wk + r * D + d4);
     *reinterpret_cast<float4*>(Wvs + r * LD + d4) = *reinterpret_cast<const float4*>(Wv + r * D + d4);
   }
-  // 1. fixed-order reduction of the per-chunk partials [nchunk][G][D+1] (eight independent loads in flight)
-  const float* pin = part + bh * nchunk * G * (D + 1);
-  constexpr int PS = G * (D + 1);
-  for (int o = tid; o < PS; o += TK_THREADS) {
-    float acc = 0.f;
-    int c = 0;
-    for (; c + 7 < nchunk; c += 8) {
-      float p[8];
+  // this head's slice of to_out.weight: requested now (registers), parked in shared memory once the reduction scratch is free
+  constexpr int WR = 8;
+  float4 wreg[WR];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) p[u] = pin[(long long)(c + u) * PS + o];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc += p[u];
-    }
-    for (; c < nchunk; ++c) acc += pin[(long long)c * PS + o];
-    const int g = o / (D + 1), dd = o - g * (D + 1);
-    if (dd == D) {
-      ssum[g] = acc;
-      s_out[bh * G + g] = acc;
-    } else {
-      q[g * LD + dd] = acc;   // q temporarily holds Tt
-      Tt_out[bh * GD + g * D + dd] = acc;
-    }
+  for (int r = 0; r < WR; ++r) {
+    const int idx = tid + r * TK_THREADS;
+    if (idx < Cout * (D / 4)) wreg[r] = *reinterpret_cast<const float4*>(Wo + (long long)(idx >> 3) * I + h * D + (idx & 7) * 4);
   }
-  __syncthreads();
+  // 1. fixed-order reduction of the per-chunk partials [nchunk][G][D+1].  The kernel's critical path is memory latency, so the
+  //    loads are spread for maximal parallelism: warp w sums chunks w, w+8, ... for ALL outputs (33 independent loads per lane
+  //    and chunk), the eight warp sums are combined in warp order through shared memory (the to_out slice is staged into that
+  //    region afterwards).  Order of additions is fixed -> bitwise reproducible.
+  const float* pin = part + bh * nchunk * G * (D + 1);
+  constexpr int PS = G * (D + 1);       // 1056 (G = 32) / 2112 (G = 64): a multiple of 32
+  float* red = Wos;                      // [8 warps][PS/2 or PS] floats <= Cout * LD (checked on the host)
+  constexpr int HALF = 33 * 32;          // outputs per pass (33 per lane)
+  for (int base_o = 0; base_o < PS; base_o += HALF) {
+    float acc[33];
+#pragma unroll
+    for (int i = 0; i < 33; ++i) acc[i] = 0.f;
+    for (int c = warp; c < nchunk; c += TK_WARPS) {
+      const float* pc = pin + (long long)c * PS + base_o + lane;
+#pragma unroll
+      for (int i = 0; i < 33; ++i) acc[i] += pc[32 * i];
+    }
+#pragma unroll
+    for (int i = 0; i < 33; ++i) red[warp * HALF + lane + 32 * i] = acc[i];
+    __syncthreads();
+    for (int o = tid; o < HALF; o += TK_THREADS) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < TK_WARPS; ++w) a += red[w * HALF + o];
+      const int oo = base_o + o, g = oo / (D + 1), dd = oo - g * (D + 1);
+      if (dd == D) {
+        ssum[g] = a;
+        s_out[bh * G + g] = a;
+      } else {
+        q[g * LD + dd] = a;   // q temporarily holds Tt
+        Tt_out[bh * GD + g * D + dd] = a;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < WR; ++r) {
+    const int idx = tid + r * TK_THREADS;
+    if (idx < Cout * (D / 4)) *reinterpret_cast<float4*>(Wos + (idx >> 3) * LD + (idx & 7) * 4) = wreg[r];
+  }
+  for (int idx = tid + WR * TK_THREADS; idx < Cout * (D / 4); idx += TK_THREADS) {   // Cout > 256
+    const int c = idx >> 3, d4 = (idx & 7) * 4;
+    *reinterpret_cast<float4*>(Wos + c * LD + d4) = *reinterpret_cast<const float4*>(Wo + (long long)c * I + h * D + d4);
+  }
   // 2. normalise
   for (int o = tid; o < GD; o += TK_THREADS) {
     const int g = o >> 5, dd = o & 31;
@@ -285,10 +308,10 @@ struct TkBwdSmem {
   static constexpr int WQ = A + G * LA, WK = WQ + TK_D * TK_LD, WV = WK + TK_D * TK_LD;
   static constexpr int SS = WV + TK_D * TK_LD;
   static constexpr int OS = SS + G;                       // O [G][TK_LD]
-  static constexpr int R0 = OS + G * TK_LD;               // region: { dP tile [G][Cout+8] | Wo slice [Cout][32] swizzled } then,
+  static constexpr int R0 = OS + G * TK_LD;               // region: { dP tile [G][Cout+4] | Wo slice [Cout][32] swizzled } then,
                                                           // once dO and dWo are done, { dA | dq | dk | dv }
   static constexpr int floats(int Cout) {
-    const int a = G * (Cout + 8) + Cout * TK_D, b = G * LA + 3 * G * TK_LD;
+    const int a = G * (Cout + 4) + Cout * TK_D, b = G * LA + 3 * G * TK_LD;
     return R0 + (a > b ? a : b);
   }
 };
@@ -314,7 +337,7 @@ __global__ void __launch_bounds__(TK_THREADS) token_attn_bwd_mma_kernel(
   float* Wvs = sm + S::WV;
   float* ssum = sm + S::SS;
   float* Os = sm + S::OS;
-  const int LP = Cout + 8;                 // dP tile row stride: conflict-free as K-contiguous AND as M-contiguous A operand
+  const int LP = Cout + 4;                 // dP tile row stride: conflict-free as the K-contiguous A operand of the long (K = Cout) contraction
   float* dPs = sm + S::R0;                 // [G][LP]
   float* Wos = dPs + G * LP;               // [Cout][32], swizzled (wo_sw)
   float* dA = sm + S::R0;                  // after the barrier below: [G][LA]
@@ -476,7 +499,8 @@ extern "C" int tbns_pa_token_attn_fwd(const float* part, int nchunk, const float
                     reinterpret_cast<uintptr_t>(Wv) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                     reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(O) | reinterpret_cast<uintptr_t>(P) |
                     reinterpret_cast<uintptr_t>(P16)) & 15) == 0;
-  if (token_mma_enabled() && D == TK_D && (G == 32 || G == 64) && Cout % 16 == 0 && al && H <= 65535 && B <= 65535) {
+  if (token_mma_enabled() && D == TK_D && (G == 32 || G == 64) && Cout % 16 == 0 && Cout * TK_LD >= TK_WARPS * 33 * 32 && al &&
+      H <= 65535 && B <= 65535) {
     const size_t smem = sizeof(float) * (size_t)(G == 32 ? TkFwdSmem<32>::floats(Cout) : TkFwdSmem<64>::floats(Cout));
     if (smem <= 227 * 1024) {
       dim3 grid(H, B);
