@@ -154,6 +154,15 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 // fused epilogue on the two 16x256b fragments of a warp's 32-lane quadrant: v[0] = lanes 0..15, v[1] = lanes 16..31 (layout
 // above); grow[k] = global row of tile row (t/4 + 8k) or -1; n = first of the 32 columns; t = lane id.
 // All global loads (GELU' input, residual) are issued before any arithmetic so their latencies overlap.
@@ -256,9 +265,11 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
         x1 = __uint_as_float(u1);
       }
       if (ok && (K_C || (GEN && p.C))) *reinterpret_cast<float2*>(p.C + gr * p.ldc + c) = make_float2(x0, x1);
-      if (EPI >= 0 && (EPI & EPI_LN)) {   // row statistics of the values just written (fused LayerNorm, pass 1)
-        st1[k] += x0 + x1;
+      if (EPI >= 0 && (EPI & EPI_LN)) {   // row statistics of the values just written (fused LayerNorm, pass 1); the values
+        st1[k] += x0 + x1;               // themselves go back into the fragment: the caller parks them in TMEM for pass 2
         st2[k] = fmaf(x0, x0, fmaf(x1, x1, st2[k]));
+        v[k >> 1][4 * j + 2 * (k & 1)] = x0;
+        v[k >> 1][4 * j + 2 * (k & 1) + 1] = x1;
       }
       if (K_C16 || (GEN && p.C16)) {
         // bf16 pairs are only 4 bytes: trade pairs with the neighbouring lane so that every thread owns 4 consecutive columns
@@ -279,10 +290,11 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
   }
 }
 
-// fused LayerNorm, pass 2: re-read this thread's own fp32 outputs of one 32-column chunk (L2 hits), normalise, bf16 store
-// (same lane-pair exchange as the C16 path: four threads fill one 32-byte sector of a row)
-__device__ __forceinline__ void tc_epi_ln_store(const TcParams& p, const long long (&grow)[4], const float (&mu)[4], const float (&rs)[4],
-                                                int n, int t) {
+// fused LayerNorm, pass 2: the post-epilogue values of one 32-column chunk come back from TMEM (fragment layout of
+// tmem_ld_16x256b_x4), are normalised and stored as bf16 (same lane-pair exchange as the C16 path: four threads fill one
+// 32-byte sector of a row)
+__device__ __forceinline__ void tc_epi_ln_store(const TcParams& p, const float (&v)[2][16], const long long (&grow)[4], const float (&mu)[4],
+                                                const float (&rs)[4], int n, int t) {
   const int cb = n + 2 * (t & 3);
   float2 g[4], b[4];
 #pragma unroll
@@ -290,19 +302,14 @@ __device__ __forceinline__ void tc_epi_ln_store(const TcParams& p, const long lo
     g[j] = *reinterpret_cast<const float2*>(p.ln_gamma + cb + 8 * j);
     b[j] = *reinterpret_cast<const float2*>(p.ln_beta + cb + 8 * j);
   }
-  float2 x[4][4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      x[k][j] = grow[k] >= 0 ? *reinterpret_cast<const float2*>(p.C + grow[k] * p.ldc + cb + 8 * j) : make_float2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const bool ok = grow[k] >= 0;
     uint32_t mine[2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float y0 = fmaf((x[k][j].x - mu[k]) * rs[k], g[j].x, b[j].x), y1 = fmaf((x[k][j].y - mu[k]) * rs[k], g[j].y, b[j].y);
+      const float x0 = v[k >> 1][4 * j + 2 * (k & 1)], x1 = v[k >> 1][4 * j + 2 * (k & 1) + 1];
+      const float y0 = fmaf((x0 - mu[k]) * rs[k], g[j].x, b[j].x), y1 = fmaf((x1 - mu[k]) * rs[k], g[j].y, b[j].y);
       __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
       mine[j & 1] = *reinterpret_cast<uint32_t*>(&h2);
       if (j & 1) {
@@ -463,19 +470,23 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         tmem_ld_16x256b_x4(ta, v[0]);                    // lanes q*32 + 0..15
         tmem_ld_16x256b_x4(ta + (16u << 16), v[1]);      // lanes q*32 + 16..31
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 * (TCP_EPI_WARPS / 4) >= BN) {
+        if (!LN && c0 + 32 * (TCP_EPI_WARPS / 4) >= BN) {
           // last TMEM read of this tile by this thread: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           mbar_arrive(bar_acce + as * 8);
           handed_back = true;
         }
         tc_epi_frag2<EPI>(p, v, grow, n0 + c0, lane, st1, st2);
+        if (LN) {   // park the post-epilogue values where the accumulator was: pass 2 reads them back without touching L2
+          tmem_st_16x256b_x4(ta, v[0]);
+          tmem_st_16x256b_x4(ta + (16u << 16), v[1]);
+        }
       }
-      if (!handed_back) mbar_arrive(bar_acce + as * 8);   // narrow tiles: this warp's column slot does not exist
+      if (!LN && !handed_back) mbar_arrive(bar_acce + as * 8);   // narrow tiles: this warp's column slot does not exist
       if (LN) {
         // fused LayerNorm of the output rows (the tile holds whole rows: N == BN).  Pass 1 above accumulated sum / sum of
         // squares of this thread's columns; combine the four lanes that share a row, then the four column-slot warps through
-        // shared memory (double-buffered by tile parity: one named barrier per tile), then normalise the values just written.
+        // shared memory (double-buffered by tile parity: one named barrier per tile), then normalise the parked values.
         float2* red = reinterpret_cast<float2*>(gen + S::LN_OFF) + (j & 1) * (4 * TC_BM);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -485,6 +496,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           st2[k] += __shfl_xor_sync(0xffffffffu, st2[k], 2);
           if ((lane & 3) == 0) red[slot * TC_BM + q * 32 + (lane >> 2) + 8 * k] = make_float2(st1[k], st2[k]);
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(TCP_THREADS - 64) : "memory");
         float mu[4], rs[4];
         const float invN = 1.0f / (float)BN;
@@ -506,7 +518,16 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
         }
 #pragma unroll 1
-        for (int c0 = slot * 32; c0 < BN; c0 += 32 * (TCP_EPI_WARPS / 4)) tc_epi_ln_store(p, grow, mu, rs, n0 + c0, lane);
+        for (int c0 = slot * 32; c0 < BN; c0 += 32 * (TCP_EPI_WARPS / 4)) {
+          float v[2][16];
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0);
+          tmem_ld_16x256b_x4(ta, v[0]);
+          tmem_ld_16x256b_x4(ta + (16u << 16), v[1]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tc_epi_ln_store(p, v, grow, mu, rs, n0 + c0, lane);
+        }
+        tc_fence_before();
+        mbar_arrive(bar_acce + as * 8);   // the buffer (accumulator, then parked values) is free for the MMA of tile j + 2
       }
     }
   }
