@@ -32,6 +32,16 @@ __device__ __forceinline__ void st_scatter_col(uint8_t* tile, uint32_t panel_str
   for (int r = 0; r < ROWS; ++r) *reinterpret_cast<float*>(p + sw128_off(r, c)) = v[r];
 }
 
+// same for a bf16 K-major operand ([rows][tokens], 2 panels of 64 tokens): the operands of the token contraction in the
+// backward kernel (dWs^T += X^T dL) - half the shared memory of the tf32 tiles, which is what lets three CTAs share an SM
+template <int ROWS>
+__device__ __forceinline__ void st_scatter_col16(uint8_t* tile, uint32_t panel_stride, int t, const float (&v)[ROWS]) {
+  uint8_t* p = tile + (t >> 6) * panel_stride + (t & 7) * 2;
+  const int c = (t & 63) >> 3;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) *reinterpret_cast<__nv_bfloat16*>(p + sw128_off(r, c)) = __float2bfloat16_rn(v[r]);
+}
+
 // Shared memory is what limits residency here (each chunk is a chain of short dependent phases, so the SM wants many CTAs
 // in flight): 53 KB per CTA for G = 32, i.e. four CTAs per SM.
 template <int G>
@@ -244,21 +254,23 @@ __device__ __forceinline__ float st_rna(float x) {
 template <int G>
 struct StBwdSmem {
   static constexpr int KP = G / 32;                    // 128-byte k-panels of a K = G operand
-  static constexpr int XS = 0;                         // 2 stages x { X tile, F tile } (TMA); within a stage the X tile later
-  static constexpr int STAGE = 2 * ST_TILE;            // becomes k-panel 0 of the w tile and the F tile k-panel 1 (G = 64) or,
-                                                       // for G = 32, the dL tile (F is dead once the first MMA group has read it)
-  static constexpr int DL = 2 * STAGE;                 // dL tile [128 tokens][G] K-major, KP panels (own region only for G = 64)
-  static constexpr int XT = DL + (KP == 1 ? 0 : KP * (int)ST_TILE);   // X^T: 4 panels x [32 d][32 tokens]; M = 128 rows are read:
-                                                       // the don't-care 12 KB tail aliases dL^T
-  static constexpr int LT = XT + 4 * ST_TP;            // dL^T: 4 panels x [G][32 tokens]
-  static constexpr int WS = LT + 4 * G * 128;          // Ws   [G][32]   K-major (B of the logits)
+  static constexpr int XS = 0;                         // { X tile, F tile } (TMA): the X tile later becomes k-panel 0 of the w
+  static constexpr int STAGE = 2 * ST_TILE;            // tile and the F tile k-panel 1 (G = 64) or, for G = 32, the dL tile
+                                                       // (F is dead once the first MMA group has read it)
+  static constexpr int DL = STAGE;                     // dL tile [128 tokens][G] K-major, KP panels (own region only for G = 64)
+  static constexpr int XT = DL + (KP == 1 ? 0 : KP * (int)ST_TILE);   // X^T bf16: 2 panels x [32 d][64 tokens]; the MMA reads
+                                                       // M = 128 rows per panel: the don't-care tail aliases what follows
+  static constexpr int XT_P = 32 * 128;                // panel stride of X^T
+  static constexpr int LT = XT + 2 * XT_P;             // dL^T bf16: 2 panels x [G][64 tokens]
+  static constexpr int WS = LT + 2 * G * 128;          // Ws   [G][32]   K-major (B of the logits)
   static constexpr int DT = WS + G * 128;              // dTt  [G][32]   K-major (B of dwv)
   static constexpr int WST = DT + G * 128;             // Ws^T [32][G]   K-major, KP panels of [32][128 B] (B of dX)
   static constexpr int DTT = WST + KP * 4096;          // dTt^T[32][G]   (B of dF)
-  static constexpr int BAR = DTT + KP * 4096;          // mbarriers: tma[2], mma ; tmem slot
+  static constexpr int BAR = DTT + KP * 4096;          // mbarriers: tma, mma ; tmem slot
   static constexpr int MISC = BAR + 32;                // bias [G], ds [G], red[4]
   static constexpr int TOTAL = MISC + (2 * G + 8) * 4; // no alignment slack: the kernel declares its dynamic smem 1024-aligned
-                                                       // (G = 32: 115 016 B, two CTAs per SM)
+                                                       // (G = 32: 65 832 B and 128 TMEM columns -> three CTAs per SM)
+  static_assert(XT + XT_P + 16384 <= TOTAL, "the 128-row reads of the X^T operand must stay inside the allocation");
 };
 
 // grid (groups, H, B), block 128
@@ -271,13 +283,15 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
                                                               int nchunk, int clamp) {
   using S = StBwdSmem<G>;
   constexpr int KP = S::KP;
-  constexpr int TMEM_COLS = 256;                 // L [G] | dwv [G] | dF [32] | dX [32] | dWs^T [G]
-  constexpr uint32_t C_L = 0, C_DW = G, C_DF = 2 * G, C_DX = 2 * G + 32, C_WS = 2 * G + 64;
+  // L [G] | dwv [G] | dWs^T [G]; dF [32] and dX [32] reuse the L / dwv columns (read into registers before the second MMA
+  // group is issued): 96 columns -> 128 allocated for G = 32, so three CTAs share the SM's 512 columns
+  constexpr int TMEM_COLS = G == 32 ? 128 : 256;
+  constexpr uint32_t C_L = 0, C_DW = G, C_DF = 0, C_DX = G, C_WS = 2 * G;
   extern __shared__ __align__(1024) uint8_t smem_al[];   // SW128 tiles need 1024-byte aligned bases
   const uint32_t base = smem_u32(smem_al);
   if (base & 1023u) __trap();
   uint8_t* gen = smem_al;
-  const uint32_t bar_tma = base + S::BAR, bar_mma = bar_tma + 16;   // bar_tma: one per stage
+  const uint32_t bar_tma = base + S::BAR, bar_mma = bar_tma + 16;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + S::BAR + 24);
   float* bsm = reinterpret_cast<float*>(gen + S::MISC);
   float* dss = bsm + G;
@@ -290,7 +304,6 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXF) : "memory");
     mbar_init(bar_tma, 1);
-    mbar_init(bar_tma + 8, 1);
     mbar_init(bar_mma, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -328,30 +341,27 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
   const uint32_t tmem = *tmem_slot;
   const float tau = st_clamp_tau(temperature[h], clamp);
   const float inv_tau = 1.0f / tau;
-  constexpr uint32_t idesc_g = umma_idesc(2, G, 0, 0);    // N = G
-  constexpr uint32_t idesc_d = umma_idesc(2, 32, 0, 0);   // N = dim_head
+  constexpr uint32_t idesc_g = umma_idesc(2, G, 0, 0);    // tf32, N = G
+  constexpr uint32_t idesc_d = umma_idesc(2, 32, 0, 0);   // tf32, N = dim_head
+  constexpr uint32_t idesc_t = umma_idesc(1, G, 0, 0);    // bf16, N = G (token contraction)
 
   uint32_t ph_mma = 0;
   float dbs_acc = 0.f, dtau_acc = 0.f;
   int iter = 0;
-  // two-stage TMA ring: the X / F tiles of this CTA's next chunk are in flight while the current chunk is processed
-  auto issue = [&](int chunk, int stage) {
-    const uint32_t bar = bar_tma + stage * 8, dst = base + S::XS + stage * S::STAGE;
-    mbar_expect_tx(bar, 2 * ST_TILE);
-    tma_load_3d(dst, &tmXF, bar, h * ST_D, chunk * ST_TOK, b);
-    tma_load_3d(dst + ST_TILE, &tmXF, bar, I + h * ST_D, chunk * ST_TOK, b);
+  // one X / F stage per CTA (three CTAs per SM cover each other's latencies); the next chunk's tiles are requested as soon as
+  // the second MMA group - the last reader of the w / dL tiles written over them - has completed
+  auto issue = [&](int chunk) {
+    mbar_expect_tx(bar_tma, 2 * ST_TILE);
+    tma_load_3d(base + S::XS, &tmXF, bar_tma, h * ST_D, chunk * ST_TOK, b);
+    tma_load_3d(base + S::XS + ST_TILE, &tmXF, bar_tma, I + h * ST_D, chunk * ST_TOK, b);
   };
-  if (tid == 0 && blockIdx.x < nchunk) issue(blockIdx.x, 0);
+  if (tid == 0 && blockIdx.x < nchunk) issue(blockIdx.x);
   for (int chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x, ++iter) {
     const int n0 = chunk * ST_TOK;
     const bool valid = n0 + tid < N;
     const long long row = (long long)b * N + n0 + tid;
-    const int stage = iter & 1;
-    const uint32_t xs = S::XS + stage * S::STAGE, fs = xs + ST_TILE;
+    const uint32_t xs = S::XS, fs = xs + ST_TILE;
     const uint32_t dl = KP == 1 ? fs : (uint32_t)S::DL;
-    // the other stage's tiles (and the w / dL tiles written over them) were last read by the MMAs of the previous
-    // iteration, which were waited for before its closing barrier
-    if (tid == 0 && chunk + (int)gridDim.x < nchunk) issue(chunk + gridDim.x, stage ^ 1);
     // this token's deslice gradient row (issued early: overlaps the TMA / MMA latency)
     float dwv[G];
     if (valid) {
@@ -371,7 +381,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
 #pragma unroll
       for (int g = 0; g < G; ++g) dwv[g] = 0.f;
     }
-    mbar_wait(bar_tma + stage * 8, (iter >> 1) & 1);
+    mbar_wait(bar_tma, iter & 1);
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -390,7 +400,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
         const float4 v = *reinterpret_cast<const float4*>(gen + xs + sw128_off(tid, c));
         x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
       }
-      st_scatter_col<ST_D>(gen + S::XT, ST_TP, tid, x);
+      st_scatter_col16<ST_D>(gen + S::XT, S::XT_P, tid, x);
     }
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
@@ -439,7 +449,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
         *reinterpret_cast<float4*>(gen + dl + (c >> 3) * ST_TILE + sw128_off(tid, c & 7)) =
             make_float4(dwv[4 * c], dwv[4 * c + 1], dwv[4 * c + 2], dwv[4 * c + 3]);
       }
-      st_scatter_col<G>(gen + S::LT, G * 128, tid, dwv);
+      st_scatter_col16<G>(gen + S::LT, G * 128, tid, dwv);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -453,27 +463,33 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
         umma_tf32(tmem + C_DX, umma_desc_kmajor_sw128(base + dl + ko), umma_desc_kmajor_sw128(base + S::WST + kb), idesc_d, k != 0);
       }
 #pragma unroll
-      for (int kp = 0; kp < 4; ++kp)     // dWs^T[d][g] += sum_t X^T[d][t] dL^T[g][t]
+      for (int kp = 0; kp < 2; ++kp)     // dWs^T[d][g] += sum_t X^T[d][t] dL^T[g][t]   (bf16 operands, 16 tokens per MMA)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_tf32(tmem + C_WS, umma_desc_kmajor_sw128(base + S::XT + kp * ST_TP + k * 32),
-                    umma_desc_kmajor_sw128(base + S::LT + kp * (G * 128) + k * 32), idesc_g, (iter | kp | k) != 0);
+          umma_bf16(tmem + C_WS, umma_desc_kmajor_sw128(base + S::XT + kp * S::XT_P + k * 32),
+                    umma_desc_kmajor_sw128(base + S::LT + kp * (G * 128) + k * 32), idesc_t, (iter | kp | k) != 0);
       umma_commit(bar_mma);
     }
-    if (tid < G) {   // dbs[g] += sum_t dL[t][g]: row g of dL^T
+    if (tid < G) {   // dbs[g] += sum_t dL[t][g]: row g of dL^T (bf16, 2 panels of 64 tokens)
       float a = 0.f;
 #pragma unroll
-      for (int kp = 0; kp < 4; ++kp)
+      for (int kp = 0; kp < 2; ++kp)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(gen + S::LT + kp * (G * 128) + sw128_off(tid, c));
-          a += (v.x + v.y) + (v.z + v.w);
+          const uint4 u = *reinterpret_cast<const uint4*>(gen + S::LT + kp * (G * 128) + sw128_off(tid, c));
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h2[j]);
+            a += f.x + f.y;
+          }
         }
       dbs_acc += a;
     }
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     tc_fence_after();
+    if (tid == 0 && chunk + (int)gridDim.x < nchunk) issue(chunk + gridDim.x);   // overlaps the stores below
     {
       // this token's dX / dF rows -> bf16 operand of the projection dgrad / wgrad GEMMs
       float o[ST_D];
