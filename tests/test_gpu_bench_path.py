@@ -366,3 +366,38 @@ def test_fused_rollout_step_equals_literal_loop():
         f2 = fd.clone().requires_grad_(True)
         m(xd, fx=f2).square().sum().backward()
         assert f2.grad is not None and bool(torch.isfinite(f2.grad).all()) and float(f2.grad.abs().max()) > 0
+
+
+def test_cfg5_two_layer_model_bf16_and_rollout_metric():
+    """BASELINE cfg 5 shape (256x256 grid, C=256, 8 heads, slice_num 64), two layers of the full model in bf16 mode: one call
+    against the fp32 oracle on bf16-representable weights / inputs, then a 3-step closed-loop rollout through the graphed
+    fused rollout step (train.GraphedRollout: history buffer, in-place prediction) against the oracle's literal loop - per-step
+    fields and the accumulated error metric (ns_vorticity_unrolling.py:264-286, "unchanged rollout error")."""
+    import transformerbasednavierstokesolver_b200 as pkg
+    from transformerbasednavierstokesolver_b200 import train
+    from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Model
+    dev = torch.device("cuda:0")
+    pkg.set_default_precision("bf16")
+    kw = dict(space_dim=2, n_layers=2, n_hidden=256, n_head=8, fun_dim=10, out_dim=1, slice_num=64, ref=8, unified_pos=1, H=256, W=256)
+    torch.manual_seed(51)
+    m = Model(**kw)
+    _condition(m)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x, fx, yy = train.synthetic_ns_batch(1, 256, 10, 3, seed=53)
+    fx, yy = fx.bfloat16().float(), yy.bfloat16().float()
+    fwd = lambda a, b: OM.model_forward(a, b, sd, 2, 8, grid=(256, 256), unified_pos=True, ref=8)
+    with torch.no_grad():
+        ref = OM.rollout(x, fx, fwd, T=3)
+    m = m.to(dev).eval()
+    xd, fd = x.to(dev), fx.to(dev)
+    with torch.no_grad():
+        first = m(xd, fx=fd)
+    assert O.rel_l2(first.cpu(), ref[..., :1]) < 3 * OUT_TOL          # preprocess + two blocks through the C -> 1 head
+    runner = train.GraphedRollout(m, (xd, fd), T=3, step=1, warmup=1)
+    roll = runner((xd, fd)).clone()
+    eager = train.rollout(m, xd, fd, T=3, step=1)
+    assert torch.equal(roll, eager), "graph replay of the fused rollout step must equal the eager fused rollout"
+    assert O.rel_l2(roll.cpu(), ref) < 2e-2
+    e_ref = float(O.rel_l2_sum(ref.reshape(1, -1), yy.reshape(1, -1)))
+    e_new = float(O.rel_l2_sum(roll.cpu().reshape(1, -1), yy.reshape(1, -1)))
+    assert abs(e_new - e_ref) < 5e-3 * abs(e_ref)
