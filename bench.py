@@ -501,7 +501,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "unrolled", "rollout_cfg5"])
     ap.add_argument("--look-ahead", type=int, default=2, help="--workload unrolled: chained model calls per window (1, 2, 4, 8, 10)")
     ap.add_argument("--rollout-batch", type=int, default=2, help="--workload rollout_cfg5: samples per GPU")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_exact"])
     ap.add_argument("--batched", type=int, default=1, help="evaluate the teacher-forced calls / windows as one batch (same math)")
     ap.add_argument("--graph", type=int, default=1, help="replay the step from CUDA graphs (fwd+bwd graph, eager NCCL all-reduce, "
                     "optimizer graph); 0 = eager launches")

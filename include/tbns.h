@@ -28,8 +28,10 @@ extern "C" {
 #define TBNS_ERR_UNSUPPORTED (-3)
 
 /* operand precision of the large token-dimension contractions (projections, to_out, MLP) */
-#define TBNS_PREC_FP32 0 /* fp32 operands, fp32 FMA accumulate  (north_star "fp32 mode", <=1e-5)  */
+#define TBNS_PREC_FP32 0 /* fp32 operands, fp32 accumulate       (north_star "fp32 mode", <=1e-5): 3xTF32 split products
+                            on tcgen05 (error <= 2^-21 per product) where the shape fills a tensor-core tile, fp32 FMA otherwise */
 #define TBNS_PREC_BF16 1 /* bf16 operands, fp32 accumulate       (north_star "bf16 mode", <=2e-3) */
+#define TBNS_PREC_FP32_EXACT 2 /* fp32 operands, fp32 FMA accumulate on the SIMT engine for every shape (also: env TBNS_FP32_TC=0) */
 
 const char* tbns_last_error(void);
 int tbns_version(void);

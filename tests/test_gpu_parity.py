@@ -33,7 +33,7 @@ def _ops():
 # ------------------------------------------------------------------------------------------------
 # generic GEMM engine
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (200, 130, 52), (37, 5, 7), (1, 300, 33), (513, 64, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (200, 130, 52), (37, 5, 7), (1, 300, 33), (513, 64, 1), (300, 257, 421), (129, 33, 32)])
 @pytest.mark.parametrize("a_kind,b_kind", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_gemm_layouts(dev, M, N, K, a_kind, b_kind):
     ops = _ops()
@@ -73,7 +73,7 @@ def test_gemm_batched_splitk_epilogues(dev):
     assert O.rel_l2(C.cpu(), (A.double() @ B.double()) * O.gelu_grad(small.double())) < 2e-6
 
 
-@pytest.mark.parametrize("Bt,Hg,Wg,C,I2", [(2, 5, 7, 8, 12), (1, 9, 4, 12, 20), (1, 1, 1, 4, 4)])
+@pytest.mark.parametrize("Bt,Hg,Wg,C,I2", [(2, 5, 7, 8, 12), (1, 9, 4, 12, 20), (1, 1, 1, 4, 4), (2, 9, 12, 32, 64), (3, 16, 16, 20, 72)])
 def test_gemm_conv_modes(dev, Bt, Hg, Wg, C, I2):
     """conv fprop / dgrad / wgrad gathers against the oracle's shifted-matmul restatement"""
     ops = _ops()
@@ -105,6 +105,35 @@ def test_gemm_conv_modes(dev, Bt, Hg, Wg, C, I2):
         assert O.rel_l2(dWfx.cpu(), rdWfx) < 2e-6
     db = ops.colsum(dXF.to(dev).reshape(Bt * N, I2), Bt * N, I2)
     assert O.rel_l2(db.cpu(), torch.cat([rdbx, rdbfx])) < 2e-6
+
+
+@pytest.mark.parametrize("a_kind,b_kind", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_fp32_mode_is_3xtf32_on_tensor_cores(dev, a_kind, b_kind):
+    """fp32 mode (TBNS_PREC_FP32) runs the 3xTF32 tcgen05 engine (csrc/gemm_x3.cu): long K (ring wrap, several phases of every
+    stage barrier), split-K, both operand orientations.  Its error against fp64 must be fp32-class (a plain TF32 product would
+    be ~5e-4), and it must not be bit-identical to the FMA engine (TBNS_PREC_FP32_EXACT) - that would mean it never ran."""
+    ops = _ops()
+    from transformerbasednavierstokesolver_b200._lib import TBNS_PREC_FP32, TBNS_PREC_FP32_EXACT
+    g = torch.Generator().manual_seed(11 + 2 * a_kind + b_kind)
+    M, N, K = 384, 256, 1000
+    # wide dynamic range: the lo parts matter
+    A = torch.randn(M, K, generator=g) * torch.exp(2 * torch.randn(M, K, generator=g))
+    B = torch.randn(K, N, generator=g) * torch.exp(2 * torch.randn(K, N, generator=g))
+    Ad = (A if a_kind == 0 else A.t()).contiguous().to(dev)
+    Bd = (B.t() if b_kind == 0 else B).contiguous().to(dev)
+    ref = A.double() @ B.double()
+    outs = {}
+    for prec in (TBNS_PREC_FP32, TBNS_PREC_FP32_EXACT):
+        for sk in (1, 4):
+            C = torch.empty(M, N, device=dev)
+            ops.gemm(M=M, N=N, K=K, A=Ad, lda=Ad.shape[1], a_kind=a_kind, B=Bd, ldb=Bd.shape[1], b_kind=b_kind, C=C, ldc=N,
+                     precision=prec, split_k=sk)
+            outs[(prec, sk)] = C.cpu()
+            assert O.rel_l2(outs[(prec, sk)], ref) < 1e-6, (prec, sk)
+    assert not torch.equal(outs[(TBNS_PREC_FP32, 1)], outs[(TBNS_PREC_FP32_EXACT, 1)])
+    # element-wise: no entry is off by more than fp32-class error relative to the magnitude of its dot product
+    scale = (A.double().abs() @ B.double().abs())
+    assert ((outs[(TBNS_PREC_FP32, 1)].double() - ref).abs() / scale).max() < 2e-6
 
 
 def test_gemm_bf16_mode_rounds_operands(dev):

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtbns.so")
 
 TBNS_PREC_FP32 = 0
 TBNS_PREC_BF16 = 1
+TBNS_PREC_FP32_EXACT = 2
 
 _fp = C.c_void_p  # device pointers travel as integers
 _ll = C.c_longlong

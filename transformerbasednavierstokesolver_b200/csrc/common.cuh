@@ -12,6 +12,7 @@ namespace tbns {
 
 void set_error(const char* fmt, ...);
 int splitk_reduce(const tbns_gemm_desc& d, cudaStream_t st);  // gemm_simt.cu
+int gemm_x3_launch(const tbns_gemm_desc& d, int vecA, int vecB, int vecC, dim3 grid, cudaStream_t st);  // gemm_x3.cu
 
 #define TBNS_REQUIRE(cond, ...)          \
   do {                                   \

@@ -18,9 +18,10 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import GemmDesc, TBNS_PREC_BF16, TBNS_PREC_FP32, check
+from ._lib import GemmDesc, TBNS_PREC_BF16, TBNS_PREC_FP32, TBNS_PREC_FP32_EXACT, check
 
-PRECISIONS = {"fp32": TBNS_PREC_FP32, "bf16": TBNS_PREC_BF16}
+# "fp32": 3xTF32 split products on tcgen05 (fp32-class error, gemm_x3.cu); "fp32_exact": fp32 FMA on the SIMT engine
+PRECISIONS = {"fp32": TBNS_PREC_FP32, "bf16": TBNS_PREC_BF16, "fp32_exact": TBNS_PREC_FP32_EXACT}
 _SM_COUNT = {}
 
 
