@@ -25,6 +25,9 @@ dXF16 = torch.randn(M, I2, generator=g).to(dev).bfloat16()
 Wd16 = (torch.randn(C, 9 * I2, generator=g) / 68).to(dev).bfloat16()
 dWx = torch.empty(C, C, 3, 3, device=dev)
 dWfx = torch.empty(C, C, 3, 3, device=dev)
+lng = torch.randn(C, generator=g).to(dev)
+lnb = torch.randn(C, generator=g).to(dev)
+PT16 = (torch.randn(B, C, C, generator=g) / 16).to(dev).bfloat16()
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
 cases = {
@@ -36,6 +39,8 @@ cases = {
     "dpred 81920x256x256 *stored gelu'+bf16 (act 4)": (lambda: ops.gemm_tc(x16, W1, None, None, 1, 1, M, C, C, act=4, aux_in=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
     "dx2 81920x256x256 fp32 out": (lambda: ops.gemm_tc(x16, W1, out, None, 1, 1, M, C, C), 2.0 * M * C * C),
     "fc2 81920x256x256 +bias+res": (lambda: ops.gemm_tc(hid16, W1, out, b1, 1, 1, M, C, C, residual=res), 2.0 * M * C * C),
+    "fc2ln 81920x256x256 +bias+res+LayerNorm": (lambda: ops.gemm_tc(hid16, W1, out, b1, 1, 1, M, C, C, residual=res, ln=(lng, lnb, 1e-5)), 2.0 * M * C * C),
+    "deslice_out 20x4096x256x256 batched P +bias+res+LayerNorm": (lambda: ops.gemm_tc(hid16, PT16, out, b1, B, 1, Hg * Wg, C, C, w_batched=1, residual=res, ln=(lng, lnb, 1e-5)), 2.0 * M * C * C),
     "conv_wgrad 2304x512x81920": (lambda: ops.gemm_tc_wgrad(x16, dXF16, B, Hg, Wg, C, I2, taps=9, scatter=(dWx, dWfx), I=C), 2.0 * M * 9 * C * I2),
 }
 only = os.environ.get("MB_ONLY")          # comma-separated name prefixes (for ncu captures)

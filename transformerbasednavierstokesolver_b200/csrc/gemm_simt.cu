@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const tbns_gemm_desc d, i
 // reduce of a 256x256 weight gradient with ~70 partials from 64 serial CTAs into 512 CTAs with 9 loads per thread.
 template <int SL>
 __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const tbns_gemm_desc d, int vecC) {
+  pdl_sync();
   constexpr int OUTS = 256 / SL;
   __shared__ float4 red[SL > 1 ? 256 : 1];
   const long long n4 = (d.N + 3) / 4;
@@ -186,11 +187,11 @@ static void launch_splitk_reduce(const tbns_gemm_desc& d, int vecC, cudaStream_t
   const long long total = (long long)d.batch * d.M * ((d.N + 3) / 4);
   if (d.split_k >= 16 && total <= (long long)sm_count() * 8 * 32) {
     int blocks = (int)((total + 31) / 32);
-    gemm_splitk_reduce_kernel<8><<<blocks, 256, 0, st>>>(d, vecC);
+    (void)launch_pdl(gemm_splitk_reduce_kernel<8>, dim3(blocks), dim3(256), 0, st, d, vecC);   // the caller checks cudaGetLastError
   } else {
     int blocks = (int)((total + 255) / 256);
     if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-    gemm_splitk_reduce_kernel<1><<<blocks, 256, 0, st>>>(d, vecC);
+    (void)launch_pdl(gemm_splitk_reduce_kernel<1>, dim3(blocks), dim3(256), 0, st, d, vecC);
   }
 }
 

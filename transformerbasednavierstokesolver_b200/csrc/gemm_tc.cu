@@ -89,6 +89,7 @@ __device__ __forceinline__ uint32_t tc_prologue(uint32_t bar_full, uint32_t bar_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();   // set-up above touched no global data: it overlapped the previous kernel (common.cuh: PDL)
   return *tmem_slot;
 }
 
@@ -381,6 +382,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -609,6 +611,7 @@ gemm_tc_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   cluster_sync_all();   // the peer's barriers exist before anything signals them
   tc_fence_after();
+  pdl_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -909,6 +912,7 @@ gemm_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  pdl_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -985,6 +989,7 @@ gemm_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 // fp32 -> bf16 (round to nearest even), 8 elements per thread
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  pdl_sync();
   const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
   if (i + 7 < n) {
     const float4 a = *reinterpret_cast<const float4*>(in + i);
@@ -1024,8 +1029,7 @@ static int launch_tcp_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int sms = sm_count();
   const int total = m_tiles * (p.N / BN);
   const int grid = total < sms ? total : sms;
-  gemm_tc_persistent_kernel<BN, STAGES, EPI><<<grid, TCP_THREADS, S::TOTAL, st>>>(tmA, tmB, p, total);
-  TBNS_LAUNCH_CHECK();
+  TBNS_CUDA(launch_pdl(gemm_tc_persistent_kernel<BN, STAGES, EPI>, dim3(grid), dim3(TCP_THREADS), S::TOTAL, st, tmA, tmB, p, total));
   return TBNS_OK;
 }
 
@@ -1065,8 +1069,7 @@ static int launch_tc2_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int pairs = (m_tiles + 1) / 2 * (p.N / TC2_BN);
   int clusters = sm_count() / 2;
   if (pairs < clusters) clusters = pairs;
-  gemm_tc_2cta_kernel<EPI><<<2 * clusters, TCP_THREADS, Tc2Smem::TOTAL, st>>>(tmA, tmB, p, pairs, m_tiles);
-  TBNS_LAUNCH_CHECK();
+  TBNS_CUDA(launch_pdl(gemm_tc_2cta_kernel<EPI>, dim3(2 * clusters), dim3(TCP_THREADS), Tc2Smem::TOTAL, st, tmA, tmB, p, pairs, m_tiles));
   return TBNS_OK;
 }
 
@@ -1089,8 +1092,7 @@ static int launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgPar
   using S = TcSmem<BN, STAGES>;
   TBNS_SMEM_OPT_IN((gemm_tc_wgrad_kernel<BN, STAGES>), S::TOTAL);
   dim3 grid(tiles, gy);
-  gemm_tc_wgrad_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(tmA, tmB, p);
-  TBNS_LAUNCH_CHECK();
+  TBNS_CUDA(launch_pdl(gemm_tc_wgrad_kernel<BN, STAGES>, grid, dim3(TC_THREADS), S::TOTAL, st, tmA, tmB, p));
   return TBNS_OK;
 }
 
@@ -1105,8 +1107,7 @@ extern "C" int tbns_cast_bf16(const float* in, void* out, long long n, void* str
   if (n == 0) return TBNS_OK;
   TBNS_REQUIRE(al16p(in) && al16p(out), "tbns_cast_bf16: unaligned");
   const long long threads = (n + 7) / 8;
-  cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
-  TBNS_LAUNCH_CHECK();
+  TBNS_CUDA(launch_pdl(cast_bf16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, in, reinterpret_cast<__nv_bfloat16*>(out), n));
   return TBNS_OK;
 }
 
@@ -1212,8 +1213,7 @@ extern "C" int tbns_gemm_tc_wgrad(const tbns_tc_wgrad_desc* dp, void* stream) {
   if (pair) {
     TBNS_SMEM_OPT_IN((gemm_tc_wgrad2_kernel), Wg2Smem::TOTAL);
     dim3 grid(2 * tiles, gy);
-    gemm_tc_wgrad2_kernel<<<grid, TC_THREADS, Wg2Smem::TOTAL, st>>>(tmA, tmB, p);
-    rc = cudaGetLastError() == cudaSuccess ? TBNS_OK : TBNS_ERR_CUDA;
+    rc = launch_pdl(gemm_tc_wgrad2_kernel, grid, dim3(TC_THREADS), Wg2Smem::TOTAL, st, tmA, tmB, p) == cudaSuccess ? TBNS_OK : TBNS_ERR_CUDA;
     if (rc) set_error("gemm_tc_wgrad2_kernel launch failed");
   } else if (BN == 256) rc = launch_wg<256, 4>(tmA, tmB, p, tiles, gy, st);
   else if (BN == 128) rc = launch_wg<128, 6>(tmA, tmB, p, tiles, gy, st);

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(const floa
                                                                     const float* __restrict__ beta, float* __restrict__ y,
                                                                     __nv_bfloat16* __restrict__ y16, float* __restrict__ mean,
                                                                     float* __restrict__ rstd, int rows, int C, float eps) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= rows) return;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_reg_kernel(const 
                                                                         const float* __restrict__ beta, float* __restrict__ y,
                                                                         __nv_bfloat16* __restrict__ y16, float* __restrict__ mean,
                                                                         float* __restrict__ rstd, int rows, float eps) {
+  pdl_sync();
   constexpr int C = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 g4[NV], b4[NV];
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
                                                                     const float* __restrict__ gamma, const float* __restrict__ dres,
                                                                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
                                                                     float* __restrict__ part, int rows, int C) {
+  pdl_sync();
   extern __shared__ __align__(16) float sm[];  // [LN_WARPS][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* dg = sm + (long long)warp * 2 * C;
@@ -240,6 +243,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_reg_kernel(const 
                                                                         float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
                                                                         float* __restrict__ part, int rows,
                                                                         const float* __restrict__ wvec) {
+  pdl_sync();
   constexpr int C = NV * 128;
   __shared__ __align__(16) float sm[LN_WARPS][3][C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -324,6 +328,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ in, long long ld
                                       int rows_per_chunk);
 
 __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, long long cols, long long ld) {
+  pdl_sync();
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < cols; j += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int i = 0; i < rows; ++i) s += in[(long long)i * ld + j];
@@ -335,6 +340,7 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restri
 // rows l, l+32, ... in ascending order, then the lanes are combined in lane order: fixed order, bit-reproducible, and the
 // loads of a thread are independent so the pass is not a chain of exposed latencies.
 __global__ void __launch_bounds__(1024) reduce_rows_par_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, long long ld) {
+  pdl_sync();
   __shared__ float red[32][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -357,6 +363,7 @@ __global__ void __launch_bounds__(1024) reduce_rows_par_kernel(const float* __re
 // rows; 32 float4-lanes x 8 row-lanes, fixed-order combine in shared memory, then a deterministic second stage.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ in, long long ld, float* __restrict__ ws, int rows,
                                                             int cols, int rows_per_chunk) {
+  pdl_sync();
   __shared__ float4 red[8][32];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 128 + cl * 4;
@@ -406,13 +413,13 @@ extern "C" int tbns_layernorm_fwd(const float* x, const float* gamma, const floa
     if (ctas > 148 * 8) ctas = 148 * 8;   // 8 CTAs of 8 warps per SM, grid-stride over row pairs
     __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(y16);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C == 128) layernorm_fwd_reg_kernel<1><<<ctas, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, o16, mean, rstd, rows, eps);
-    else if (C == 256) layernorm_fwd_reg_kernel<2><<<ctas, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, o16, mean, rstd, rows, eps);
-    else layernorm_fwd_reg_kernel<4><<<ctas, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, o16, mean, rstd, rows, eps);
+    if (C == 128) TBNS_CUDA(launch_pdl(layernorm_fwd_reg_kernel<1>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, y, o16, mean, rstd, rows, eps));
+    else if (C == 256) TBNS_CUDA(launch_pdl(layernorm_fwd_reg_kernel<2>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, y, o16, mean, rstd, rows, eps));
+    else TBNS_CUDA(launch_pdl(layernorm_fwd_reg_kernel<4>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, y, o16, mean, rstd, rows, eps));
     TBNS_LAUNCH_CHECK();
     return TBNS_OK;
   }
-  layernorm_fwd_kernel<<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, reinterpret_cast<__nv_bfloat16*>(y16), mean, rstd, rows, C, eps);
+  TBNS_CUDA(launch_pdl(layernorm_fwd_kernel, dim3(cdiv(rows, LN_WARPS)), dim3(LN_WARPS * 32), 0, (cudaStream_t)stream, x, gamma, beta, y, reinterpret_cast<__nv_bfloat16*>(y16), mean, rstd, rows, C, eps));
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
@@ -423,17 +430,17 @@ extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long
   TBNS_REQUIRE(in && out && rows >= 0 && cols >= 0, "tbns_reduce_rows: bad args");
   if (cols == 0) return TBNS_OK;
   if (rows >= 64 && cols <= (long long)sm_count() * 32 * 8) {
-    reduce_rows_par_kernel<<<(unsigned)((cols + 31) / 32), 1024, 0, (cudaStream_t)stream>>>(in, out, rows, (int)cols, cols);
+    TBNS_CUDA(launch_pdl(reduce_rows_par_kernel, dim3((unsigned)((cols + 31) / 32)), dim3(1024), 0, (cudaStream_t)stream, in, out, rows, (int)cols, cols));
     TBNS_LAUNCH_CHECK();
     return TBNS_OK;
   }
   if (cols <= 0x7fffffffLL && (cols % 4 == 0) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && cols / 128 < 65535 * 32) {
     // 8 row-lanes x 32 float4 column-lanes per CTA, fixed summation order
-    colsum_partial_kernel<<<dim3((unsigned)((cols + 127) / 128), 1), 256, 0, (cudaStream_t)stream>>>(in, cols, out, rows, (int)cols, rows);
+    TBNS_CUDA(launch_pdl(colsum_partial_kernel, dim3(dim3((unsigned)((cols + 127) / 128), 1)), dim3(256), 0, (cudaStream_t)stream, in, cols, out, rows, (int)cols, rows));
   } else {
     int blocks = (int)((cols + 127) / 128);
     if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-    reduce_rows_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(in, out, rows, cols, cols);
+    TBNS_CUDA(launch_pdl(reduce_rows_kernel, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, in, out, rows, cols, cols));
   }
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
@@ -454,11 +461,11 @@ extern "C" int tbns_layernorm_bwd16(const void* dy16, const float* x, const floa
   const float* dy = reinterpret_cast<const float*>(dy16);
   int ctas = cdiv(rows, LN_WARPS * 2);
   if (ctas > LN_BWD_CTAS) ctas = LN_BWD_CTAS;
-  if (C == 128) layernorm_bwd_reg_kernel<1, false, true><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
-  else if (C == 256) layernorm_bwd_reg_kernel<2, false, true><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
-  else layernorm_bwd_reg_kernel<4, false, true><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
+  if (C == 128) TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<1, false, true>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr));
+  else if (C == 256) TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<2, false, true>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr));
+  else TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<4, false, true>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr));
   TBNS_LAUNCH_CHECK();
-  reduce_rows_par_kernel<<<cdiv(3 * C, 32), 1024, 0, st>>>(ws, sums, ctas, 3 * C, 3LL * C);
+  TBNS_CUDA(launch_pdl(reduce_rows_par_kernel, dim3(cdiv(3 * C, 32)), dim3(1024), 0, st, ws, sums, ctas, 3 * C, 3LL * C));
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
@@ -475,23 +482,23 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
   if (aligned && (C == 128 || C == 256 || C == 512)) {
     int ctas = cdiv(rows, LN_WARPS * 2);
     if (ctas > LN_BWD_CTAS) ctas = LN_BWD_CTAS;
-    if (C == 128) layernorm_bwd_reg_kernel<1, false><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
-    else if (C == 256) layernorm_bwd_reg_kernel<2, false><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
-    else layernorm_bwd_reg_kernel<4, false><<<ctas, LN_WARPS * 32, 0, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr);
+    if (C == 128) TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<1, false>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr));
+    else if (C == 256) TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<2, false>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr));
+    else TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<4, false>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr));
     TBNS_LAUNCH_CHECK();
     // ws rows are [dgamma | dbeta | colsum(dx)], width 3C: fixed-order reduction; a single launch when the caller's three
     // outputs are one contiguous [3][C] array
     if (dsum && dbeta == dgamma + C && dsum == dgamma + 2 * C) {
-      reduce_rows_par_kernel<<<cdiv(3 * C, 32), 1024, 0, st>>>(ws, dgamma, ctas, 3 * C, 3LL * C);
+      TBNS_CUDA(launch_pdl(reduce_rows_par_kernel, dim3(cdiv(3 * C, 32)), dim3(1024), 0, st, ws, dgamma, ctas, 3 * C, 3LL * C));
       TBNS_LAUNCH_CHECK();
       return TBNS_OK;
     }
-    reduce_rows_par_kernel<<<cdiv(C, 32), 1024, 0, st>>>(ws, dgamma, ctas, C, 3LL * C);
+    TBNS_CUDA(launch_pdl(reduce_rows_par_kernel, dim3(cdiv(C, 32)), dim3(1024), 0, st, ws, dgamma, ctas, C, 3LL * C));
     TBNS_LAUNCH_CHECK();
-    reduce_rows_par_kernel<<<cdiv(C, 32), 1024, 0, st>>>(ws + C, dbeta, ctas, C, 3LL * C);
+    TBNS_CUDA(launch_pdl(reduce_rows_par_kernel, dim3(cdiv(C, 32)), dim3(1024), 0, st, ws + C, dbeta, ctas, C, 3LL * C));
     TBNS_LAUNCH_CHECK();
     if (dsum) {
-      reduce_rows_par_kernel<<<cdiv(C, 32), 1024, 0, st>>>(ws + 2 * C, dsum, ctas, C, 3LL * C);
+      TBNS_CUDA(launch_pdl(reduce_rows_par_kernel, dim3(cdiv(C, 32)), dim3(1024), 0, st, ws + 2 * C, dsum, ctas, C, 3LL * C));
       TBNS_LAUNCH_CHECK();
     }
     return TBNS_OK;
@@ -503,11 +510,11 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
   int ctas = cdiv(rows, LN_WARPS * 4);
   if (ctas > LN_MAX_CTAS) ctas = LN_MAX_CTAS;
   if (ctas < 1) ctas = 1;
-  layernorm_bwd_kernel<<<ctas, LN_WARPS * 32, smem, st>>>(dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, C);
+  TBNS_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(ctas), dim3(LN_WARPS * 32), smem, st, dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, C));
   TBNS_LAUNCH_CHECK();
-  reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws, dgamma, ctas, C, 2LL * C);
+  TBNS_CUDA(launch_pdl(reduce_rows_kernel, dim3(cdiv(C, 128)), dim3(128), 0, st, ws, dgamma, ctas, C, 2LL * C));
   TBNS_LAUNCH_CHECK();
-  reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(ws + C, dbeta, ctas, C, 2LL * C);
+  TBNS_CUDA(launch_pdl(reduce_rows_kernel, dim3(cdiv(C, 128)), dim3(128), 0, st, ws + C, dbeta, ctas, C, 2LL * C));
   TBNS_LAUNCH_CHECK();
   if (dsum) {   // column sums of dx through the generic reduction
     float* tmp = ws;  // ws is free again: reuse it as the colsum workspace (needs COLSUM_ROWS*C <= LN_BWD_CTAS*3*C floats)
@@ -515,9 +522,9 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
     if (chunks > COLSUM_ROWS) chunks = COLSUM_ROWS;
     const int rpc = cdiv(rows, chunks);
     chunks = cdiv(rows, rpc);
-    colsum_partial_kernel<<<dim3(cdiv(C, 128), chunks), 256, 0, st>>>(dx, C, tmp, rows, C, rpc);
+    TBNS_CUDA(launch_pdl(colsum_partial_kernel, dim3(dim3(cdiv(C, 128), chunks)), dim3(256), 0, st, dx, C, tmp, rows, C, rpc));
     TBNS_LAUNCH_CHECK();
-    reduce_rows_kernel<<<cdiv(C, 128), 128, 0, st>>>(tmp, dsum, chunks, C, C);
+    TBNS_CUDA(launch_pdl(reduce_rows_kernel, dim3(cdiv(C, 128)), dim3(128), 0, st, tmp, dsum, chunks, C, C));
     TBNS_LAUNCH_CHECK();
   }
   return TBNS_OK;
@@ -526,6 +533,7 @@ extern "C" int tbns_layernorm_bwd(const float* dy, const float* x, const float* 
 // bf16 input variant: 16 column-lanes x 8 columns (one uint4) per row-lane
 __global__ void __launch_bounds__(256) colsum16_partial_kernel(const __nv_bfloat16* __restrict__ in, long long ld, float* __restrict__ ws,
                                                               int rows, int cols, int rows_per_chunk) {
+  pdl_sync();
   __shared__ float red[16][16][8];
   const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
   const int c = blockIdx.x * 128 + cl * 8;
@@ -571,7 +579,7 @@ extern "C" int tbns_colsum(const float* in, long long ld, float* out, float* ws,
   const int rows_per_chunk = cdiv(rows, chunks);
   chunks = cdiv(rows, rows_per_chunk);
   dim3 grid(cdiv(cols, 128), chunks);
-  colsum_partial_kernel<<<grid, 256, 0, st>>>(in, ld, ws, rows, cols, rows_per_chunk);
+  TBNS_CUDA(launch_pdl(colsum_partial_kernel, dim3(grid), dim3(256), 0, st, in, ld, ws, rows, cols, rows_per_chunk));
   TBNS_LAUNCH_CHECK();
   return tbns_reduce_rows(ws, out, chunks, cols, stream);
 }
@@ -585,7 +593,7 @@ extern "C" int tbns_colsum_bf16(const void* in16, long long ld, float* out, floa
   const int rows_per_chunk = cdiv(rows, chunks);
   chunks = cdiv(rows, rows_per_chunk);
   dim3 grid(cdiv(cols, 128), chunks);
-  colsum16_partial_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in16), ld, ws, rows, cols, rows_per_chunk);
+  TBNS_CUDA(launch_pdl(colsum16_partial_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(in16), ld, ws, rows, cols, rows_per_chunk));
   TBNS_LAUNCH_CHECK();
   return tbns_reduce_rows(ws, out, chunks, cols, stream);
 }
@@ -599,6 +607,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_linear1_fwd_kernel(const flo
                                                                      const float* __restrict__ b, float* __restrict__ out,
                                                                      long long ldo, float* __restrict__ mean,
                                                                      float* __restrict__ rstd, int rows, int C, float eps) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= rows) return;
@@ -653,7 +662,7 @@ extern "C" int tbns_ln_linear1_fwd_strided(const float* x, const float* gamma, c
   TBNS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
                  reinterpret_cast<uintptr_t>(w)) & 15) == 0, "tbns_ln_linear1_fwd: pointers must be 16-byte aligned");
   if (rows == 0) return TBNS_OK;
-  ln_linear1_fwd_kernel<<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, w, b, out, ldo, mean, rstd, rows, C, eps);
+  TBNS_CUDA(launch_pdl(ln_linear1_fwd_kernel, dim3(cdiv(rows, LN_WARPS)), dim3(LN_WARPS * 32), 0, (cudaStream_t)stream, x, gamma, beta, w, b, out, ldo, mean, rstd, rows, C, eps));
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
@@ -671,11 +680,11 @@ extern "C" int tbns_ln_linear1_bwd(const float* dout, const float* w, const floa
   __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(dx16);
   int ctas = cdiv(rows, LN_WARPS * 2);
   if (ctas > LN_BWD_CTAS) ctas = LN_BWD_CTAS;
-  if (C == 128) layernorm_bwd_reg_kernel<1, true><<<ctas, LN_WARPS * 32, 0, st>>>(dout, x, mean, rstd, gamma, dres, dx, o16, ws, rows, w);
-  else if (C == 256) layernorm_bwd_reg_kernel<2, true><<<ctas, LN_WARPS * 32, 0, st>>>(dout, x, mean, rstd, gamma, dres, dx, o16, ws, rows, w);
-  else layernorm_bwd_reg_kernel<4, true><<<ctas, LN_WARPS * 32, 0, st>>>(dout, x, mean, rstd, gamma, dres, dx, o16, ws, rows, w);
+  if (C == 128) TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<1, true>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dout, x, mean, rstd, gamma, dres, dx, o16, ws, rows, w));
+  else if (C == 256) TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<2, true>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dout, x, mean, rstd, gamma, dres, dx, o16, ws, rows, w));
+  else TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<4, true>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dout, x, mean, rstd, gamma, dres, dx, o16, ws, rows, w));
   TBNS_LAUNCH_CHECK();
-  reduce_rows_par_kernel<<<cdiv(3 * C, 32), 1024, 0, st>>>(ws, sums, ctas, 3 * C, 3LL * C);
+  TBNS_CUDA(launch_pdl(reduce_rows_par_kernel, dim3(cdiv(3 * C, 32)), dim3(1024), 0, st, ws, sums, ctas, 3 * C, 3LL * C));
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }

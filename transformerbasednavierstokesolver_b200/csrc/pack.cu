@@ -16,6 +16,7 @@ namespace tbns {
 __global__ void pack_inputs_kernel(const __nv_bfloat16* __restrict__ tab16, int R, const float* __restrict__ src1, long long ld1,
                                    int F1, const float* __restrict__ src2, long long ld2, int F2, __nv_bfloat16* __restrict__ out,
                                    int Kp, long long rows, int N) {
+  pdl_sync();
   const int cpr = Kp >> 3;   // 16-byte chunks per output row
   const long long total = rows * cpr;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -54,8 +55,8 @@ extern "C" int tbns_pack_inputs(const void* tab16, int R, const float* src1, lon
   const long long total = rows * (Kp / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
-  pack_inputs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(tab16), R, src1, ld1, F1,
-                                                                         src2, ld2, F2, reinterpret_cast<__nv_bfloat16*>(out16), Kp, rows, N);
+  TBNS_CUDA(launch_pdl(pack_inputs_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(tab16), R, src1, ld1, F1,
+                                                                         src2, ld2, F2, reinterpret_cast<__nv_bfloat16*>(out16), Kp, rows, N));
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }

@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(TOKEN_THREADS, 2) token_attn_bwd_kernel(const 
 
 __global__ void dtau_finish_kernel(const float* __restrict__ dtau_part, const float* __restrict__ temperature,
                                    float* __restrict__ dtemperature, int B, int H, int nchunk, int clamp) {
+  pdl_sync();
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
   float acc = 0.f;
@@ -517,6 +518,7 @@ __global__ void pack_proj_weights_kernel(const float* __restrict__ Wx, const flo
                                          const float* __restrict__ bfx, float* __restrict__ Wf, float* __restrict__ Wd,
                                          __nv_bfloat16* __restrict__ Wf16, __nv_bfloat16* __restrict__ Wd16,
                                          float* __restrict__ bcat, int I, int C, int taps) {
+  pdl_sync();
   const long long total = 2LL * I * C * taps;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     // idx enumerates the packed fprop layout (coalesced writes to Wf)
@@ -539,6 +541,7 @@ __global__ void pack_proj_weights_kernel(const float* __restrict__ Wx, const flo
 // operand layouts of a Linear weight (forward / data-gradient contraction) in ONE launch.  32 x 32 tiles through shared memory.
 __global__ void __launch_bounds__(256) cast_bf16_pair_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out,
                                                             __nv_bfloat16* __restrict__ outT, int R, int K, int Kp) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -718,7 +721,7 @@ extern "C" int tbns_pa_slice_bwd(const float* XF, const float* Ws, const float* 
 extern "C" int tbns_pa_dtau_finish(const float* dtau_part, const float* temperature, float* dtemperature, int B, int H, int nchunk,
                                    int clamp, void* stream) {
   TBNS_REQUIRE(dtau_part && temperature && dtemperature && B > 0 && H > 0 && nchunk > 0, "tbns_pa_dtau_finish: bad args");
-  dtau_finish_kernel<<<cdiv(H, 64), 64, 0, (cudaStream_t)stream>>>(dtau_part, temperature, dtemperature, B, H, nchunk, clamp);
+  TBNS_CUDA(launch_pdl(dtau_finish_kernel, dim3(cdiv(H, 64)), dim3(64), 0, (cudaStream_t)stream, dtau_part, temperature, dtemperature, B, H, nchunk, clamp));
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
@@ -730,8 +733,8 @@ extern "C" int tbns_pack_proj_weights16(const float* Wx, const float* bx, const 
   const long long total = 2LL * I * C * taps;
   int blocks = (int)((total + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  pack_proj_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Wx, bx, Wfx, bfx, Wf, Wd, reinterpret_cast<__nv_bfloat16*>(Wf16),
-                                                                     reinterpret_cast<__nv_bfloat16*>(Wd16), bcat, I, C, taps);
+  TBNS_CUDA(launch_pdl(pack_proj_weights_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, Wx, bx, Wfx, bfx, Wf, Wd, reinterpret_cast<__nv_bfloat16*>(Wf16),
+                                                                     reinterpret_cast<__nv_bfloat16*>(Wd16), bcat, I, C, taps));
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }
@@ -745,8 +748,8 @@ extern "C" int tbns_pack_proj_weights(const float* Wx, const float* bx, const fl
 extern "C" int tbns_cast_bf16_pair(const float* W, void* out16, void* outT16, int R, int K, int Kp, void* stream) {
   TBNS_REQUIRE(W && (out16 || outT16) && R > 0 && K > 0 && Kp >= K, "tbns_cast_bf16_pair: bad args");
   dim3 grid(cdiv(Kp, 32), cdiv(R, 32));
-  cast_bf16_pair_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, reinterpret_cast<__nv_bfloat16*>(out16),
-                                                                reinterpret_cast<__nv_bfloat16*>(outT16), R, K, Kp);
+  TBNS_CUDA(launch_pdl(cast_bf16_pair_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, W, reinterpret_cast<__nv_bfloat16*>(out16),
+                                                                reinterpret_cast<__nv_bfloat16*>(outT16), R, K, Kp));
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_fwd_tc_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_sync();   // barrier init / TMEM allocation overlapped the previous kernel (common.cuh: PDL)
   for (int idx = tid; idx < G * 8; idx += ST_TOK) {   // Ws -> K-major swizzled B operand
     const int g = idx >> 3, c = idx & 7;
     *reinterpret_cast<float4*>(gen + S::WS + sw128_off(g, c)) = *reinterpret_cast<const float4*>(Ws + g * ST_D + c * 4);
@@ -238,8 +239,8 @@ static int launch_slice_fwd_tc(const float* XF, const float* Ws, const float* bs
   if (rc) return rc;
   TBNS_SMEM_OPT_IN((slice_fwd_tc_kernel<G>), StFwdSmem<G>::TOTAL);
   dim3 grid(groups, H, B);
-  slice_fwd_tc_kernel<G><<<grid, ST_TOK, StFwdSmem<G>::TOTAL, st>>>(tm, Ws, bs, temperature, w16, part, N, H, cdiv(N, ST_TOK), clamp);
-  TBNS_LAUNCH_CHECK();
+  TBNS_CUDA(launch_pdl(slice_fwd_tc_kernel<G>, grid, dim3(ST_TOK), StFwdSmem<G>::TOTAL, st, tm, Ws, bs, temperature, w16, part, N, H,
+                       cdiv(N, ST_TOK), clamp));
   return TBNS_OK;
 }
 
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_sync();
   // per-(b,h) constant operands: Ws, dTt (K-major over dim_head) and their transposes (K-major over the slice index)
   const float* dTh = dTt + bh * G * ST_D;
   for (int idx = tid; idx < G * 8; idx += ST_TOK) {
@@ -543,9 +545,8 @@ static int launch_slice_bwd_tc(const float* XF, const float* Ws, const float* bs
   if (rc) return rc;
   TBNS_SMEM_OPT_IN((slice_bwd_tc_kernel<G>), StBwdSmem<G>::TOTAL);
   dim3 grid(groups, H, B);
-  slice_bwd_tc_kernel<G><<<grid, ST_TOK, StBwdSmem<G>::TOTAL, st>>>(tm, Ws, bs, temperature, dw, dTt, ds, dXF16, dWs_part, dtau_part, N, H,
-                                                                    cdiv(N, ST_TOK), clamp);
-  TBNS_LAUNCH_CHECK();
+  TBNS_CUDA(launch_pdl(slice_bwd_tc_kernel<G>, grid, dim3(ST_TOK), StBwdSmem<G>::TOTAL, st, tm, Ws, bs, temperature, dw, dTt, ds, dXF16,
+                       dWs_part, dtau_part, N, H, cdiv(N, ST_TOK), clamp));
   return TBNS_OK;
 }
 

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(TK_THREADS) token_attn_fwd_mma_kernel(
     const float* __restrict__ Wo, float* __restrict__ s_out, float* __restrict__ Tt_out, float* __restrict__ tok_out,
     float* __restrict__ q_out, float* __restrict__ k_out, float* __restrict__ v_out, float* __restrict__ A_out, float* __restrict__ O_out,
     float* __restrict__ P, __nv_bfloat16* __restrict__ P16, __nv_bfloat16* __restrict__ PT16, int H, int Cout) {
+  pdl_sync();
   using S = TkFwdSmem<G>;
   constexpr int D = TK_D, LD = TK_LD, LA = S::LA, GD = G * D, MT = G / 16;
   extern __shared__ float sm[];
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(TK_THREADS) token_attn_bwd_mma_kernel(
     const float* __restrict__ Wo, const float* __restrict__ s_in, const float* __restrict__ tok_in, const float* __restrict__ q_in,
     const float* __restrict__ k_in, const float* __restrict__ v_in, const float* __restrict__ A_in, const float* __restrict__ O_in,
     float* __restrict__ dTt, float* __restrict__ ds, float* __restrict__ dWqkv_part, float* __restrict__ dWo_part, int H, int Cout) {
+  pdl_sync();
   using S = TkBwdSmem<G>;
   constexpr int D = TK_D, LD = TK_LD, LA = S::LA, GD = G * D, MT = G / 16;
   extern __shared__ float sm[];
@@ -509,10 +511,10 @@ extern "C" int tbns_pa_token_attn_fwd(const float* part, int nchunk, const float
       __nv_bfloat16* pt16 = reinterpret_cast<__nv_bfloat16*>(PT16);
       if (G == 32) {
         TBNS_SMEM_OPT_IN((token_attn_fwd_mma_kernel<32>), 227 * 1024);
-        token_attn_fwd_mma_kernel<32><<<grid, TK_THREADS, smem, st>>>(part, nchunk, Wq, Wk, Wv, Wo, s, Tt, tok, q, k, v, A, O, P, p16, pt16, H, Cout);
+        TBNS_CUDA(launch_pdl(token_attn_fwd_mma_kernel<32>, dim3(grid), dim3(TK_THREADS), smem, st, part, nchunk, Wq, Wk, Wv, Wo, s, Tt, tok, q, k, v, A, O, P, p16, pt16, H, Cout));
       } else {
         TBNS_SMEM_OPT_IN((token_attn_fwd_mma_kernel<64>), 227 * 1024);
-        token_attn_fwd_mma_kernel<64><<<grid, TK_THREADS, smem, st>>>(part, nchunk, Wq, Wk, Wv, Wo, s, Tt, tok, q, k, v, A, O, P, p16, pt16, H, Cout);
+        TBNS_CUDA(launch_pdl(token_attn_fwd_mma_kernel<64>, dim3(grid), dim3(TK_THREADS), smem, st, part, nchunk, Wq, Wk, Wv, Wo, s, Tt, tok, q, k, v, A, O, P, p16, pt16, H, Cout));
       }
       TBNS_LAUNCH_CHECK();
       return TBNS_OK;
@@ -541,10 +543,10 @@ extern "C" int tbns_pa_token_attn_bwd(const float* dP, const float* Wq, const fl
       cudaStream_t st = (cudaStream_t)stream;
       if (G == 32) {
         TBNS_SMEM_OPT_IN((token_attn_bwd_mma_kernel<32>), 227 * 1024);
-        token_attn_bwd_mma_kernel<32><<<grid, TK_THREADS, smem, st>>>(dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part, dWo_part, H, Cout);
+        TBNS_CUDA(launch_pdl(token_attn_bwd_mma_kernel<32>, dim3(grid), dim3(TK_THREADS), smem, st, dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part, dWo_part, H, Cout));
       } else {
         TBNS_SMEM_OPT_IN((token_attn_bwd_mma_kernel<64>), 227 * 1024);
-        token_attn_bwd_mma_kernel<64><<<grid, TK_THREADS, smem, st>>>(dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part, dWo_part, H, Cout);
+        TBNS_CUDA(launch_pdl(token_attn_bwd_mma_kernel<64>, dim3(grid), dim3(TK_THREADS), smem, st, dP, Wq, Wk, Wv, Wo, s, tok, q, k, v, A, O, dTt, ds, dWqkv_part, dWo_part, H, Cout));
       }
       TBNS_LAUNCH_CHECK();
       return TBNS_OK;
