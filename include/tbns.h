@@ -198,18 +198,23 @@ int tbns_slice_groups(int B, int N, int H);  /* partials per (batch, head) writt
 int tbns_pa_slice_fwd(const float* XF, const float* Ws, const float* bs, const float* temperature, float* w, void* w16,
                       float* part, int B, int N, int H, int D, int G, int clamp, void* stream);
 
-/* Tensor-core variant of the slice stage (tcgen05.mma kind::tf32 on 128-token x one-head tiles, softmax fused between the
- * two contractions); bf16 mode, dim_head == 32 and slice_num in {32, 64} (tbns_pa_slice_tc_supported).  Same outputs as
- * tbns_pa_slice_fwd with w16 only. */
+/* Tensor-core variant of the slice stage (tcgen05.mma kind::f16 with bf16 operands on 128-token x one-head tiles, softmax
+ * fused between the two contractions); bf16 mode, dim_head == 32 and slice_num in {32, 64} (tbns_pa_slice_tc_supported).
+ * XF16: the projections [B*N, 2*H*D] in bf16 (the projection GEMM's C16 output - no fp32 copy of XF exists on this route).
+ * Same outputs as tbns_pa_slice_fwd with w16 only. */
 int tbns_pa_slice_tc_supported(int D, int G);
-int tbns_pa_slice_fwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, void* w16, float* part,
+int tbns_pa_slice_fwd_tc(const void* XF16, const float* Ws, const float* bs, const float* temperature, void* w16, float* part,
                          int B, int N, int H, int D, int G, int clamp, void* stream);
-/* backward twin: dXF16 (bf16) only; the projection-bias gradients follow from dbs and s on the host side
- * (db_x = dbs.Ws, db_fx = s.dTt), so no dbcat_part is produced. */
-/* dw16: the deslice gradient [B,N,H*G] in bf16 (written by the dw GEMM's bf16 output) */
-int tbns_pa_slice_bwd_tc(const float* XF, const float* Ws, const float* bs, const float* temperature, const void* dw16,
+/* backward twin: dXF16 (bf16) only; the projection-bias gradients follow from dbs and s (tbns_pa_proj_bias_grad), so no
+ * dbcat_part is produced.  dw16: the deslice gradient [B,N,H*G] in bf16 (written by the dw GEMM's bf16 output) */
+int tbns_pa_slice_bwd_tc(const void* XF16, const float* Ws, const float* bs, const float* temperature, const void* dw16,
                          const float* dTt, const float* ds, void* dXF16, float* dWs_part, float* dtau_part, int B, int N,
                          int H, int D, int G, int clamp, void* stream);
+/* projection-bias gradients of the tensor-core route from token-reduced quantities (fixed summation order):
+ *   db_x[h*D+d] = sum_g (sum_{b,chunk} dWs_part[b,h,chunk,g,D]) * Ws[g,d],   db_fx[h*D+d] = sum_{b,g} s[b,h,g] * dTt[b,h,g,d]
+ * (model/Physics_Attention.py:94-97: the biases of in_project_x / in_project_fx).  dWs_part is tbns_pa_slice_bwd_tc's output. */
+int tbns_pa_proj_bias_grad(const float* dWs_part, const float* Ws, const float* s, const float* dTt, float* dbx, float* dbfx,
+                           int B, int H, int D, int G, int groups, void* stream);
 
 /* Token stage (model/Physics_Attention.py:43-52 / :102-111) + fold of to_out into P:
  *   reduces `part` -> s[B,H,G], Tt[B,H,G,D]; tok = Tt/(s+1e-5); q,k,v; A = softmax(q k^T D^-1/2); O = A v;

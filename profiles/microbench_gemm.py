@@ -15,6 +15,7 @@ x16 = torch.randn(M, C, generator=g).to(dev).bfloat16()
 Wf16 = (torch.randn(I2, 9 * C, generator=g) / 48).to(dev).bfloat16()
 bias = torch.randn(I2, generator=g).to(dev)
 XF = torch.empty(M, I2, device=dev)
+XF16 = torch.empty(M, I2, device=dev, dtype=torch.bfloat16)
 W1 = (torch.randn(C, C, generator=g) / 16).to(dev).bfloat16()
 b1 = torch.randn(C, generator=g).to(dev)
 pre16 = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
@@ -32,6 +33,7 @@ flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
 cases = {
     "conv_fprop 81920x2304x512": (lambda: ops.gemm_tc(x16, Wf16, XF, bias, B, Hg, Wg, C, I2, 9, 0), 2.0 * M * 9 * C * I2),
+    "conv_fprop16 81920x2304x512 bf16 out": (lambda: ops.gemm_tc(x16, Wf16, None, bias, B, Hg, Wg, C, I2, 9, 0, C16=XF16), 2.0 * M * 9 * C * I2),
     "conv_dgrad 81920x4608x256": (lambda: ops.gemm_tc(dXF16, Wd16, out, None, B, Hg, Wg, I2, C, 9, 1), 2.0 * M * 9 * C * I2),
     "fc1 81920x256x256 +bias+gelu+pre16+bf16": (lambda: ops.gemm_tc(x16, W1, None, b1, 1, 1, M, C, C, act=1, aux_out=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
     "dpre 81920x256x256 gelu'(pre16)+bf16": (lambda: ops.gemm_tc(x16, W1, None, None, 1, 1, M, C, C, act=2, aux_in=pre16, aux_bf16=1, C16=hid16), 2.0 * M * C * C),
@@ -71,6 +73,7 @@ lib = _lib.load()
 H, D, G = 8, 32, 32
 N = Hg * Wg
 XFs = torch.randn(M, I2, generator=g).to(dev)
+XFs16 = XFs.bfloat16()
 Ws = (torch.randn(G, D, generator=g) * 0.3).to(dev); bs = torch.randn(G, generator=g).to(dev); tau = torch.full((H,), 0.5, device=dev)
 groups = lib.tbns_slice_groups(B, N, H)
 w16 = torch.empty(B, N, H * G, device=dev, dtype=torch.bfloat16)
@@ -83,9 +86,9 @@ st = torch.cuda.current_stream().cuda_stream
 P = lambda t: t.data_ptr()
 cases2 = {
     "slice_fwd SIMT": lambda: lib.tbns_pa_slice_fwd(P(XFs), P(Ws), P(bs), P(tau), None, P(w16), P(part), B, N, H, D, G, 1, st),
-    "slice_fwd tcgen05": lambda: lib.tbns_pa_slice_fwd_tc(P(XFs), P(Ws), P(bs), P(tau), P(w16), P(part), B, N, H, D, G, 1, st),
+    "slice_fwd tcgen05": lambda: lib.tbns_pa_slice_fwd_tc(P(XFs16), P(Ws), P(bs), P(tau), P(w16), P(part), B, N, H, D, G, 1, st),
     "slice_bwd SIMT": lambda: lib.tbns_pa_slice_bwd(P(XFs), P(Ws), P(bs), P(tau), P(dw), P(dTt), P(ds), None, P(dXF16o), P(dWs_p), P(dtau_p), P(dbc), B, N, H, D, G, 1, st),
-    "slice_bwd tcgen05": lambda: lib.tbns_pa_slice_bwd_tc(P(XFs), P(Ws), P(bs), P(tau), P(dw16), P(dTt), P(ds), P(dXF16o), P(dWs_p), P(dtau_p), B, N, H, D, G, 1, st),
+    "slice_bwd tcgen05": lambda: lib.tbns_pa_slice_bwd_tc(P(XFs16), P(Ws), P(bs), P(tau), P(dw16), P(dTt), P(ds), P(dXF16o), P(dWs_p), P(dtau_p), B, N, H, D, G, 1, st),
 }
 for name, fn in cases2.items():
     for _ in range(3):

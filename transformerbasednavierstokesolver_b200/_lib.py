@@ -100,6 +100,7 @@ _SIGS = {
     "tbns_pa_slice_tc_supported": (_i, [_i, _i]),
     "tbns_pa_slice_fwd_tc": (_i, [_fp] * 6 + [_i] * 6 + [_fp]),
     "tbns_pa_slice_bwd_tc": (_i, [_fp] * 10 + [_i] * 6 + [_fp]),
+    "tbns_pa_proj_bias_grad": (_i, [_fp] * 6 + [_i] * 5 + [_fp]),
     "tbns_pa_token_attn_fwd": (_i, [_fp, _i] + [_fp] * 15 + [_i] * 5 + [_fp]),
     "tbns_pa_token_attn_bwd": (_i, [_fp] * 16 + [_i] * 5 + [_fp]),
     "tbns_pa_slice_bwd": (_i, [_fp] * 12 + [_i] * 6 + [_fp]),

@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                const cuuint32_t* box) {
+                const cuuint32_t* box, CUtensorMapSwizzle swz) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   TmapKey k;
@@ -24,7 +24,7 @@ int encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, int ran
   int dev = 0;
   cudaGetDevice(&dev);
   k.v[0] = reinterpret_cast<uint64_t>(ptr);
-  k.v[1] = ((uint64_t)dt << 32) | ((uint64_t)rank << 8) | (uint64_t)(dev & 0xff);
+  k.v[1] = ((uint64_t)dt << 32) | ((uint64_t)swz << 16) | ((uint64_t)rank << 8) | (uint64_t)(dev & 0xff);
   for (int i = 0; i < rank; ++i) {
     k.v[2 + i] = dims[i];
     k.v[10 + i] = box[i];
@@ -38,7 +38,7 @@ int encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, int ran
       return TBNS_OK;
     }
   }
-  const int rc = encode_tmap_uncached(m, dt, ptr, rank, dims, strides_bytes, box);
+  const int rc = encode_tmap_uncached(m, dt, ptr, rank, dims, strides_bytes, box, swz);
   if (rc == TBNS_OK) {
     std::lock_guard<std::mutex> lock(mu);
     if (cache.size() > 8192) cache.clear();

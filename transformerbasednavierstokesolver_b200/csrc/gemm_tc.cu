@@ -1042,7 +1042,7 @@ static int launch_tcp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPa
 #define TBNS_EPI_CASE(code) case (code): return launch_tcp_epi<BN, STAGES, (code)>(tmA, tmB, p, m_tiles, st);
       TBNS_EPI_CASE(EPI_C)                                                          // dgrad, dx2
       TBNS_EPI_CASE(EPI_BIAS | EPI_C)                                               // projection fprop
-      TBNS_EPI_CASE(EPI_BIAS | EPI_ROUND | EPI_C)                                   // projection fprop feeding the tf32 slice stage
+      TBNS_EPI_CASE(EPI_BIAS | EPI_C16)                                             // projection fprop feeding the bf16 slice stage
       TBNS_EPI_CASE(EPI_BIAS | EPI_RES | EPI_C)                                     // deslice (+) to_out + residual, fc2 + residual
       TBNS_EPI_CASE(EPI_BIAS | EPI_RES | EPI_C | EPI_LN)                            // ... + the next stage's LayerNorm
       TBNS_EPI_CASE(EPI_BIAS | EPI_C | EPI_LN)                                      // preprocess fc2 + the first block's ln_1
@@ -1080,7 +1080,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPa
     case (EPI_C): return launch_tc2_epi<EPI_C>(tmA, tmB, p, m_tiles, st);
     case (EPI_C16): return launch_tc2_epi<EPI_C16>(tmA, tmB, p, m_tiles, st);
     case (EPI_BIAS | EPI_C): return launch_tc2_epi<EPI_BIAS | EPI_C>(tmA, tmB, p, m_tiles, st);
-    case (EPI_BIAS | EPI_ROUND | EPI_C): return launch_tc2_epi<EPI_BIAS | EPI_ROUND | EPI_C>(tmA, tmB, p, m_tiles, st);
+    case (EPI_BIAS | EPI_C16): return launch_tc2_epi<EPI_BIAS | EPI_C16>(tmA, tmB, p, m_tiles, st);
     default: break;
   }
   *handled = false;

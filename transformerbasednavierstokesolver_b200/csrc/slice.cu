@@ -512,6 +512,49 @@ __global__ void dtau_finish_kernel(const float* __restrict__ dtau_part, const fl
   dtemperature[h] = acc;
 }
 
+// Projection-bias gradients of the tensor-core route (model/Physics_Attention.py:94-97, biases of in_project_x / in_project_fx)
+// from token-reduced quantities: db_x = (sum_t dL).Ws with sum_t dL = the bias column of the slice backward's partials,
+// db_fx = (sum_t w).dTt.  One CTA per head, fixed summation order (replicas stay bitwise identical).
+// block 256; dynamic shared memory: (G + 8 * D) floats
+__global__ void proj_bias_grad_kernel(const float* __restrict__ dWs_part, const float* __restrict__ Ws, const float* __restrict__ s,
+                                      const float* __restrict__ dTt, float* __restrict__ dbx, float* __restrict__ dbfx, int B, int H,
+                                      int D, int G, int groups) {
+  pdl_sync();
+  extern __shared__ float pbg_sm[];
+  float* dbs = pbg_sm;        // [G]  sum over (batch, chunk) of the logit-bias partials
+  float* red = pbg_sm + G;    // [8][D]
+  const int h = blockIdx.x, tid = threadIdx.x;
+  for (int g = tid; g < G; g += blockDim.x) {
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float* p = dWs_part + (((long long)b * H + h) * groups) * G * (D + 1) + g * (D + 1) + D;
+      for (int c = 0; c < groups; ++c) a += p[(long long)c * G * (D + 1)];
+    }
+    dbs[g] = a;
+  }
+  // db_fx: 8 row groups x D columns, each summing its share of the (b, g) pairs in order
+  const int d = tid % D, part = tid / D, nparts = blockDim.x / D;
+  float acc = 0.f;
+  if (part < 8 && part < nparts) {
+    const int P = nparts < 8 ? nparts : 8;
+    for (int bg = part; bg < B * G; bg += P) {
+      const int b = bg / G, g = bg - b * G;
+      acc = fmaf(s[((long long)b * H + h) * G + g], dTt[(((long long)b * H + h) * G + g) * D + d], acc);
+    }
+    red[part * D + d] = acc;
+  }
+  __syncthreads();
+  if (tid < D) {
+    const int P = nparts < 8 ? nparts : 8;
+    float f = 0.f;
+    for (int q = 0; q < P; ++q) f += red[q * D + tid];
+    dbfx[h * D + tid] = f;
+    float x = 0.f;
+    for (int g = 0; g < G; ++g) x = fmaf(dbs[g], Ws[g * D + tid], x);
+    dbx[h * D + tid] = x;
+  }
+}
+
 // Wf[n][tap*C+ci], Wd[ci][tap*2I+n], bcat[n]  from nn.Conv2d/Linear weights [I][C][taps]; fp32 and/or bf16 (K-major tensor-core
 // operand) outputs: the bf16 copies are written directly, so a weight refresh after an optimizer step is one launch per layer
 __global__ void pack_proj_weights_kernel(const float* __restrict__ Wx, const float* __restrict__ bx, const float* __restrict__ Wfx,
@@ -723,6 +766,15 @@ extern "C" int tbns_pa_dtau_finish(const float* dtau_part, const float* temperat
   TBNS_REQUIRE(dtau_part && temperature && dtemperature && B > 0 && H > 0 && nchunk > 0, "tbns_pa_dtau_finish: bad args");
   TBNS_CUDA(launch_pdl(dtau_finish_kernel, dim3(cdiv(H, 64)), dim3(64), 0, (cudaStream_t)stream, dtau_part, temperature, dtemperature, B, H, nchunk, clamp));
   TBNS_LAUNCH_CHECK();
+  return TBNS_OK;
+}
+
+extern "C" int tbns_pa_proj_bias_grad(const float* dWs_part, const float* Ws, const float* s, const float* dTt, float* dbx, float* dbfx,
+                                      int B, int H, int D, int G, int groups, void* stream) {
+  TBNS_REQUIRE(dWs_part && Ws && s && dTt && dbx && dbfx, "tbns_pa_proj_bias_grad: null pointer");
+  TBNS_REQUIRE(B > 0 && H > 0 && D > 0 && D <= 256 && G > 0 && groups > 0, "tbns_pa_proj_bias_grad: bad dims");
+  TBNS_CUDA(launch_pdl(proj_bias_grad_kernel, dim3(H), dim3(256), (size_t)(G + 8 * D) * sizeof(float), (cudaStream_t)stream, dWs_part, Ws,
+                       s, dTt, dbx, dbfx, B, H, D, G, groups));
   return TBNS_OK;
 }
 

@@ -189,6 +189,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 // byte offset of (row, 16-byte chunk) inside a 128B-swizzled tile whose rows are 128 bytes (tile base 1024-byte aligned)
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk16) { return (uint32_t)row * 128u + ((uint32_t)(chunk16 ^ (row & 7)) << 4); }
 
+// K-major, 64B-swizzled operand tile: rows of 64 bytes (32 bf16), 8-row atoms of 512 bytes (SBO); the tile a TMA box of 32 bf16
+// with CU_TENSOR_MAP_SWIZZLE_64B lands as.  (cute UMMA::LayoutType::SWIZZLE_64B = 4)
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// byte offset of (row, 16-byte chunk) inside a 64B-swizzled tile whose rows are 64 bytes: address bits [4,6) ^= bits [7,9)
+__device__ __forceinline__ uint32_t sw64_off(int row, int chunk16) { return (uint32_t)row * 64u + ((uint32_t)(chunk16 ^ ((row >> 1) & 3)) << 4); }
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -221,12 +235,13 @@ struct TmapKeyHash {
   }
 };
 int encode_tmap_uncached(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, int rank, const cuuint64_t* dims,
-                         const cuuint64_t* strides_bytes, const cuuint32_t* box);
+                         const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swz);
 int encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, int rank, const cuuint64_t* dims,
-                const cuuint64_t* strides_bytes, const cuuint32_t* box);   // cached; defined in api.cu
+                const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);   // cached; defined in api.cu
 
 inline int encode_tmap_uncached(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, int rank, const cuuint64_t* dims,
-                                const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                                const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -234,7 +249,7 @@ inline int encode_tmap_uncached(CUtensorMap* m, CUtensorMapDataType dt, const vo
   }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);

@@ -581,13 +581,17 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
     Hg, Wg = grid if structured else (1, N)
     tc = _pa_tc_ok(precision, C_, I2, HG, Cout, taps, Wf16 is not None)
     # (1a) projections: XF = [x_mid | fx_mid]   Physics_Attention.py:94-97 / :36-39
-    XF = torch.empty(B * N, I2, **f32)
+    slice_tc = tc and bool(lib.tbns_pa_slice_tc_supported(D, G))
+    # the tensor-core slice stage consumes the projections in bf16: the GEMM epilogue writes nothing else (no fp32 XF)
+    XF = torch.empty(B * N, I2, **(bf if slice_tc else f32))
     if tc:
         # tensor-core path: bf16 operands through TMA, tcgen05.mma, fp32 accumulate in TMEM
         if x16 is None:
             x16 = cast_bf16(x)
-        slice_tc = bool(lib.tbns_pa_slice_tc_supported(D, G))
-        gemm_tc(x16, Wf16, XF, bcat, B, Hg, Wg, C_, I2, taps, 0, tag="proj_fprop", round_tf32=int(slice_tc))
+        if slice_tc:
+            gemm_tc(x16, Wf16, None, bcat, B, Hg, Wg, C_, I2, taps, 0, tag="proj_fprop", C16=XF)
+        else:
+            gemm_tc(x16, Wf16, XF, bcat, B, Hg, Wg, C_, I2, taps, 0, tag="proj_fprop")
     elif structured:
         gemm(M=B * N, N=I2, K=9 * C_, A=x, lda=C_, a_kind=0, B=Wf, ldb=9 * C_, b_kind=0, C=XF, ldc=I2, conv_mode=1, Hg=Hg,
              Wg=Wg, Cin=C_, bias=bcat, precision=precision, tag="proj_fprop")
@@ -599,7 +603,7 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
     w = None if tc else torch.empty(B, N, HG, **f32)
     w16 = torch.empty(B, N, HG, **bf) if tc else None     # tensor-core mode keeps only the bf16 copy
     part = torch.empty(B * H * groups * G * (D + 1), **f32)
-    if tc and slice_tc:
+    if slice_tc:
         with _Timed("slice_fwd"):
             check(lib.tbns_pa_slice_fwd_tc(_p(XF), _p(Ws), _p(bs), _p(temperature), _p(w16), _p(part), B, N, H, D, G, int(structured), st),
                   "tbns_pa_slice_fwd_tc")
@@ -699,9 +703,10 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
                                            _p(dtau_part), B, N, H, D, G, int(structured), st), "tbns_pa_slice_bwd_tc")
         with _OnSide():
             # projection-bias gradients from token-reduced quantities: db_x = (sum_t dL).Ws, db_fx = (sum_t w).dTt
-            dbs_bh = dWs_part.view(B, H, groups, G, D + 1)[..., D].sum(2)
-            dbx = (dbs_bh.sum(0) @ Ws).reshape(I)
-            dbfx = torch.einsum("bhg,bhgd->hd", s, dTt).reshape(I)
+            dbx, dbfx = torch.empty(I, **f32), torch.empty(I, **f32)
+            check(lib.tbns_pa_proj_bias_grad(_p(dWs_part), _p(Ws), _p(s), _p(dTt), _p(dbx), _p(dbfx), B, H, D, G, groups, _stream()),
+                  "tbns_pa_proj_bias_grad")
+            _count(1)
     else:
         dbcat_part = torch.empty(B * groups, H * 2 * D, **f32)
         with _Timed("slice_bwd"):
