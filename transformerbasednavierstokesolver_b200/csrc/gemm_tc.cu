@@ -1170,7 +1170,10 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
   // (Linear / deslice / MLP: the fused epilogue outweighs the main loop) may run 128-wide tiles (TBNS_TC_SHORTK_BN128=1).
   static const bool bn128 = [] { const char* e = getenv("TBNS_TC_SHORTK_BN128"); return e && atoi(e) != 0; }();
   const bool short_k = K / TC_BK <= 8 && N % 128 == 0;
-  const int BN = (N % 256 == 0 && !(short_k && bn128)) ? 256 : (N % 128 == 0 ? 128 : 64);
+  // small M (one literal / unrolled model call): 256-wide tiles would leave SMs idle, 128-wide ones double the CTA count
+  // (not with the fused LayerNorm, whose tile must hold whole rows)
+  const bool few_tiles = short_k && !d.ln_gamma && m_tiles * (N / 256) < sm_count();
+  const int BN = (N % 256 == 0 && !(short_k && (bn128 || few_tiles))) ? 256 : (N % 128 == 0 ? 128 : 64);
   rc = encode_w(&tmB, BN);
   if (rc) return rc;
   if (BN == 256) return launch_tcp<256, 4>(tmA, tmB, p, (int)m_tiles, st);

@@ -515,43 +515,59 @@ __global__ void dtau_finish_kernel(const float* __restrict__ dtau_part, const fl
 // Projection-bias gradients of the tensor-core route (model/Physics_Attention.py:94-97, biases of in_project_x / in_project_fx)
 // from token-reduced quantities: db_x = (sum_t dL).Ws with sum_t dL = the bias column of the slice backward's partials,
 // db_fx = (sum_t w).dTt.  One CTA per head, fixed summation order (replicas stay bitwise identical).
-// block 256; dynamic shared memory: (G + 8 * D) floats
+// block 256; dynamic shared memory: (G + 8 * max(D, G)) floats
 __global__ void proj_bias_grad_kernel(const float* __restrict__ dWs_part, const float* __restrict__ Ws, const float* __restrict__ s,
                                       const float* __restrict__ dTt, float* __restrict__ dbx, float* __restrict__ dbfx, int B, int H,
                                       int D, int G, int groups) {
   pdl_sync();
   extern __shared__ float pbg_sm[];
-  float* dbs = pbg_sm;        // [G]  sum over (batch, chunk) of the logit-bias partials
-  float* red = pbg_sm + G;    // [8][D]
+  float* dbs = pbg_sm;              // [G]  sum over (batch, chunk) of the logit-bias partials
+  float* red = pbg_sm + G;          // [8][max(D, G)]
   const int h = blockIdx.x, tid = threadIdx.x;
-  for (int g = tid; g < G; g += blockDim.x) {
-    float a = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float* p = dWs_part + (((long long)b * H + h) * groups) * G * (D + 1) + g * (D + 1) + D;
-      for (int c = 0; c < groups; ++c) a += p[(long long)c * G * (D + 1)];
+  const int W = D > G ? D : G;
+  // (1) dbs[g]: the B*groups partials are split over up to 8 thread groups, then combined in a fixed order
+  {
+    const int g = tid % G, part = tid / G, P = min(8, (int)blockDim.x / G);
+    if (part < P) {
+      float a = 0.f;
+      const int n = B * groups;
+#pragma unroll 4
+      for (int i = part; i < n; i += P) {
+        const int b = i / groups, c = i - b * groups;
+        a += dWs_part[((((long long)b * H + h) * groups + c) * G + g) * (D + 1) + D];
+      }
+      red[part * W + g] = a;
     }
-    dbs[g] = a;
-  }
-  // db_fx: 8 row groups x D columns, each summing its share of the (b, g) pairs in order
-  const int d = tid % D, part = tid / D, nparts = blockDim.x / D;
-  float acc = 0.f;
-  if (part < 8 && part < nparts) {
-    const int P = nparts < 8 ? nparts : 8;
-    for (int bg = part; bg < B * G; bg += P) {
-      const int b = bg / G, g = bg - b * G;
-      acc = fmaf(s[((long long)b * H + h) * G + g], dTt[(((long long)b * H + h) * G + g) * D + d], acc);
+    __syncthreads();
+    if (tid < G) {
+      float a = 0.f;
+      for (int q = 0; q < P; ++q) a += red[q * W + tid];
+      dbs[tid] = a;
     }
-    red[part * D + d] = acc;
+    __syncthreads();
   }
-  __syncthreads();
-  if (tid < D) {
-    const int P = nparts < 8 ? nparts : 8;
-    float f = 0.f;
-    for (int q = 0; q < P; ++q) f += red[q * D + tid];
-    dbfx[h * D + tid] = f;
-    float x = 0.f;
-    for (int g = 0; g < G; ++g) x = fmaf(dbs[g], Ws[g * D + tid], x);
-    dbx[h * D + tid] = x;
+  // (2) db_fx[d] = sum_{b,g} s[b,h,g] dTt[b,h,g,d], same split; db_x[d] = sum_g dbs[g] Ws[g,d]
+  {
+    const int d = tid % D, part = tid / D, P = min(8, (int)blockDim.x / D);
+    if (part < P) {
+      float acc = 0.f;
+      const int n = B * G;
+#pragma unroll 4
+      for (int bg = part; bg < n; bg += P) {
+        const int b = bg / G, g = bg - b * G;
+        acc = fmaf(s[((long long)b * H + h) * G + g], dTt[(((long long)b * H + h) * G + g) * D + d], acc);
+      }
+      red[part * W + d] = acc;
+    }
+    __syncthreads();
+    if (tid < D) {
+      float f = 0.f;
+      for (int q = 0; q < P; ++q) f += red[q * W + tid];
+      dbfx[h * D + tid] = f;
+      float x = 0.f;
+      for (int g = 0; g < G; ++g) x = fmaf(dbs[g], Ws[g * D + tid], x);
+      dbx[h * D + tid] = x;
+    }
   }
 }
 
@@ -641,6 +657,8 @@ extern "C" int tbns_slice_groups(int B, int N, int H) {
   // of chunk-times on the critical path, rounds(B*H*groups over the resident-CTA slots) x chunks per CTA, for the backward
   // kernel (2 CTAs / SM, weighted double) and the forward kernel (4 CTAs / SM); ties go to fewer partials.
   const int nchunk = cdiv(N, TOK);
+  static const int forced = [] { const char* e = getenv("TBNS_SLICE_GROUPS"); return e ? atoi(e) : 0; }();   // tuning knob
+  if (forced > 0) return forced < nchunk ? forced : nchunk;
   const long long bh = (long long)(B > 0 ? B : 1) * (H > 0 ? H : 1);
   long long best_cost = -1;
   int best = 1;
@@ -772,8 +790,8 @@ extern "C" int tbns_pa_dtau_finish(const float* dtau_part, const float* temperat
 extern "C" int tbns_pa_proj_bias_grad(const float* dWs_part, const float* Ws, const float* s, const float* dTt, float* dbx, float* dbfx,
                                       int B, int H, int D, int G, int groups, void* stream) {
   TBNS_REQUIRE(dWs_part && Ws && s && dTt && dbx && dbfx, "tbns_pa_proj_bias_grad: null pointer");
-  TBNS_REQUIRE(B > 0 && H > 0 && D > 0 && D <= 256 && G > 0 && groups > 0, "tbns_pa_proj_bias_grad: bad dims");
-  TBNS_CUDA(launch_pdl(proj_bias_grad_kernel, dim3(H), dim3(256), (size_t)(G + 8 * D) * sizeof(float), (cudaStream_t)stream, dWs_part, Ws,
+  TBNS_REQUIRE(B > 0 && H > 0 && D > 0 && D <= 256 && G > 0 && G <= 256 && groups > 0, "tbns_pa_proj_bias_grad: bad dims");
+  TBNS_CUDA(launch_pdl(proj_bias_grad_kernel, dim3(H), dim3(256), (size_t)(G + 8 * (D > G ? D : G)) * sizeof(float), (cudaStream_t)stream, dWs_part, Ws,
                        s, dTt, dbx, dbfx, B, H, D, G, groups));
   return TBNS_OK;
 }

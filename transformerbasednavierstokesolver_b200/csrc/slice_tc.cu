@@ -100,7 +100,7 @@ struct StFwdSmem {
 
 // grid (groups, H, B), block 128
 template <int G>
-__global__ void __launch_bounds__(ST_TOK) slice_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmXF, const float* __restrict__ Ws,
+__global__ void __launch_bounds__(ST_TOK, (G == 32 ? 8 : 3)) slice_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmXF, const float* __restrict__ Ws,
                                                               const float* __restrict__ bs, const float* __restrict__ temperature,
                                                               __nv_bfloat16* __restrict__ w16, float* __restrict__ part, int N, int H,
                                                               int nchunk, int clamp) {
@@ -295,7 +295,7 @@ struct StBwdSmem {
 
 // grid (groups, H, B), block 128
 template <int G>
-__global__ void __launch_bounds__(ST_TOK) slice_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmXF, const float* __restrict__ Ws,
+__global__ void __launch_bounds__(ST_TOK, (G == 32 ? 4 : 1)) slice_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmXF, const float* __restrict__ Ws,
                                                               const float* __restrict__ bs, const float* __restrict__ temperature,
                                                               const __nv_bfloat16* __restrict__ dw, const float* __restrict__ dTt,
                                                               const float* __restrict__ ds, __nv_bfloat16* __restrict__ dXF16,
