@@ -11,8 +11,8 @@ import it; the product package never does (it raises when the CUDA library is mi
 
 Parity pin: the reference ships no tests / golden vectors.  The pins are
 (1) `tests/golden/*.pt`, produced by `oracle/make_golden.py` from the *live* reference modules
-imported from /root/reference in the build container, and (2) `tests/test_oracle_vs_reference.py`,
-which re-imports the reference whenever /root/reference is mounted.
+imported from /root/reference in the build container, and (2) the live-reference cases of `tests/test_oracle.py`,
+which re-import the reference whenever /root/reference (or the byte-compiled `oracle/_ref`) is present.
 """
 from __future__ import annotations
 

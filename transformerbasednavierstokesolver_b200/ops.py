@@ -666,7 +666,7 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
     dP = torch.empty(B, HG, Cout, **f32)
     slice_tc = tc and bool(lib.tbns_pa_slice_tc_supported(D, G))
     dw = None if slice_tc else torch.empty(B, N, HG, **f32)
-    dw16 = torch.empty(B, N, HG, device=dev, dtype=torch.bfloat16) if slice_tc else None   # the tf32 slice kernel reads bf16
+    dw16 = torch.empty(B, N, HG, device=dev, dtype=torch.bfloat16) if slice_tc else None   # the tensor-core slice kernel reads bf16
     if tc:
         if dout16 is None:
             dout16 = cast_bf16(dout)
