@@ -179,22 +179,60 @@ static int epi_code(const TcParams& p) {
          (p.aux_bf16 ? EPI_AUX16 : 0) | (gelu && p.aux_out ? EPI_AUXOUT : 0) | (p.ln_gamma ? EPI_LN : 0);
 }
 
+// The fused epilogue works on HALF fragments (one tcgen05.ld 16x256b.x4 = 16 TMEM lanes x 32 columns): v[16] holds tile rows
+// (t/4 + 8k) for the half's two k values, grow2[kk] = global row of tile row k0 + kk or -1, n = first of the 32 columns.
+// tc_epi_load_half issues the global loads the half needs (residual, or the GELU' stream of dpre) into `ld`; the persistent
+// kernel calls it one half AHEAD of tc_epi_half, so the loads of half h+1 are in flight while half h is converted and stored
+// (the short-K contractions were bound by exactly this latency: ncu long_scoreboard on the first use of the residual).
 template <int EPI>
-__device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][16], const long long (&grow)[4], int n, int t,
-                                             float* st1 = nullptr, float* st2 = nullptr) {
+__device__ __forceinline__ constexpr int tc_epi_act(int runtime_act) {
+  return EPI < 0 ? runtime_act : ((EPI & EPI_GELU) ? ((EPI & EPI_DERIV) ? 3 : 1) : (EPI & EPI_DGELU) ? ((EPI & EPI_DERIV) ? 4 : 2) : 0);
+}
+template <int EPI>
+__device__ __forceinline__ bool tc_epi_has_loads(const TcParams& pp) {
+  const int act = tc_epi_act<EPI>(pp.act);
+  return act == 2 || act == 4 || (EPI < 0 ? pp.residual != nullptr : (EPI & EPI_RES) != 0);
+}
+
+template <int EPI>
+__device__ __forceinline__ void tc_epi_load_half(const TcParams& pp, const int* grow2, int n, int t, float2 (&ld)[2][4]) {
+  const int act = tc_epi_act<EPI>(pp.act);
+  const bool mulaux = act == 2 || act == 4;   // multiply by GELU'(aux_in) / by aux_in itself
+  if (!tc_epi_has_loads<EPI>(pp)) return;
+  const float* src = mulaux ? pp.aux_in : pp.residual;
+  const long long lds = mulaux ? pp.ldaux : pp.ldr;
+  const bool h16 = mulaux && (EPI < 0 ? pp.aux_bf16 != 0 : (EPI & EPI_AUX16) != 0);
+  const int cb = n + 2 * (t & 3);
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (grow2[kk] < 0) {
+        ld[kk][j] = make_float2(0.f, 0.f);
+      } else if (h16) {
+        ld[kk][j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(src) + (long long)grow2[kk] * lds + cb + 8 * j));
+      } else {
+        ld[kk][j] = *reinterpret_cast<const float2*>(src + (long long)grow2[kk] * lds + cb + 8 * j);
+      }
+    }
+}
+
+// EPI < 0: every option is a runtime test on TcParams.  EPI >= 0: a bit set of EPI_* flags fixed at compile time, so the
+// short-K contractions (whose time is all epilogue) run straight-line code for exactly the options they use.
+template <int EPI>
+__device__ __forceinline__ void tc_epi_half(const TcParams& pp, float (&v)[16], const int* grow2, int n, int t,
+                                            const float2 (&ld)[2][4], float* st1 = nullptr, float* st2 = nullptr) {
   // compile-time view of the options (constant-folded when EPI >= 0)
   struct {
-    const float* bias; int act; float* aux_out; const float* aux_in; long long ldaux; const float* residual; long long ldr;
+    const float* bias; int act; float* aux_out; long long ldaux; const float* residual;
     float* C; long long ldc; __nv_bfloat16* C16; long long ldc16; int round_tf32; int aux_bf16;
   } p;
   constexpr bool GEN = EPI < 0;
   p.bias = (GEN || (EPI & EPI_BIAS)) ? pp.bias : nullptr;
-  p.act = GEN ? pp.act : ((EPI & EPI_GELU) ? ((EPI & EPI_DERIV) ? 3 : 1) : (EPI & EPI_DGELU) ? ((EPI & EPI_DERIV) ? 4 : 2) : 0);
+  p.act = tc_epi_act<EPI>(pp.act);
   p.aux_out = (GEN || (EPI & EPI_AUXOUT)) ? pp.aux_out : nullptr;
-  p.aux_in = pp.aux_in;
   p.ldaux = pp.ldaux;
   p.residual = (GEN || (EPI & EPI_RES)) ? pp.residual : nullptr;
-  p.ldr = pp.ldr;
   p.C = (GEN || (EPI & EPI_C)) ? pp.C : nullptr;
   p.ldc = pp.ldc;
   p.C16 = (GEN || (EPI & EPI_C16)) ? pp.C16 : nullptr;
@@ -204,38 +242,19 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
   constexpr bool K_BIAS = !GEN && (EPI & EPI_BIAS), K_RES = !GEN && (EPI & EPI_RES), K_C = !GEN && (EPI & EPI_C),
                  K_C16 = !GEN && (EPI & EPI_C16), K_AUXOUT = !GEN && (EPI & EPI_AUXOUT);
   const int cb = n + 2 * (t & 3);
-  float2 ld[4][4];   // [row k][column group j]
-  const bool mulaux = p.act == 2 || p.act == 4;   // multiply by GELU'(aux_in) / by aux_in itself
-  const float* src = mulaux ? p.aux_in : p.residual;
-  const long long lds = mulaux ? p.ldaux : p.ldr;
-  if (K_RES || mulaux || (GEN && src)) {
-    const bool h16 = mulaux && p.aux_bf16;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (grow[k] < 0) {
-          ld[k][j] = make_float2(0.f, 0.f);
-        } else if (h16) {
-          ld[k][j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(src) + grow[k] * lds + cb + 8 * j));
-        } else {
-          ld[k][j] = *reinterpret_cast<const float2*>(src + grow[k] * lds + cb + 8 * j);
-        }
-      }
-  }
   float2 bias[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     bias[j] = (K_BIAS || (GEN && p.bias)) ? *reinterpret_cast<const float2*>(p.bias + cb + 8 * j) : make_float2(0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const long long gr = grow[k];
+  for (int kk = 0; kk < 2; ++kk) {
+    const long long gr = grow2[kk];   // 64-bit from here on: gr * ld overflows 32 bits
     const bool ok = gr >= 0;   // rows past the end of the tensor: no stores, but every lane stays in the warp shuffles below
     uint32_t mine[2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = cb + 8 * j;
-      float x0 = v[k >> 1][4 * j + 2 * (k & 1)] + bias[j].x, x1 = v[k >> 1][4 * j + 2 * (k & 1) + 1] + bias[j].y;
+      float x0 = v[4 * j + 2 * kk] + bias[j].x, x1 = v[4 * j + 2 * kk + 1] + bias[j].y;
       if (p.act == 1 || p.act == 3) {
         float c0, d0, c1, d1;
         gelu_parts(x0, c0, d0);
@@ -249,14 +268,14 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
         x0 *= c0;
         x1 *= c1;
       } else if (p.act == 2) {
-        x0 *= gelu_grad_fast(ld[k][j].x);
-        x1 *= gelu_grad_fast(ld[k][j].y);
+        x0 *= gelu_grad_fast(ld[kk][j].x);
+        x1 *= gelu_grad_fast(ld[kk][j].y);
       } else if (p.act == 4) {
-        x0 *= ld[k][j].x;
-        x1 *= ld[k][j].y;
+        x0 *= ld[kk][j].x;
+        x1 *= ld[kk][j].y;
       } else if (K_RES || (GEN && p.residual)) {
-        x0 += ld[k][j].x;
-        x1 += ld[k][j].y;
+        x0 += ld[kk][j].x;
+        x1 += ld[kk][j].y;
       }
       if (p.round_tf32) {
         uint32_t u0, u1;
@@ -267,10 +286,10 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
       }
       if (ok && (K_C || (GEN && p.C))) *reinterpret_cast<float2*>(p.C + gr * p.ldc + c) = make_float2(x0, x1);
       if (EPI >= 0 && (EPI & EPI_LN)) {   // row statistics of the values just written (fused LayerNorm, pass 1); the values
-        st1[k] += x0 + x1;               // themselves go back into the fragment: the caller parks them in TMEM for pass 2
-        st2[k] = fmaf(x0, x0, fmaf(x1, x1, st2[k]));
-        v[k >> 1][4 * j + 2 * (k & 1)] = x0;
-        v[k >> 1][4 * j + 2 * (k & 1) + 1] = x1;
+        st1[kk] += x0 + x1;              // themselves go back into the fragment: the caller parks them in TMEM for pass 2
+        st2[kk] = fmaf(x0, x0, fmaf(x1, x1, st2[kk]));
+        v[4 * j + 2 * kk] = x0;
+        v[4 * j + 2 * kk + 1] = x1;
       }
       if (K_C16 || (GEN && p.C16)) {
         // bf16 pairs are only 4 bytes: trade pairs with the neighbouring lane so that every thread owns 4 consecutive columns
@@ -291,10 +310,22 @@ __device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][1
   }
 }
 
+// whole 32-lane quadrant fragment at once (CTA-pair kernel): v[0] = lanes 0..15, v[1] = lanes 16..31; all global loads are
+// issued before any arithmetic so their latencies overlap
+template <int EPI>
+__device__ __forceinline__ void tc_epi_frag2(const TcParams& pp, float (&v)[2][16], const int (&grow)[4], int n, int t,
+                                             float* st1 = nullptr, float* st2 = nullptr) {
+  float2 ld[2][2][4];
+  tc_epi_load_half<EPI>(pp, grow, n, t, ld[0]);
+  tc_epi_load_half<EPI>(pp, grow + 2, n, t, ld[1]);
+  tc_epi_half<EPI>(pp, v[0], grow, n, t, ld[0], st1, st2);
+  tc_epi_half<EPI>(pp, v[1], grow + 2, n, t, ld[1], st1 ? st1 + 2 : nullptr, st2 ? st2 + 2 : nullptr);
+}
+
 // fused LayerNorm, pass 2: the post-epilogue values of one 32-column chunk come back from TMEM (fragment layout of
 // tmem_ld_16x256b_x4), are normalised and stored as bf16 (same lane-pair exchange as the C16 path: four threads fill one
 // 32-byte sector of a row)
-__device__ __forceinline__ void tc_epi_ln_store(const TcParams& p, const float (&v)[2][16], const long long (&grow)[4], const float (&mu)[4],
+__device__ __forceinline__ void tc_epi_ln_store(const TcParams& p, const float (&v)[2][16], const int (&grow)[4], const float (&mu)[4],
                                                 const float (&rs)[4], int n, int t) {
   const int cb = n + 2 * (t & 3);
   float2 g[4], b[4];
@@ -321,7 +352,7 @@ __device__ __forceinline__ void tc_epi_ln_store(const TcParams& p, const float (
         o.y = even ? got : mine[1];
         const int c = cb + 8 * j;
         const int cc = even ? (c - 8) : (c - 2);
-        if (ok) *reinterpret_cast<uint2*>(p.ln_out16 + grow[k] * (long long)p.N + cc) = o;
+        if (ok) *reinterpret_cast<uint2*>(p.ln_out16 + (long long)grow[k] * p.N + cc) = o;
       }
     }
   }
@@ -451,40 +482,48 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, bimg = mt / (p.tiles_w * p.tiles_h);
       const int n0 = nt * BN;
       // the four tile rows this thread touches: q*32 + lane/4 + 8k
-      long long grow[4];
+      int grow[4];   // global row index (< 2^31, checked on the host) or -1
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = q * 32 + (lane >> 2) + 8 * k;
         const int hh = r / p.BW, ww = r - hh * p.BW;
         const int h = th * p.BH + hh, w = tw * p.BW + ww;
-        grow[k] = (h < p.Hg && w < p.Wg) ? ((long long)bimg * p.Hg + h) * p.Wg + w : -1;
+        grow[k] = (h < p.Hg && w < p.Wg) ? (bimg * p.Hg + h) * p.Wg + w : -1;
       }
       const uint32_t as = j & 1;
-      mbar_wait(bar_accf + as * 8, (j >> 1) & 1);
-      tc_fence_after();
-      bool handed_back = false;
       constexpr bool LN = EPI >= 0 && (EPI & EPI_LN);
+      constexpr int SL = TCP_EPI_WARPS / 4;                       // column slots
+      constexpr int NCH = BN / (32 * SL) > 0 ? BN / (32 * SL) : 1;   // 32-column chunks per warp
       float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int c0 = slot * 32; c0 < BN; c0 += 32 * (TCP_EPI_WARPS / 4)) {
-        float v[2][16];
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0);
-        tmem_ld_16x256b_x4(ta, v[0]);                    // lanes q*32 + 0..15
-        tmem_ld_16x256b_x4(ta + (16u << 16), v[1]);      // lanes q*32 + 16..31
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!LN && c0 + 32 * (TCP_EPI_WARPS / 4) >= BN) {
-          // last TMEM read of this tile by this thread: hand the accumulator buffer back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(bar_acce + as * 8);
-          handed_back = true;
+      if (slot * 32 < BN) {
+        // half-steps hs = 2 * chunk + half; the global loads of half-step hs + 1 are issued before half-step hs is processed
+        const bool has_ld = tc_epi_has_loads<EPI>(p);
+        float2 ld[2][2][4];
+        if (has_ld) tc_epi_load_half<EPI>(p, grow, n0 + slot * 32, lane, ld[0]);   // in flight while the accumulator completes
+        mbar_wait(bar_accf + as * 8, (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hs = 0; hs < 2 * NCH; ++hs) {
+          const int c0 = slot * 32 + (hs >> 1) * 32 * SL, half = hs & 1;
+          if (has_ld && hs + 1 < 2 * NCH)
+            tc_epi_load_half<EPI>(p, grow + 2 * ((hs + 1) & 1), n0 + slot * 32 + ((hs + 1) >> 1) * 32 * SL, lane, ld[(hs + 1) & 1]);
+          float v[16];
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32 + 16 * half) << 16) + (uint32_t)(as * BN + c0);
+          tmem_ld_16x256b_x4(ta, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (!LN && hs + 1 == 2 * NCH) {
+            // last TMEM read of this tile by this thread: hand the accumulator buffer back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(bar_acce + as * 8);
+          }
+          tc_epi_half<EPI>(p, v, grow + 2 * half, n0 + c0, lane, ld[hs & 1], st1 + 2 * half, st2 + 2 * half);
+          if (LN) tmem_st_16x256b_x4(ta, v);   // park the post-epilogue values where the accumulator was: pass 2 reads them back
         }
-        tc_epi_frag2<EPI>(p, v, grow, n0 + c0, lane, st1, st2);
-        if (LN) {   // park the post-epilogue values where the accumulator was: pass 2 reads them back without touching L2
-          tmem_st_16x256b_x4(ta, v[0]);
-          tmem_st_16x256b_x4(ta + (16u << 16), v[1]);
-        }
+      } else {
+        mbar_wait(bar_accf + as * 8, (j >> 1) & 1);
+        tc_fence_after();
+        if (!LN) mbar_arrive(bar_acce + as * 8);   // narrow tiles: this warp's column slot does not exist
       }
-      if (!LN && !handed_back) mbar_arrive(bar_acce + as * 8);   // narrow tiles: this warp's column slot does not exist
       if (LN) {
         // fused LayerNorm of the output rows (the tile holds whole rows: N == BN).  Pass 1 above accumulated sum / sum of
         // squares of this thread's columns; combine the four lanes that share a row, then the four column-slot warps through
@@ -681,13 +720,13 @@ gemm_tc_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int nt = tile % n_tiles, mt = 2 * (tile / n_tiles) + (int)rank;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, bimg = mt / (p.tiles_w * p.tiles_h);
       const int n0 = nt * BN;
-      long long grow[4];
+      int grow[4];   // global row index (< 2^31, checked on the host) or -1
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = q * 32 + (lane >> 2) + 8 * k;
         const int hh = r / p.BW, ww = r - hh * p.BW;
         const int h = th * p.BH + hh, w = tw * p.BW + ww;
-        grow[k] = (mt < m_tiles && h < p.Hg && w < p.Wg) ? ((long long)bimg * p.Hg + h) * p.Wg + w : -1;
+        grow[k] = (mt < m_tiles && h < p.Hg && w < p.Wg) ? (bimg * p.Hg + h) * p.Wg + w : -1;
       }
       const uint32_t as = j & 1;
       mbar_wait(bar_accf + as * 8, (j >> 1) & 1);
@@ -1121,7 +1160,7 @@ extern "C" int tbns_gemm_tc(const tbns_tc_desc* dp, void* stream) {
   TBNS_REQUIRE(d.A16 && d.W16 && (d.C || d.C16), "tbns_gemm_tc: null pointer");
   TBNS_REQUIRE(tbns_gemm_tc_supported(d.Cin, d.N, d.taps), "tbns_gemm_tc: unsupported shape Cin=%d N=%d taps=%d (need Cin%%64==0, N%%64==0)",
                d.Cin, d.N, d.taps);
-  TBNS_REQUIRE(d.Bimg > 0 && d.Hg > 0 && d.Wg > 0, "tbns_gemm_tc: bad dims");
+  TBNS_REQUIRE(d.Bimg > 0 && d.Hg > 0 && d.Wg > 0 && (long long)d.Bimg * d.Hg * d.Wg < 0x7fffffffLL, "tbns_gemm_tc: bad dims");
   TBNS_REQUIRE(d.act >= 0 && d.act <= 4 && ((d.act != 2 && d.act != 4) || d.aux_in), "tbns_gemm_tc: bad activation spec");
   TBNS_REQUIRE(al16p(d.A16) && al16p(d.W16) && (!d.C || (al16p(d.C) && d.ldc % 4 == 0)) && (!d.C16 || (al16p(d.C16) && d.ldc16 % 8 == 0)) &&
                    (!d.bias || al16p(d.bias)) && (!d.residual || (al16p(d.residual) && d.ldr % 4 == 0)) &&
