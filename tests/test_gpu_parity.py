@@ -325,9 +325,9 @@ def test_pa_baseline_config_sizes(dev, cfg, precision):
     if cfg == "cfg1_ns64":
         cls, kw, B, N = PA.Physics_Attention_Structured_Mesh_2D, dict(dim=256, heads=8, dim_head=32, slice_num=32, H=64, W=64), 2, 4096
     elif cfg == "cfg3_darcy85":
-        cls, kw, B, N = PA.Physics_Attention_Structured_Mesh_2D, dict(dim=128, heads=8, dim_head=16, slice_num=64, H=85, W=85), 1, 7225
+        cls, kw, B, N = PA.Physics_Attention_Structured_Mesh_2D, dict(dim=128, heads=8, dim_head=16, slice_num=64, H=85, W=85), 4, 7225   # SURVEY §8d cfg 3: batch 4
     else:
-        cls, kw, B, N = PA.Physics_Attention_Irregular_Mesh, dict(dim=128, heads=8, dim_head=16, slice_num=64), 1, 972
+        cls, kw, B, N = PA.Physics_Attention_Irregular_Mesh, dict(dim=128, heads=8, dim_head=16, slice_num=64), 2, 972
     m = _rand_state(cls, kw, 7)
     x = torch.nn.functional.layer_norm(torch.randn(B, N, kw["dim"]), (kw["dim"],))
     if precision == "bf16":
