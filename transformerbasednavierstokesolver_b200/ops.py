@@ -64,11 +64,19 @@ def _count(n: int):
     LAUNCHES += n
 
 
+# TBNS_NVTX=1: every tagged stage of the block (proj_fprop, slice_fwd, token_attn_fwd, deslice_out, mlp_fc1, ...) is wrapped in
+# an NVTX range, so timelines taken with the CUDA profilers name the stages of model/Physics_Attention.py:88-119
+_NVTX = os.environ.get("TBNS_NVTX", "0") == "1"
+
+
 class _Timed:
     def __init__(self, tag):
         self.tag = tag if (PROFILE is not None and tag is not None) else None
+        self.nvtx = tag if (_NVTX and tag is not None) else None
 
     def __enter__(self):
+        if self.nvtx is not None:
+            torch.cuda.nvtx.range_push(self.nvtx)
         if self.tag is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
@@ -78,6 +86,8 @@ class _Timed:
         if self.tag is not None:
             self.e1.record()
             PROFILE.setdefault(self.tag, []).append((self.e0, self.e1))
+        if self.nvtx is not None:
+            torch.cuda.nvtx.range_pop()
 
 
 def _stream() -> int:
