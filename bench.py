@@ -276,8 +276,12 @@ def run_train(args, unrolled: bool):
     train.broadcast_parameters(model)
     grads = train.FlatGradients(model.parameters())
     graphed = bool(args.graph)
-    opt = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-3, device=dev) if graphed else 1e-3, weight_decay=1e-5,
-                            fused=True, capturable=graphed)
+    if args.optimizer == "flat" and not (world > 1 and args.buckets > 1):
+        # AdamW as one libtbns kernel over flat parameter / gradient / moment buffers (same update rule as torch.optim.AdamW)
+        opt = train.FlatAdamW(model.parameters(), grads, lr=1e-3, weight_decay=1e-5)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-3, device=dev) if graphed else 1e-3, weight_decay=1e-5,
+                                fused=True, capturable=graphed)
     total_steps = 2 * (args.steps + args.warmup) + 32
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-3, total_steps=total_steps)
 
@@ -421,6 +425,8 @@ def run_train(args, unrolled: bool):
                        "global_batch": gb, "parallelism": f"dp{world}",
                        "calls_batched": batched, "images_per_launch": imgs_per_launch, "model_calls_per_step": calls,
                        "cuda_graph": graphed, "allreduce_buckets": (gstep.nb if gstep is not None else 1),
+                       "optimizer": ("AdamW as one libtbns kernel over flat buffers (train.FlatAdamW)" if isinstance(opt, train.FlatAdamW)
+                                     else "torch.optim.AdamW(fused=True)") + " + OneCycleLR",
                        "replicas_identical": replicas_identical,
                        "l2": "activations written per step (>1 GB) exceed the 126 MB L2; fresh input batch every step"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": per_step_in, "d2h_bytes_per_step": 4,
@@ -522,6 +528,8 @@ def main():
                     "optimizer graph); 0 = eager launches")
     ap.add_argument("--buckets", type=int, default=1, help="N > 1 GPUs: cut backward into this many stage graphs and all-reduce each "
                     "stage's gradient range beside the next stages")
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"], help="flat: train.FlatAdamW (one libtbns kernel over flat "
+                    "buffers); torch: torch.optim.AdamW(fused=True)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cpu-1thread", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")

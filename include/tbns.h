@@ -244,6 +244,11 @@ int tbns_pa_dtau_finish(const float* dtau_part, const float* temperature, float*
 
 /* out[j] = sum_i in[i*cols + j], i < rows (fixed order, deterministic). */
 int tbns_reduce_rows(const float* in, float* out, int rows, long long cols, void* stream);
+
+/* AdamW step over flat fp32 buffers (parameters, gradients, first / second moments, n elements each; torch.optim.AdamW
+ * semantics, exp_ns.py:172-173,208-209).  hp: 7 floats on the device written by the caller before the launch
+ * {lr, beta1, beta2, eps, weight_decay, 1 - beta1^t, 1 - beta2^t} - a graph replay picks up the scheduler's new values. */
+int tbns_adamw_flat(float* p, const float* g, float* m, float* v, const float* hp, long long n, void* stream);
 /* column sums of a [rows, cols] matrix (bias gradients); ws: tbns_colsum_ws_floats(cols) floats */
 size_t tbns_colsum_ws_floats(long long cols);
 int tbns_colsum_bf16(const void* in16, long long ld, float* out, float* ws, int rows, int cols, void* stream);

@@ -89,3 +89,75 @@ def test_graphed_step_matches_eager_steps(buckets):
             assert torch.allclose(p1, p2, rtol=1e-4, atol=1e-6), k
     finally:
         pkg.set_default_precision("bf16")
+
+
+def test_flat_adamw_matches_torch_adamw_with_onecycle():
+    """train.FlatAdamW (one libtbns kernel over flat parameter / gradient / moment buffers) against torch.optim.AdamW with
+    OneCycleLR driving lr AND beta1 (cycle_momentum) as in exp_ns.py:172-176:
+    (a) the optimizers alone on identical gradient streams (update rule, bias corrections, decoupled weight decay);
+    (b) a model trained eagerly with FlatAdamW vs the same steps replayed from CUDA graphs (GraphedTrainStep hands the changing
+        hyper-parameters to the device before each replay);
+    (c) the loss trajectory against the stock optimizer (the parameters live at different addresses, so gradients may differ in
+        the last bit and Adam turns that into O(lr) differences on near-zero-gradient entries: trajectories, not bits)."""
+    import transformerbasednavierstokesolver_b200 as pkg
+    from transformerbasednavierstokesolver_b200 import train
+    dev = torch.device("cuda:0")
+    # (a)
+    torch.manual_seed(0)
+    a1 = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.Linear(64, 3), torch.nn.Linear(3, 1)).to(dev)   # odd sizes: padded layout
+    a2 = copy.deepcopy(a1)
+    oa1 = torch.optim.AdamW(a1.parameters(), lr=1e-3, weight_decay=1e-2)
+    sa1 = torch.optim.lr_scheduler.OneCycleLR(oa1, max_lr=5e-3, total_steps=16)
+    ga2 = train.FlatGradients(a2.parameters())
+    oa2 = train.FlatAdamW(a2.parameters(), ga2, lr=1e-3, weight_decay=1e-2)
+    sa2 = torch.optim.lr_scheduler.OneCycleLR(oa2, max_lr=5e-3, total_steps=16)
+    assert all(p.data_ptr() % 16 == 0 for p in a2.parameters())              # views of the flat buffer stay 16-byte aligned
+    for _ in range(8):
+        gs = [torch.randn_like(p) for p in a1.parameters()]
+        for p, g in zip(a1.parameters(), gs):
+            p.grad = g.clone()
+        for p, g in zip(a2.parameters(), gs):
+            p.grad.copy_(g)
+        oa1.step(); sa1.step(); oa2.step(); sa2.step()
+    torch.cuda.synchronize()
+    assert oa2.param_groups[0]["betas"][0] != 0.9                             # the scheduler really cycled beta1
+    for p1, p2 in zip(a1.parameters(), a2.parameters()):
+        assert torch.allclose(p1, p2, rtol=1e-5, atol=1e-7)
+    try:
+        m1 = _small_model(dev, "fp32")
+        m2 = copy.deepcopy(m1)
+        m3 = copy.deepcopy(m1)
+        batches = [train.synthetic_ns_batch(2, 8, 4, 3, seed=30 + i, device=dev) for i in range(5)]
+        g1 = train.FlatGradients(m1.parameters())
+        o1 = torch.optim.AdamW(m1.parameters(), lr=1e-3, weight_decay=1e-2)
+        s1 = torch.optim.lr_scheduler.OneCycleLR(o1, max_lr=5e-3, total_steps=16)
+        g2 = train.FlatGradients(m2.parameters())
+        o2 = train.FlatAdamW(m2.parameters(), g2, lr=1e-3, weight_decay=1e-2)
+        s2 = torch.optim.lr_scheduler.OneCycleLR(o2, max_lr=5e-3, total_steps=16)
+        l1, l2 = [], []
+        for b in batches:
+            l1.append(float(train.train_step(m1, o1, s1, g1, *b, T=3, step=1, batched=True)))
+            l2.append(float(train.train_step(m2, o2, s2, g2, *b, T=3, step=1, batched=True)))
+        for x1, x2 in zip(l1, l2):                                             # (c)
+            assert abs(x1 - x2) <= 2e-3 * abs(x1), (l1, l2)
+        # (b) flat optimizer through CUDA graphs: restart from the initial point after warm-up / capture
+        g3 = train.FlatGradients(m3.parameters())
+        o3 = train.FlatAdamW(m3.parameters(), g3, lr=1e-3, weight_decay=1e-2)
+        state0 = copy.deepcopy(m3.state_dict())
+        gs = train.GraphedTrainStep(m3, o3, None, g3, batches[0], T=3, step=1, batched=True, warmup=2)
+        m3.load_state_dict(state0)
+        o3.exp_avg.zero_()
+        o3.exp_avg_sq.zero_()
+        o3.t = 0
+        o3.param_groups[0]["lr"], o3.param_groups[0]["betas"] = 1e-3, (0.9, 0.999)
+        gs.sched = torch.optim.lr_scheduler.OneCycleLR(o3, max_lr=5e-3, total_steps=16)
+        for b in batches:
+            gs(b)
+        torch.cuda.synchronize()
+        for (k, p2), (_, p3) in zip(m2.named_parameters(), m3.named_parameters()):
+            assert torch.allclose(p2, p3, rtol=1e-4, atol=1e-6), k
+        # checkpoints still load into the relocated parameters
+        m3.load_state_dict(m1.state_dict())
+        assert torch.equal(next(m3.parameters()), next(m1.parameters())) and next(m3.parameters()).data_ptr() == o3.flat_p.data_ptr()
+    finally:
+        pkg.set_default_precision("bf16")

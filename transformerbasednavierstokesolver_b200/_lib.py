@@ -106,6 +106,7 @@ _SIGS = {
     "tbns_pa_slice_bwd": (_i, [_fp] * 12 + [_i] * 6 + [_fp]),
     "tbns_pa_dtau_finish": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp]),
     "tbns_reduce_rows": (_i, [_fp, _fp, _i, _ll, _fp]),
+    "tbns_adamw_flat": (_i, [_fp] * 5 + [_ll, _fp]),
     "tbns_colsum_ws_floats": (C.c_size_t, [_ll]),
     "tbns_colsum": (_i, [_fp, _ll, _fp, _fp, _i, _i, _fp]),
     "tbns_colsum_bf16": (_i, [_fp, _ll, _fp, _fp, _i, _i, _fp]),

@@ -32,16 +32,23 @@ class FlatGradients:
     """All parameter gradients live in ONE flat fp32 buffer (p.grad are views), so the data-parallel exchange is a single
     NCCL all-reduce (cfg 1: 11.2 M elements = 44.8 MB) and the optimizer reads contiguous memory."""
 
+    ALIGN = 4   # every view starts on a 16-byte boundary (FlatAdamW lays the PARAMETERS out the same way, and libtbns reads
+                # weights with 16-byte vector loads / TMA); the padding elements stay zero
+
+    @staticmethod
+    def padded(n: int) -> int:
+        return -(-n // FlatGradients.ALIGN) * FlatGradients.ALIGN
+
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        total = sum(self.padded(p.numel()) for p in self.params)
         self.flat = torch.zeros(total, device=self.params[0].device, dtype=torch.float32)
         off = 0
         self.views = []
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             p.grad = self.views[-1]
-            off += p.numel()
+            off += self.padded(p.numel())
 
     def zero(self):
         self.flat.zero_()
@@ -82,6 +89,70 @@ def broadcast_parameters(model: torch.nn.Module, src: int = 0):
                 dist.broadcast(t.detach(), src)
         from . import ops
         ops.invalidate_weight_caches()   # the collective wrote into the masters behind autograd's version counters
+
+
+class FlatAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics (exp_ns.py:172-173: AdamW(lr, weight_decay); amsgrad / maximize off) as ONE libtbns kernel
+    over flat buffers: the parameters become views into one fp32 buffer laid out like `grads.flat`, the moments are flat, and
+    a step is a single elementwise pass (`tbns_adamw_flat`, ~50 us for the 11.2 M parameters of cfg 1; torch's fused
+    multi-tensor AdamW needs ~0.45 ms for the same ~180 tensors).  Hyper-parameters are ordinary `param_groups` entries, so
+    `OneCycleLR` drives `lr` and (cycle_momentum) `betas[0]` as with the stock optimizer; before every launch they are copied
+    into a small device array that the kernel reads - which also makes the step replayable from a CUDA graph with changing
+    lr / beta1 (`GraphedTrainStep` calls `prepare_step()` before each replay).  One parameter group."""
+
+    def __init__(self, params, grads: FlatGradients, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        params = [p for p in params if p.requires_grad]
+        if [id(p) for p in params] != [id(p) for p in grads.params]:
+            raise ValueError("FlatAdamW: parameters must be the ones (and in the order) of the FlatGradients buffer")
+        if not params[0].is_cuda:
+            raise RuntimeError("transformerbasednavierstokesolver_b200 has no CPU path: FlatAdamW needs CUDA parameters")
+        super().__init__(params, dict(lr=float(lr), betas=tuple(betas), eps=float(eps), weight_decay=float(weight_decay)))
+        self.grads = grads
+        dev = params[0].device
+        self.flat_p = torch.zeros_like(grads.flat)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view      # state_dict / checkpoint loading keep working: they copy into the views
+                off += grads.padded(p.numel())
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.hp = torch.zeros(8, device=dev, dtype=torch.float32)
+        # ring of pinned host slots: the copy of step t is asynchronous, so its source must stay untouched until it has run;
+        # the host cannot be 256 optimizer steps ahead of the device (launch-queue depth)
+        self._hp_host = torch.zeros(256, 8, dtype=torch.float32).pin_memory()
+        self.t = 0
+        self._order = tuple(id(p) for p in grads.params)
+
+    def prepare_step(self):
+        """advance the step count and hand this step's hyper-parameters to the device (asynchronous 32-byte copy)"""
+        g = self.param_groups[0]
+        self.t += 1
+        lr = float(g["lr"])
+        b1, b2 = (float(b) for b in g["betas"])
+        h = self._hp_host[self.t % self._hp_host.shape[0]]
+        h[0], h[1], h[2], h[3], h[4] = lr, b1, b2, float(g["eps"]), float(g["weight_decay"])
+        h[5], h[6] = 1.0 - b1 ** self.t, 1.0 - b2 ** self.t
+        self.hp.copy_(h, non_blocking=True)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import _lib
+        if closure is not None:
+            raise RuntimeError("FlatAdamW: closures are not supported")
+        if self._order != tuple(id(p) for p in self.grads.params):
+            raise RuntimeError("FlatAdamW: the FlatGradients layout changed (bucketed stage order): rebuild the optimizer")
+        if not torch.cuda.is_current_stream_capturing():
+            self.prepare_step()       # under capture only the kernel is recorded; the replaying host calls prepare_step()
+        from . import ops
+        ops._count(1)
+        lib = _lib.load()
+        _lib.check(lib.tbns_adamw_flat(self.flat_p.data_ptr(), self.grads.flat.data_ptr(), self.exp_avg.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), self.hp.data_ptr(), self.flat_p.numel(),
+                                       torch.cuda.current_stream().cuda_stream), "tbns_adamw_flat")
+        return None
 
 
 def teacher_forced_inputs(fx: torch.Tensor, yy: torch.Tensor, T: int, step: int = 1) -> torch.Tensor:
@@ -346,7 +417,7 @@ class GraphedTrainStep:
             start = off
             for p in ps:
                 fg.views.append(fg.flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+                off += fg.padded(p.numel())
             self.ranges.append((start, off))
         assert off == fg.flat.numel()
         for p, v in zip(fg.params, fg.views):
@@ -420,6 +491,8 @@ class GraphedTrainStep:
         else:
             self.g_fb.replay()
             self.grads.all_reduce()
+        if hasattr(self.opt, "prepare_step"):
+            self.opt.prepare_step()   # FlatAdamW: this step's lr / betas / bias corrections into the device array the graph reads
         self.g_opt.replay()
         self._ops.invalidate_weight_caches()   # the replay changed the masters without bumping their version counters
         if self.sched is not None:
