@@ -156,6 +156,12 @@ def test_flat_adamw_matches_torch_adamw_with_onecycle():
         torch.cuda.synchronize()
         for (k, p2), (_, p3) in zip(m2.named_parameters(), m3.named_parameters()):
             assert torch.allclose(p2, p3, rtol=1e-4, atol=1e-6), k
+        # optimizer checkpoint round trip (moments live in flat buffers)
+        sd = o3.state_dict()
+        o3.exp_avg.zero_()
+        o3.t = 0
+        o3.load_state_dict(sd)
+        assert o3.t == len(batches) and torch.equal(o3.exp_avg, sd["flat"]["exp_avg"]) and float(o3.exp_avg.abs().sum()) > 0
         # checkpoints still load into the relocated parameters
         m3.load_state_dict(m1.state_dict())
         assert torch.equal(next(m3.parameters()), next(m1.parameters())) and next(m3.parameters()).data_ptr() == o3.flat_p.data_ptr()

@@ -98,7 +98,8 @@ class FlatAdamW(torch.optim.Optimizer):
     multi-tensor AdamW needs ~0.45 ms for the same ~180 tensors).  Hyper-parameters are ordinary `param_groups` entries, so
     `OneCycleLR` drives `lr` and (cycle_momentum) `betas[0]` as with the stock optimizer; before every launch they are copied
     into a small device array that the kernel reads - which also makes the step replayable from a CUDA graph with changing
-    lr / beta1 (`GraphedTrainStep` calls `prepare_step()` before each replay).  One parameter group."""
+    lr / beta1 (`GraphedTrainStep` calls `prepare_step()` before each replay).  One parameter group.  Build it AFTER the model
+    is on its device (`module.to()` would re-allocate the parameters and detach them from the flat buffer)."""
 
     def __init__(self, params, grads: FlatGradients, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         params = [p for p in params if p.requires_grad]
@@ -125,6 +126,20 @@ class FlatAdamW(torch.optim.Optimizer):
         self._hp_host = torch.zeros(256, 8, dtype=torch.float32).pin_memory()
         self.t = 0
         self._order = tuple(id(p) for p in grads.params)
+
+    # checkpoint / resume: the moments live in the flat buffers, not in `self.state`
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["flat"] = {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "t": self.t}
+        return sd
+
+    def load_state_dict(self, sd):
+        sd = dict(sd)
+        flat = sd.pop("flat")
+        super().load_state_dict(sd)
+        self.exp_avg.copy_(flat["exp_avg"])
+        self.exp_avg_sq.copy_(flat["exp_avg_sq"])
+        self.t = int(flat["t"])
 
     def prepare_step(self):
         """advance the step count and hand this step's hyper-parameters to the device (asynchronous 32-byte copy)"""
