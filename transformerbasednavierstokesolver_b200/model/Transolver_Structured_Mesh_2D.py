@@ -76,8 +76,13 @@ class Model(nn.Module):
             tab16 = self._pos16(fx.device) if self.unified_pos else None
             src1 = None if self.unified_pos else x
             ln1 = self.blocks[0].ln_1 if (T is None and isinstance(self.blocks[0], _Block)) else None   # computed by the second Linear
+            # all blocks' derived weights (packed projections, bf16 MLP operands) are refreshed on the side stream beside the
+            # preprocess MLP; each block then finds them in the cache
+            forked = ops.refresh_weights_ahead(self, self.blocks, ops.TBNS_PREC_BF16)
             fx = ops.PackedMlpFn.apply(tab16, src1, fx, pre.weight, pre.bias, post.weight, post.bias,
                                        *((ln1.weight, ln1.bias, ln1.eps) if ln1 is not None else (None, None, 1e-5)))
+            if forked:
+                ops._join_side()
         else:
             if self.unified_pos:
                 if self.pos.device != x.device:

@@ -451,6 +451,34 @@ def _join_side():
         torch.cuda.current_stream().wait_stream(_side())
 
 
+_PREFETCH_WEIGHTS = os.environ.get("TBNS_SIDE_PREFETCH", "1") != "0"
+
+
+def refresh_weights_ahead(owner, blocks, prec: int) -> bool:
+    """Issue the derived-weight refresh of ALL blocks (packed bf16 projection operands, bf16 pairs of the MLP weights) on the
+    side stream at the start of a forward pass, so that it overlaps the preprocess MLP instead of sitting in front of every
+    block's first GEMM (24 small launches per step at cfg 1).  The later per-block lookups hit the cache.  Returns True when
+    work was forked: the caller joins (`_join_side()`) before the first block.  `owner` remembers the cache context it
+    prefetched for, so calls within the same weight generation (unrolled / rollout loops) cost nothing."""
+    if prec != TBNS_PREC_BF16 or not _USE_SIDE or not _PREFETCH_WEIGHTS:
+        return False
+    ctx = cache_context()
+    if getattr(owner, "_tbns_prefetched_ctx", None) == ctx:
+        return False
+    with _OnSide():
+        for b in blocks:
+            attn = getattr(b, "Attn", None)
+            mlp = getattr(b, "mlp", None)
+            if attn is None or mlp is None or not hasattr(attn, "_packed_weights"):
+                continue
+            attn._packed_weights(prec)
+            for lin in (mlp.linear_pre[0], mlp.linear_post):
+                if lin.weight.is_cuda and tc_supported(lin.weight.shape[1], lin.weight.shape[0], 1):
+                    weight_bf16_pair(lin.weight)
+    owner._tbns_prefetched_ctx = ctx
+    return True
+
+
 # Side products of a fused backward stage (a bf16 copy of the gradient it returns, its column sums = the bias gradient of
 # the layer that produced the stream) are handed to the stage autograd runs next as an ATTRIBUTE OF THE RETURNED TENSOR
 # OBJECT.  PyTorch preserves the Python object of a live tensor, so the next custom Function's backward receives the very
