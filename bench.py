@@ -225,9 +225,14 @@ def profile_eager_steps(step_fn, n=3):
     """CUDA-event pairs around every tagged libtbns launch during `n` eager steps, side stream off so that each tagged kernel
     runs alone (kernels inside a replayed graph cannot be bracketed by events) -> {tag: ms per step}, raw event pairs"""
     from transformerbasednavierstokesolver_b200 import ops
-    ops.PROFILE = {}
     side_saved, ops._USE_SIDE = ops._USE_SIDE, False
     try:
+        # one untimed eager replay first: the graphed region ran from a private memory pool, so the first eager step pays for
+        # allocator growth (host-synchronous cudaMalloc) and cold caches; kernels are timed after warm-up like everything else
+        ops.PROFILE = None
+        step_fn(0)
+        torch.cuda.synchronize()
+        ops.PROFILE = {}
         for i in range(n):
             # keep the stream backlogged while the host enqueues the eager step (~100 ms spin kernel first): an event recorded
             # on an idle stream is stamped at enqueue time, so host launch latency between the two records of a pair would be
