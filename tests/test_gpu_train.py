@@ -167,3 +167,47 @@ def test_flat_adamw_matches_torch_adamw_with_onecycle():
         assert torch.equal(next(m3.parameters()), next(m1.parameters())) and next(m3.parameters()).data_ptr() == o3.flat_p.data_ptr()
     finally:
         pkg.set_default_precision("bf16")
+
+
+def test_direct_gradient_destinations_equal_gathered_gradients():
+    """FlatGradients.begin() arms every parameter with its view of the flat buffer; the bf16-route backward stages write the
+    large weight gradients (conv projections, MLP weights) straight into those views (ops._claim_grad).  The flat buffer must
+    equal, bit for bit, the gradients of a plain backward pass - for a parameter used once (teacher-forced step) and for
+    parameters shared by several calls (unrolled training: the first gradient lands in place, autograd accumulates the
+    rest into it)."""
+    import transformerbasednavierstokesolver_b200 as pkg
+    from transformerbasednavierstokesolver_b200 import ops, train
+    from transformerbasednavierstokesolver_b200.model.Transolver_Structured_Mesh_2D import Model
+    from transformerbasednavierstokesolver_b200.model.SOL_Transolver_Structured_Mesh_2D import SOL_Transolver_Structured_Mesh_2D
+    dev = torch.device("cuda:0")
+    pkg.set_default_precision("bf16")
+    torch.manual_seed(3)
+    cfg = dict(space_dim=2, n_layers=2, n_hidden=256, dropout=0.0, n_head=8, Time_Input=False, mlp_ratio=1, fun_dim=10, out_dim=1,
+               slice_num=32, ref=8, unified_pos=1, H=64, W=64)
+    sol = SOL_Transolver_Structured_Mesh_2D(step=1, look_ahead=5, **cfg).to(dev)
+    model = sol.transolver_model
+    assert isinstance(model, Model)
+    x, fx, yy = train.synthetic_ns_batch(2, 64, 10, 10, seed=5, device=dev)
+    cases = {"teacher_forced": lambda: train.step_loss(model, x, fx, yy, 10, 1, True),
+             "unrolled_la5": lambda: train.unrolled_step_loss(sol, x, fx, yy, 10, 1, True)}   # every weight is used by 5 chained calls
+    for name, loss_fn in cases.items():
+        for p in model.parameters():
+            p.grad = None
+        loss_fn().backward()
+        want = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        g = train.FlatGradients(model.parameters())
+        g.flat.fill_(float("nan"))
+        g.begin()
+        loss_fn().backward()
+        conv = model.blocks[0].Attn.in_project_x.weight
+        view = g.views[[id(p) for p in g.params].index(id(conv))]
+        if name == "teacher_forced":
+            assert conv.grad.data_ptr() == view.data_ptr(), "the conv weight gradient was not written in place"
+        g.finish()
+        torch.cuda.synchronize()
+        for k, p in model.named_parameters():
+            if k in want:
+                assert torch.equal(p.grad, want[k]), (name, k)
+            assert p.grad.data_ptr() == g.views[[id(q) for q in g.params].index(id(p))].data_ptr()
+            assert getattr(p, "_tbns_grad_dst", None) is None      # disarmed after the pass
+

@@ -454,6 +454,28 @@ def _join_side():
 _PREFETCH_WEIGHTS = os.environ.get("TBNS_SIDE_PREFETCH", "1") != "0"
 
 
+# Gradient destinations.  train.FlatGradients.begin() arms every parameter with (view of the flat gradient buffer, token of
+# this backward pass).  A forward stage notes the destinations of its large weights in its ctx; the matching backward lets the
+# wgrad kernels write straight into the view and returns an alias of it, so the end-of-backward gather has nothing to copy for
+# that parameter (cfg 1: 42 of the 45 MB).  A view is claimed at most once per pass - a parameter used by several calls
+# (unrolled training) gets the first gradient in place and autograd accumulates the others into it.
+_DIRECT_GRADS = os.environ.get("TBNS_DIRECT_GRADS", "1") != "0"
+
+
+def _grad_dst(param):
+    return getattr(param, "_tbns_grad_dst", None) if _DIRECT_GRADS else None
+
+
+def _claim_grad(dst, shape, **kw):
+    """-> tensor the weight gradient of this stage should be written to"""
+    if dst is not None:
+        view, token = dst
+        if tuple(view.shape) == tuple(shape) and getattr(view, "_tbns_claimed", None) is not token:
+            view._tbns_claimed = token
+            return view.detach()      # fresh tensor object on the same memory: autograd adopts it as p.grad without a copy
+    return torch.empty(shape, **kw)
+
+
 def refresh_weights_ahead(owner, blocks, prec: int) -> bool:
     """Issue the derived-weight refresh of ALL blocks (packed bf16 projection operands, bf16 pairs of the MLP weights) on the
     side stream at the start of a forward pass, so that it overlaps the preprocess MLP instead of sitting in front of every
@@ -675,7 +697,8 @@ def pa_forward(x, temperature, Wf, bcat, Ws, bs, Wq, Wk, Wv, Wo, bo, residual, h
 
 
 def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo, saved, heads: int,
-                grid: Optional[Tuple[int, int]], precision: int, Wd16=None, dout16=None, dbo=None, dx_bf16: bool = False):
+                grid: Optional[Tuple[int, int]], precision: int, Wd16=None, dout16=None, dbo=None, dx_bf16: bool = False,
+                grad_dst=(None, None)):
     """returns dx and the parameter gradients in reference (state_dict) layouts.  `saved` is pa_forward's tuple; its last
     entry is the module input (fp32 in SIMT mode, its bf16 copy in tensor-core mode)."""
     lib = _lib.load()
@@ -765,8 +788,8 @@ def pa_backward(dout, xshape, temperature, Wd, Wx_shape, Ws, bs, Wq, Wk, Wv, Wo,
     dx = torch.empty(B, N, C_, device=dev, dtype=torch.bfloat16) if dx_bf16 else torch.empty(B, N, C_, **f32)
     if tc:
         with _OnSide():
-            dWx = torch.empty(Wx_shape, **f32)
-            dWfx = torch.empty(Wx_shape, **f32)
+            dWx = _claim_grad(grad_dst[0], Wx_shape, **f32)
+            dWfx = _claim_grad(grad_dst[1], Wx_shape, **f32)
             gemm_tc_wgrad(xs, dXF16, B, Hg, Wg, C_, I2, taps=taps, scatter=(dWx, dWfx), I=I, tag="proj_wgrad")
         if dx_bf16:
             gemm_tc(dXF16, Wd16, None, None, B, Hg, Wg, I2, C_, taps, 1, C16=dx, tag="proj_dgrad")
@@ -1239,6 +1262,7 @@ class AttnBlockFn(torch.autograd.Function):
         ctx.save_for_backward(fx, ln_w, mean, rstd, temperature_c, Wd, Ws, bs, Wq, Wk, Wv, Wo, *saved)
         ctx.Wd16 = Wd16
         ctx.cfg = (heads, grid, precision, tuple(Wx.shape), tuple(fx.shape))
+        ctx.grad_dst = (_grad_dst(Wx), _grad_dst(Wfx))
         return out
 
     @staticmethod
@@ -1251,7 +1275,7 @@ class AttnBlockFn(torch.autograd.Function):
         ln16 = bool(_lib.load().tbns_layernorm_bwd_supported16(fx.shape[-1]))
         dx1, g = pa_backward(dout, xshape, temperature, Wd, wshape, Ws.contiguous(), bs.contiguous(), Wq.contiguous(), Wk.contiguous(),
                              Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16, dout16=dout16,
-                             dbo=dsum, dx_bf16=ln16)
+                             dbo=dsum, dx_bf16=ln16, grad_dst=ctx.grad_dst)
         if dx1.dtype == torch.bfloat16:
             dfx, dfx16, dlw, dlb, dfsum = layernorm_bwd16(dx1, fx, mean, rstd, ln_w, dres=dout)
         else:
@@ -1281,6 +1305,7 @@ class LnMlpFn(torch.autograd.Function):
         use_tc = (precision == TBNS_PREC_BF16 and Cout == C_ and tc_supported(C_, R, 1) and tc_supported(R, Cout, 1)
                   and wgrad_supported(Cout, R, 1) and wgrad_supported(R, C_, 1))
         got = _take_ln(fx, gamma, beta, eps) if use_tc else None
+        W1_param, W2_param = W1, W2
         gamma, beta, W1, b1, W2, b2 = (t.contiguous() for t in (gamma, beta, W1, b1, W2, b2))
         if got is not None:      # ln_2 was computed in the epilogue of the attention's output GEMM
             x2, (x2_16, mean, rstd) = None, got
@@ -1301,6 +1326,7 @@ class LnMlpFn(torch.autograd.Function):
                 _attach_ln(out, ln_out, nln_w, nln_b, nln_eps)
             ctx.save_for_backward(fx, gamma, W1, W2, x2_16, mean, rstd, pre, hid16)
             ctx.precision = precision
+            ctx.grad_dst = (_grad_dst(W1_param), _grad_dst(W2_param))
             return out
         hid = torch.empty(M, R, device=fx.device, dtype=torch.float32)
         gemm(M=M, N=R, K=C_, A=x2, lda=C_, a_kind=0, B=W1, ldb=C_, b_kind=0, C=hid, ldc=R, bias=b1, act=1, aux_out=pre, ldaux=R,
@@ -1326,18 +1352,19 @@ class LnMlpFn(torch.autograd.Function):
         dout16, db2 = _take_grad16(dout)
         if db2 is None:
             db2 = colsum(dout, M, Cout)
-        dW2 = torch.empty(Cout, R, **f32)
+        gdst = getattr(ctx, "grad_dst", (None, None))
         if hid.dtype == torch.bfloat16:   # tensor-core mode
             if dout16 is None:
                 dout16 = cast_bf16(dout)
             W2t16, W1t16 = weight_bf16(W2, transpose=True), weight_bf16(W1, transpose=True)
             with _OnSide():
+                dW2 = _claim_grad(gdst[1], (Cout, R), **f32)
                 gemm_tc_wgrad(dout16, hid, 1, 1, M, Cout, R, C=dW2, tag="mlp_dW2")
             dpre16 = torch.empty(M, R, device=fx.device, dtype=torch.bfloat16)
             gemm_tc(dout16, W2t16, None, None, 1, 1, M, Cout, R, act=4, aux_in=pre, aux_bf16=1, C16=dpre16, tag="mlp_dpre")
             with _OnSide():
                 db1 = colsum_bf16(dpre16, M, R)
-                dW1 = torch.empty(R, C_, **f32)
+                dW1 = _claim_grad(gdst[0], (R, C_), **f32)
                 gemm_tc_wgrad(dpre16, x2, 1, 1, M, R, C_, C=dW1, tag="mlp_dW1")
             if _lib.load().tbns_layernorm_bwd_supported16(C_):
                 dx2 = torch.empty(M, C_, device=fx.device, dtype=torch.bfloat16)   # feeds the LayerNorm backward only: bf16
@@ -1351,6 +1378,7 @@ class LnMlpFn(torch.autograd.Function):
             dfx = dfx.view_as(fx)
             _stash_grad16(dfx, dfx16, dfsum)   # the attention stage's backward consumes dfx next: bf16 copy + to_out bias gradient
             return dfx, dg, db, dW1, db1, dW2, db2, None, None, None, None, None
+        dW2 = torch.empty(Cout, R, **f32)
         gemm(M=Cout, N=R, K=M, A=dout, lda=Cout, a_kind=1, B=hid, ldb=R, b_kind=1, C=dW2, ldc=R, precision=precision,
              split_k=_split_k(Cout, R, M))
         dpre = torch.empty(M, R, **f32)

@@ -58,8 +58,10 @@ class FlatGradients:
     def begin(self):
         """start of a backward pass: detach the views so autograd hands each parameter its gradient tensor as is
         (no `grad += new` kernel per parameter, no zero fill of the flat buffer)."""
-        for p in self.params:
+        token = object()   # identifies this backward pass: a view is handed out at most once per pass (ops._claim_grad)
+        for p, v in zip(self.params, self.views):
             p.grad = None
+            p._tbns_grad_dst = (v, token)
 
     def finish(self):
         """end of a backward pass: gather the per-parameter gradients into the flat buffer with one multi-tensor copy and
@@ -75,6 +77,7 @@ class FlatGradients:
             torch._foreach_copy_(dst, src)
         for p, v in zip(self.params, self.views):
             p.grad = v
+            p._tbns_grad_dst = None
 
     def all_reduce(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not _NO_ALLREDUCE:
