@@ -125,3 +125,29 @@ def test_flat_gradients_gather_equals_accumulate():
         off += g.padded(p.numel())
     assert off == g.flat.numel()
     assert float(model.unused.grad.abs().sum()) == 0.0
+
+
+def test_flat_gradients_arm_destinations_once_per_pass():
+    """host logic of the direct gradient destinations (ops._claim_grad): begin() arms every parameter with (view, token), a
+    view is handed out once per backward pass and only for a matching shape, finish() disarms; a second begin() re-arms."""
+    from transformerbasednavierstokesolver_b200 import ops
+    model = TinyModel(3)
+    g = train.FlatGradients(model.parameters())
+    p = g.params[0]
+    g.begin()
+    dst = ops._grad_dst(p)
+    assert dst is not None and dst[0] is g.views[0]
+    a = ops._claim_grad(dst, p.shape)
+    assert a.data_ptr() == g.views[0].data_ptr() and a is not g.views[0]          # alias: a fresh tensor object on the view
+    b = ops._claim_grad(dst, p.shape)
+    assert b.data_ptr() != g.views[0].data_ptr()                                  # second user of the parameter in this pass
+    c = ops._claim_grad(ops._grad_dst(g.params[1]), (7, 7))
+    assert c.shape == (7, 7)                                                      # shape mismatch -> plain allocation
+    assert ops._claim_grad(None, (2, 2)).shape == (2, 2)
+    for q in g.params:
+        q.grad = torch.zeros_like(q)
+    g.finish()
+    assert all(getattr(q, "_tbns_grad_dst", None) is None for q in g.params)
+    g.begin()
+    assert ops._claim_grad(ops._grad_dst(p), p.shape).data_ptr() == g.views[0].data_ptr()   # new pass, new token
+    g.finish()
