@@ -142,6 +142,9 @@ int tbns_layernorm_bwd(const float* dy, const float* x, const float* mean, const
 /* same for a bf16 incoming gradient dy16 (written bf16-only by the data-gradient GEMM in bf16 mode); C in {128, 256, 512};
  * sums [3][C] = dgamma | dbeta | column sums of dx */
 int tbns_layernorm_bwd_supported16(int C);
+/* sums may be NULL: the per-CTA partials stay in ws as [tbns_layernorm_bwd_ctas(rows)][3*C] for the caller to reduce
+ * (tbns_reduce_rows), e.g. on another stream */
+int tbns_layernorm_bwd_ctas(int rows);
 int tbns_layernorm_bwd16(const void* dy16, const float* x, const float* mean, const float* rstd, const float* gamma,
                          const float* dres, float* dx, void* dx16, float* sums, float* ws, int rows, int C, void* stream);
 

@@ -87,6 +87,7 @@ _SIGS = {
     "tbns_layernorm_bwd": (_i, [_fp] * 12 + [_i, _i, _fp]),
     "tbns_layernorm_bwd_supported16": (_i, [_i]),
     "tbns_layernorm_bwd16": (_i, [_fp] * 10 + [_i, _i, _fp]),
+    "tbns_layernorm_bwd_ctas": (_i, [_i]),
     "tbns_ln_linear1_supported": (_i, [_i]),
     "tbns_ln_linear1_fwd": (_i, [_fp] * 8 + [_i, _i, C.c_float, _fp]),
     "tbns_ln_linear1_fwd_strided": (_i, [_fp] * 6 + [_ll] + [_fp] * 2 + [_i, _i, C.c_float, _fp]),

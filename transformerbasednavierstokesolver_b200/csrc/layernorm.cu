@@ -446,12 +446,17 @@ extern "C" int tbns_reduce_rows(const float* in, float* out, int rows, long long
   return TBNS_OK;
 }
 
+extern "C" int tbns_layernorm_bwd_ctas(int rows) {
+  int ctas = cdiv(rows, LN_WARPS * 2);
+  return ctas > LN_BWD_CTAS ? LN_BWD_CTAS : ctas;
+}
+
 extern "C" int tbns_layernorm_bwd_supported16(int C) { return (C == 128 || C == 256 || C == 512) ? 1 : 0; }
 
 extern "C" int tbns_layernorm_bwd16(const void* dy16, const float* x, const float* mean, const float* rstd, const float* gamma,
                                     const float* dres, float* dx, void* dx16, float* sums /* [3][C] */, float* ws, int rows, int C,
                                     void* stream) {
-  TBNS_REQUIRE(dy16 && x && mean && rstd && gamma && dx && sums && ws, "tbns_layernorm_bwd16: null pointer");
+  TBNS_REQUIRE(dy16 && x && mean && rstd && gamma && dx && ws, "tbns_layernorm_bwd16: null pointer");
   TBNS_REQUIRE(rows > 0 && tbns_layernorm_bwd_supported16(C), "tbns_layernorm_bwd16: C=%d unsupported (128, 256, 512)", C);
   TBNS_REQUIRE(((reinterpret_cast<uintptr_t>(dy16) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
                  reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(dx16)) & 15) == 0,
@@ -465,7 +470,9 @@ extern "C" int tbns_layernorm_bwd16(const void* dy16, const float* x, const floa
   else if (C == 256) TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<2, false, true>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr));
   else TBNS_CUDA(launch_pdl(layernorm_bwd_reg_kernel<4, false, true>, dim3(ctas), dim3(LN_WARPS * 32), 0, st, dy, x, mean, rstd, gamma, dres, dx, o16, ws, rows, nullptr));
   TBNS_LAUNCH_CHECK();
-  TBNS_CUDA(launch_pdl(reduce_rows_par_kernel, dim3(cdiv(3 * C, 32)), dim3(1024), 0, st, ws, sums, ctas, 3 * C, 3LL * C));
+  // sums == nullptr: the caller reduces the per-CTA partials ws[tbns_layernorm_bwd_ctas(rows)][3*C] itself (tbns_reduce_rows on
+  // another stream: the column sums are parameter gradients, off the critical path of the data gradient)
+  if (sums) TBNS_CUDA(launch_pdl(reduce_rows_par_kernel, dim3(cdiv(3 * C, 32)), dim3(1024), 0, st, ws, sums, ctas, 3 * C, 3LL * C));
   TBNS_LAUNCH_CHECK();
   return TBNS_OK;
 }

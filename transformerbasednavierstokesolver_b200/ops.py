@@ -371,20 +371,24 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5, want32: bool 
 
 
 def layernorm_bwd16(dy16, x, mean, rstd, gamma, dres=None, want16: bool = True):
-    """layernorm_bwd for a bf16 incoming gradient -> (dx, dx16 | None, dgamma, dbeta, colsum(dx))"""
+    """layernorm_bwd for a bf16 incoming gradient -> (dx, dx16 | None, dgamma, dbeta, colsum(dx), keep-alive)"""
     _chk(x, mean, rstd, gamma, dres)
     lib = _lib.load()
     C_ = x.shape[-1]
     rows = x.numel() // C_
     dx = torch.empty_like(x)
     dx16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want16 else None
-    out3 = torch.empty(3, C_, device=x.device, dtype=torch.float32)
     ws = torch.empty(lib.tbns_layernorm_bwd_ws_floats(C_), device=x.device, dtype=torch.float32)
     with _Timed("layernorm_bwd"):
-        check(lib.tbns_layernorm_bwd16(_p(dy16), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), _p(out3), _p(ws),
+        check(lib.tbns_layernorm_bwd16(_p(dy16), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx16), None, _p(ws),
                                        rows, C_, _stream()), "tbns_layernorm_bwd16")
-    _count(2)
-    return dx, dx16, out3[0], out3[1], out3[2]
+    _count(1)
+    # dgamma | dbeta | colsum(dx) are parameter gradients: their fixed-order reduction over the per-CTA partials runs on the
+    # side stream (the callers join before they return; `ws` must stay referenced until then - it is returned for that)
+    ctas = lib.tbns_layernorm_bwd_ctas(rows)
+    with _OnSide():
+        out3 = reduce_rows(ws, ctas, 3 * C_).view(3, C_)
+    return dx, dx16, out3[0], out3[1], out3[2], ws
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, want16: bool = False, want_sum: bool = False):
@@ -1277,7 +1281,7 @@ class AttnBlockFn(torch.autograd.Function):
                              Wv.contiguous(), Wo.contiguous(), tuple(saved), heads, grid, precision, ctx.Wd16, dout16=dout16,
                              dbo=dsum, dx_bf16=ln16, grad_dst=ctx.grad_dst)
         if dx1.dtype == torch.bfloat16:
-            dfx, dfx16, dlw, dlb, dfsum = layernorm_bwd16(dx1, fx, mean, rstd, ln_w, dres=dout)
+            dfx, dfx16, dlw, dlb, dfsum, _ln_keep = layernorm_bwd16(dx1, fx, mean, rstd, ln_w, dres=dout)   # noqa: F841 (alive until the join)
         else:
             dfx, dfx16, dlw, dlb, dfsum = layernorm_bwd(dx1, fx, mean, rstd, ln_w, dres=dout, want16=precision == TBNS_PREC_BF16,
                                                         want_sum=True)
@@ -1369,7 +1373,7 @@ class LnMlpFn(torch.autograd.Function):
             if _lib.load().tbns_layernorm_bwd_supported16(C_):
                 dx2 = torch.empty(M, C_, device=fx.device, dtype=torch.bfloat16)   # feeds the LayerNorm backward only: bf16
                 gemm_tc(dpre16, W1t16, None, None, 1, 1, M, R, C_, C16=dx2, tag="mlp_dx2")
-                dfx, dfx16, dg, db, dfsum = layernorm_bwd16(dx2, fx, mean, rstd, gamma, dres=dout)
+                dfx, dfx16, dg, db, dfsum, _ln_keep = layernorm_bwd16(dx2, fx, mean, rstd, gamma, dres=dout)   # noqa: F841 (alive until the join)
             else:
                 dx2 = torch.empty(M, C_, **f32)
                 gemm_tc(dpre16, W1t16, dx2, None, 1, 1, M, R, C_, tag="mlp_dx2")
