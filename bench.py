@@ -522,7 +522,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "unrolled", "rollout_cfg5"])
     ap.add_argument("--look-ahead", type=int, default=2, help="--workload unrolled: chained model calls per window (1, 2, 4, 8, 10)")
