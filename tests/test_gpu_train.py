@@ -211,3 +211,28 @@ def test_direct_gradient_destinations_equal_gathered_gradients():
             assert p.grad.data_ptr() == g.views[[id(q) for q in g.params].index(id(p))].data_ptr()
             assert getattr(p, "_tbns_grad_dst", None) is None      # disarmed after the pass
 
+
+
+@pytest.mark.parametrize("n", [1003, 4096, 7])
+def test_adamw_flat_kernel_matches_formula(n):
+    """tbns_adamw_flat through the C ABI on raw buffers (vector body + scalar tail) against the AdamW formula in fp64"""
+    from transformerbasednavierstokesolver_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(n)
+    p, gr, m, v = (torch.randn(n, generator=g) for _ in range(4))
+    v = v.abs()
+    lr, b1, b2, eps, wd, t = 3e-3, 0.87, 0.995, 1e-8, 1e-2, 5
+    hp = torch.tensor([lr, b1, b2, eps, wd, 1 - b1 ** t, 1 - b2 ** t, 0.0])
+    pd, gd, md, vd = (x.double() for x in (p, gr, m, v))
+    pd = pd * (1 - lr * wd)
+    md = b1 * md + (1 - b1) * gd
+    vd = b2 * vd + (1 - b2) * gd * gd
+    pd = pd - (lr / (1 - b1 ** t)) * md / (vd.sqrt() / (1 - b2 ** t) ** 0.5 + eps)
+    pc, gc, mc, vc, hc = (x.to(dev) for x in (p, gr, m, v, hp))
+    _lib.check(lib.tbns_adamw_flat(pc.data_ptr(), gc.data_ptr(), mc.data_ptr(), vc.data_ptr(), hc.data_ptr(), n,
+                                   torch.cuda.current_stream().cuda_stream), "tbns_adamw_flat")
+    torch.cuda.synchronize()
+    assert torch.allclose(pc.cpu().double(), pd, rtol=2e-6, atol=1e-7)
+    assert torch.allclose(mc.cpu().double(), md, rtol=2e-6, atol=1e-7)
+    assert torch.allclose(vc.cpu().double(), vd, rtol=2e-6, atol=1e-7)
