@@ -542,6 +542,8 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
+        # a CPU step is 3+ s: two untimed steps are enough to page everything in (the line reports the W actually used)
+        args.warmup = min(args.warmup, 2)
         run_reference(args)
     elif args.workload == "rollout_cfg5":
         run_rollout_cfg5(args)
